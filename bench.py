@@ -1,0 +1,398 @@
+#!/usr/bin/env python3
+"""bench.py -- polymul/s of the batched NTT polynomial multiplier (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl reference]
+
+One "step" = one pass of the hot path (fused NTT -> pointwise -> INTT kernel) over one batch
+of synthetic polynomial pairs.  Default workload = BASELINE.json configs[1]: batch 2^16 at
+the reference default (n=256, q=12289).  With N>1 (torchrun, one process per GPU) every rank
+runs the same per-GPU batch on its own rows -- no data-path collective (the products share
+nothing), torch.distributed only provides the barrier and the max-over-ranks of the time.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` is the same
+metric through the host-buffer C-ABI call (pinned host memory, H2D and D2H inside the timed
+region); `roofline` is the fused kernel against the measured HBM peak; `int_roofline` is the
+same kernel against the integer-multiply issue rate measured live; `cpu_baseline` is the
+reference's own C code on this box's host cores (N=1 only).
+
+`--impl reference` times the reference's CPU implementation instead (oracle/_ref compiled
+from the unmodified sources; the oracle port for (n,q) the reference cannot run).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import multiprocessing as mp
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "ntt-based-polynomial-multiplier-fpga_b200"
+
+WORKLOADS = {
+    # name: (n, q, psi, log2 batch, description)
+    "c2": (256, 12289, 1002, 16, "BASELINE configs[1]: batch 2^16 polymuls at the reference default (n=256,q=12289)"),
+    "c3": (256, 7681, 0, 20, "BASELINE configs[2] (Kyber-like): n=256 q=7681 (3329 has no 512-th root), batch 2^20"),
+    "c4": (1024, 12289, 0, 18, "BASELINE configs[3] (Falcon/NewHope-like): n=1024 q=12289 batch 2^18"),
+    "c5": (65536, 2013265921, 0, 10, "BASELINE configs[4]: n=2^16 q=2013265921 batch 2^10, multi-pass"),
+}
+SEED = 0x4E545442323030
+L2_BYTES = 126 * 1000 * 1000
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------
+# clocks: NVML sampling thread covering the timed region
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        self._timed = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((self._timed.is_set(), mhz))
+                if self._timed.is_set():
+                    for bit, name in self.REASONS.items():
+                        if r & bit and name != "gpu_idle":
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.ok:
+            self.t.start()
+
+    def timed(self, on: bool):
+        (self._timed.set if on else self._timed.clear)()
+
+    def stop(self):
+        self._stop.set()
+        if self.ok:
+            self.t.join(timeout=2)
+        timed = [m for t, m in self.samples if t] or [m for _, m in self.samples]
+        return {"sm_mhz": statistics.median(timed) if timed else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples_in_timed_region": sum(1 for t, _ in self.samples if t)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU side: the reference's own C code on the host cores
+# --------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_worker_init(n, q, psi, use_ref, variant):
+    from oracle import loader
+    _W["variant"] = variant
+    _W["n"], _W["q"], _W["psi"] = n, q, psi
+    if use_ref:
+        _W["ref"] = loader.Reference()
+    else:
+        _W["orc"] = loader.Oracle()
+
+
+def _cpu_worker_loop(args):
+    """Timed loop (cpu_baseline leg): seconds of work on a private slice, returns (rate, calls)."""
+    seed, rows, seconds = args
+    from oracle import loader
+    O = loader.Oracle()
+    n, q = _W["n"], _W["q"]
+    a, b = O.random((rows, n), q, seed), O.random((rows, n), q, seed + 1)
+    if "ref" in _W:
+        return _W["ref"].bench_loop(a, b, _W["variant"], seconds)
+    return _W["orc"].bench_loop(n, q, a, b, _W["variant"], seconds, _W["psi"])
+
+
+def _cpu_worker_step(args):
+    """One slice of one step (--impl reference leg)."""
+    seed, rows = args
+    key = ("data", seed, rows)
+    from oracle import loader
+    if key not in _W:
+        O = loader.Oracle()
+        _W[key] = (O.random((rows, _W["n"]), _W["q"], seed), O.random((rows, _W["n"]), _W["q"], seed + 1))
+    a, b = _W[key]
+    t0 = time.perf_counter()
+    if "ref" in _W:
+        c = _W["ref"].product(a, b, _W["variant"])
+    else:
+        c = _W["orc"].product(_W["n"], _W["q"], a, b, _W["variant"], _W["psi"])
+    return time.perf_counter() - t0, int(c[0, 0])
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_pool(n, q, psi, cores):
+    from oracle import loader
+    use_ref = (n, q) == (256, 12289) and loader.reference_available()
+    variant = loader.REF_RED_CT if use_ref else loader.PRODUCT_MERGED
+    ctx = mp.get_context("fork")
+    pool = ctx.Pool(cores, initializer=_cpu_worker_init, initargs=(n, q, psi, use_ref, variant))
+    kind = "reference" if use_ref else "port"
+    what = ("ntt_red256_product1 (optimized CT, Longa-Naehrig) from oracle/_ref, gcc -O3, unmodified sources"
+            if use_ref else "oracle port of the merged CT-fwd/GS-inv pipeline (ntt_oracle.c)")
+    return pool, kind, what
+
+
+def cpu_baseline(n, q, psi, seconds=4.0):
+    cores = host_cores()
+    pool, kind, what = cpu_pool(n, q, psi, cores)
+    rows = max(1, min(4096, (1 << 20) // n))
+    try:
+        res = pool.map(_cpu_worker_loop, [(SEED + 17 * i, rows, seconds) for i in range(cores)])
+    finally:
+        pool.close()
+        pool.join()
+    total = sum(r for r, _ in res)
+    return {"value": total, "unit": "polymul/s", "cores": cores, "kind": kind,
+            "per_core": total / cores,
+            "sample": f"{what}; one process per core, each looping over a private slice of {rows} random "
+                      f"polymuls for {seconds:.0f} s (operand restore excluded, as time_testing256.c:175-185)"}
+
+
+def run_reference_arm(args, n, q, psi, logb, desc):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = host_cores()
+    pool, kind, what = cpu_pool(n, q, psi, cores)
+    full = 1 << logb
+    # bounded sample per step: ~0.25 s of all-core work at ~1e5 polymul/s/core (n=256)
+    est_rate = cores * 1.0e5 * (256 * 8) / (n * max(1, n.bit_length() - 1))
+    sample = int(min(full, max(cores, est_rate * 0.25)))
+    per = max(1, sample // cores)
+    sample = per * cores
+    jobs = [(SEED + 31 * i, per) for i in range(cores)]
+    try:
+        for _ in range(max(1, args.warmup)):
+            pool.map(_cpu_worker_step, jobs)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_cpu_worker_step, jobs)
+        dt = time.perf_counter() - t0
+    finally:
+        pool.close()
+        pool.join()
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "polymul/s", "value": value, "unit": "polymul/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": desc, "n": n, "q": q, "batch_per_step": sample,
+                   "note": "CPU arm: host cores only, no GPU, no host<->device copies"},
+        "cpu_baseline": {"value": value, "unit": "polymul/s", "cores": cores, "kind": kind,
+                         "sample": f"{what}; each step = {sample} of the workload's {full} polymuls "
+                                   f"split over {cores} processes (one per core)"},
+        "e2e": {"value": value, "unit": "polymul/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
+    args = ap.parse_args()
+    n, q, psi, logb, desc = WORKLOADS[args.workload]
+    batch = 1 << logb
+
+    if args.impl == "reference":
+        return run_reference_arm(args, n, q, psi, logb, desc)
+
+    import torch
+    mod = importlib.import_module(PKG)
+    sh = importlib.import_module(PKG + ".sharding")
+    rank, world, local = sh.env_rank_world()
+    if not torch.cuda.is_available() or mod.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    mod.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        sh.init_distributed("nccl")
+    warmup = max(3, args.warmup)
+
+    plan = mod.Plan(n, q, psi)
+    row_bytes = n * 4
+    # distinct buffer sets so that successive steps never find their inputs in the 126 MB L2
+    sets = max(2, -(-3 * L2_BYTES // (3 * batch * row_bytes)) + 1)
+    g = torch.Generator(device=dev).manual_seed(SEED % (2**31) + rank)
+    bufs = []
+    for _ in range(sets):
+        a = torch.randint(0, q, (batch, n), dtype=torch.int32, device=dev, generator=g)
+        b = torch.randint(0, q, (batch, n), dtype=torch.int32, device=dev, generator=g)
+        c = torch.empty_like(a)
+        bufs.append((a, b, c))
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(i):
+        a, b, c = bufs[i % sets]
+        plan.polymul_dev(c.data_ptr(), a.data_ptr(), b.data_ptr(), batch, stream)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for i in range(warmup):
+        step(i)
+    launches_per_step = mod.last_launch_count()
+    torch.cuda.synchronize()
+    sh.barrier(local)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.timed(True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    sampler.timed(False)
+    sh.barrier(local)
+    ms_local = e0.elapsed_time(e1)
+    ms = sh.max_over_ranks(ms_local, dev)
+    clocks = sampler.stop()
+    value = world * batch * args.steps / (ms * 1e-3)
+
+    # per-launch duration of the dominant kernel, CUDA events on the launching stream
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 50))]
+    for i, (s, e) in enumerate(evs):
+        s.record()
+        step(i)
+        e.record()
+    torch.cuda.synchronize()
+    launch_ms = statistics.mean(s.elapsed_time(e) for s, e in evs)
+    # a back-to-back stream hides launch gaps: the K-step region gives the better per-launch figure
+    per_launch_ms = min(launch_ms, ms_local / args.steps) / max(1, launches_per_step)
+
+    # parity spot check of what was just timed (never skip work silently)
+    from oracle import loader
+    O = loader.Oracle()
+    a, b, c = bufs[(args.steps - 1) % sets]
+    idx = torch.tensor([0, 1, batch // 2, batch - 1], device=dev)
+    want = O.product(n, q, a[idx].cpu().numpy(), b[idx].cpu().numpy(), loader.PRODUCT_MERGED)
+    parity_ok = bool((c[idx].cpu().numpy() == want).all())
+
+    # e2e: host buffers (pinned) through nttb200_polymul_batch: H2D + kernel + D2H per step
+    e2e_steps = args.e2e_steps or min(args.steps, 20)
+    ha, hb, hc = mod.host_alloc((batch, n)), mod.host_alloc((batch, n)), mod.host_alloc((batch, n))
+    ha.array[:] = bufs[0][0].cpu().numpy()
+    hb.array[:] = bufs[0][1].cpu().numpy()
+    for _ in range(3):
+        plan.polymul_host_ptr(hc.ptr, ha.ptr, hb.ptr, batch)
+    sh.barrier(local)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plan.polymul_host_ptr(hc.ptr, ha.ptr, hb.ptr, batch)
+    e2e_s = sh.max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_ok = bool((hc.array[:2] == O.product(n, q, ha.array[:2], hb.array[:2], loader.PRODUCT_MERGED)).all())
+    e2e_value = world * batch * e2e_steps / e2e_s
+
+    peak_gbs, peak_src = measured_peaks()
+    alg_bytes = 12 * n * batch                      # read a, read b, write c (int32 API)
+    achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
+    logn = n.bit_length() - 1
+    modmuls = 3 * (n // 2) * logn + n               # M
+    imad_peak = mod.measure_int_peak(0)
+    imadhi_peak = mod.measure_int_peak(1)
+    bfly_peak = mod.measure_int_peak(3)
+    int_achieved = (batch / (per_launch_ms * 1e-3)) * 3 * modmuls
+
+    line = {
+        "metric": "polymul/s", "value": value, "unit": "polymul/s", "n_gpus": world,
+        "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic",
+        "config": {"workload": desc, "n": n, "q": q, "psi": plan.psi, "batch_per_gpu": batch,
+                   "plan": plan.describe(),
+                   "l2": f"inputs rotate over {sets} buffer sets ({sets * 3 * batch * row_bytes >> 20} MiB) "
+                         f"> 126 MB L2, so no step finds its operands cached",
+                   "parallelism": f"batch-sharded x{world}, no collective"},
+        "e2e": {"value": e2e_value, "unit": "polymul/s", "h2d_bytes_per_step": 2 * batch * row_bytes,
+                "d2h_bytes_per_step": batch * row_bytes, "steps": e2e_steps,
+                "api": "nttb200_polymul_batch (host buffers, pinned; 3-slot stream ring)", "parity_ok": e2e_ok},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                     "kernel": "polymul_small_kernel" if n <= 1024 else "large multi-pass",
+                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms},
+        "int_roofline": {"bound": "imad-issue", "achieved": int_achieved, "peak": imad_peak,
+                         "unit": "IMAD lane-ops/s", "frac": int_achieved / imad_peak if imad_peak else None,
+                         "imad_per_polymul": 3 * modmuls, "imad_hi_peak": imadhi_peak,
+                         "lazy_butterflies_per_s_peak": bfly_peak,
+                         "note": "3 IMAD-class issues per modmul (Shoup), M = 3(n/2)log2(n)+n modmuls; peak "
+                                 "measured live by nttb200_measure_int_peak"},
+        "parity_ok": parity_ok,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline(n, q, psi)
+        except Exception as ex:  # the baseline is a report, never a reason to lose the GPU line
+            line["cpu_baseline"] = {"value": None, "error": repr(ex)}
+    for h in (ha, hb, hc):
+        h.free()
+    plan.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0 if (parity_ok and e2e_ok) else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

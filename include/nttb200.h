@@ -1,0 +1,176 @@
+/*
+ * nttb200.h -- C ABI of libnttb200.so: batched NTT-based negacyclic polynomial
+ * multiplication  c = INTT(NTT(a) o NTT(b))  in Z_q[x]/(x^n + 1)  on NVIDIA B200.
+ *
+ * Plain C, plain pointers and sizes; no CUDA or torch types in any signature (a
+ * CUDA stream crosses the boundary as `void *`).  This is the layer that replaces
+ * the reference's host<->FPGA transfer path
+ *   Multiplier_NTT_Based/Software_Hardware_Comunnicator/linux_app/NTT_PCIECommunicationv2.c:109-252
+ *   (mode 1/2: DMA polyA/polyB to the board, mode 3: GO, DMA polyC back)
+ * with CUDA streams and pinned buffers, and that the reference's product/NTT call
+ * surface (nttb200_legacy.h) is implemented on.
+ *
+ * Reference paths below are relative to
+ *   R/ = Multiplier_NTT_Based/NTT_Software/NTT_Software_Evaluations/NTT-256/
+ *
+ * Data layout everywhere: row-major int32_t [batch][n], one polynomial per row,
+ * coefficient i of polynomial r at r*n + i, values in [0, q)  (the reference's
+ * `int32_t a[256]`, R/NTT/ntt256.h:76-83, batched).
+ *
+ * There is NO CPU fallback: every entry point that computes fails with
+ * NTTB200_ECUDA when no CUDA device is usable.
+ */
+#ifndef NTTB200_H
+#define NTTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NTTB200_VERSION 100
+
+/* ---- error codes (0 = OK).  The reference functions are `void` and abort on
+ * violated preconditions (assert in R/NTT-RED/ntt_red.c:42,79,94); the nttb200_*
+ * functions return a code instead and keep a per-thread message. --------------- */
+enum {
+  NTTB200_OK = 0,
+  NTTB200_EPARAM = -1,   /* bad (n, q, psi), NULL pointer, unsupported size       */
+  NTTB200_ECUDA = -2,    /* CUDA runtime/driver error, or no device               */
+  NTTB200_ENOMEM = -3,   /* host or device allocation failed                      */
+  NTTB200_ERANGE = -4    /* an input coefficient outside [0, q) (checked on request) */
+};
+const char *nttb200_last_error(void);
+int nttb200_version(void);
+
+/* ---- devices ------------------------------------------------------------------ */
+int nttb200_device_count(void);          /* >= 0, or NTTB200_ECUDA                  */
+int nttb200_set_device(int device);      /* device for plans created by this thread */
+int nttb200_get_device(void);
+
+/* ---- plans: one (n, q, psi) parameter set, its twiddle tables on one GPU ------- */
+typedef struct nttb200_plan nttb200_plan;
+
+/* flags */
+#define NTTB200_PLAN_DEFAULT 0u
+#define NTTB200_PLAN_CYCLIC 1u /* psi-free surface: product mod x^n - 1 (needs n | q-1 only;
+                                  R/NTT/ntt256.h:28,37 + R/NTT/ntt.h:52).  `psi` is then read
+                                  as omega (0 = smallest primitive n-th root).            */
+
+/* n: power of two, 8 <= n <= 2^17.  q: odd prime < 2^31 with 2n | q-1 (n | q-1 when
+ * CYCLIC).  psi: primitive 2n-th root of unity mod q, or 0 for the smallest one -- the
+ * rule of Generator_Params/generate_params.C:25-44.  The reference's own tables use
+ * psi = 1002 for (256, 12289) (R/NTT/ntt256_tables.h:20); products do not depend on the
+ * choice, standalone transforms do. */
+int nttb200_plan_create(nttb200_plan **plan, uint32_t n, uint32_t q, uint32_t psi, uint32_t flags);
+void nttb200_plan_destroy(nttb200_plan *plan);
+uint32_t nttb200_plan_n(const nttb200_plan *plan);
+uint32_t nttb200_plan_q(const nttb200_plan *plan);
+uint32_t nttb200_plan_psi(const nttb200_plan *plan);
+int nttb200_plan_device(const nttb200_plan *plan);
+/* name of the kernel family / arithmetic class the plan dispatches to (for reports) */
+const char *nttb200_plan_describe(const nttb200_plan *plan);
+
+/* ---- products ------------------------------------------------------------------
+ * Replaces, batched:  ntt256_product1 / ntt256_product4 (R/NTT/ntt256.C:5-24) and
+ * ntt_red256_product1 / ntt_red256_product4 (R/NTT-RED/ntt_red256.C:5-52); all four
+ * return the same canonical c, so one entry point serves them.  Unlike the reference
+ * (R/NTT/ntt256.h:80 "arrays a and b are modified") a and b are left untouched;
+ * c must not overlap a or b.
+ *
+ * Host buffers: pageable or pinned (nttb200_host_alloc); the call stages through
+ * pinned memory, overlaps H2D / kernel / D2H across an internal stream ring and
+ * returns when c is complete. */
+int nttb200_polymul_batch(nttb200_plan *plan, int32_t *c, const int32_t *a, const int32_t *b,
+                          size_t batch);
+/* Device-resident buffers (the timed path: no PCIe in the loop).  Asynchronous on
+ * `stream` (a cudaStream_t passed as void*, NULL = the legacy default stream). */
+int nttb200_polymul_batch_dev(nttb200_plan *plan, int32_t *c_dev, const int32_t *a_dev,
+                              const int32_t *b_dev, size_t batch, void *stream);
+
+/* ---- standalone transforms ("the NTT call surface") ---------------------------
+ * In place on [batch][n].  Outputs are canonical [0, q) and bit-identical to the
+ * reference function of the same dataflow run with the same table.             */
+enum nttb200_transform {
+  /* forward, standard order in -> bit-reversed order out */
+  NTTB200_NTT_STD2REV = 0,      /* ntt_ct_std2rev(omega_powers_rev) == ntt_gs_std2rev(omega_powers)
+                                   R/NTT/ntt.C:295-329, 467-493                             */
+  NTTB200_MULNTT_STD2REV = 1,   /* mulntt_ct_std2rev(mixed_powers_rev): NTT of a[i]*psi^i
+                                   R/NTT/ntt.C:342-371                                      */
+  /* inverse (UNSCALED, like the reference: intt(ntt(a)) = n*a, R/NTT/ntt256.h:16-17),
+   * bit-reversed order in -> standard order out */
+  NTTB200_INTT_REV2STD = 2,     /* ntt_gs_rev2std(inv_omega_powers_rev) == ntt_ct_rev2std(inv_omega_powers)
+                                   R/NTT/ntt.C:387-416, 216-243                             */
+  NTTB200_INTTMUL_REV2STD = 3,  /* nttmul_gs_rev2std(inv_mixed_powers_rev): result[i]*psi^-i
+                                   R/NTT/ntt.C:428-451                                      */
+  /* same as 2/3 with the n^-1 scaling folded in (what the products use) */
+  NTTB200_INTT_REV2STD_SCALED = 4,
+  NTTB200_INTTMUL_REV2STD_SCALED = 5,
+  /* forward with the INVERSE root, standard in -> bit-reversed out, and inverse-root
+   * twins used by intt256_ct_std2rev / intt256_gs_std2rev (R/NTT/ntt256.h:45-51) */
+  NTTB200_INTT_STD2REV = 6,
+  /* forward root, bit-reversed in -> standard out: ntt256_ct_rev2std / ntt256_gs_rev2std
+   * (R/NTT/ntt256.h:20-26) */
+  NTTB200_NTT_REV2STD = 7
+};
+int nttb200_ntt_batch(nttb200_plan *plan, int transform, int32_t *a, size_t batch);
+int nttb200_ntt_batch_dev(nttb200_plan *plan, int transform, int32_t *a_dev, size_t batch,
+                          void *stream);
+
+/* Table-driven transforms: the exact dataflow of the reference function run with the
+ * CALLER's table `p` (n entries, layout p[t+j] of R/NTT/ntt256_tables.C) -- what the
+ * legacy drop-ins in nttb200_legacy.h are built on.  `dataflow`: */
+enum nttb200_dataflow {
+  NTTB200_DF_CT_STD2REV = 0,    /* R/NTT/ntt.C:295-371  (ntt_ct_std2rev, mulntt_ct_std2rev)   */
+  NTTB200_DF_GS_REV2STD = 1,    /* R/NTT/ntt.C:387-451  (ntt_gs_rev2std, nttmul_gs_rev2std)   */
+  NTTB200_DF_CT_REV2STD = 2,    /* R/NTT/ntt.C:216-278  (ntt_ct_rev2std, mulntt_ct_rev2std)   */
+  NTTB200_DF_GS_STD2REV = 3     /* R/NTT/ntt.C:467-525  (ntt_gs_std2rev, nttmul_gs_std2rev)   */
+};
+int nttb200_ntt_table_batch(uint32_t n, uint32_t q, int dataflow, const uint32_t *p, int32_t *a,
+                            size_t batch);
+
+/* ---- elementwise surface (R/NTT/ntt.C:119-153), batched, host buffers ----------- */
+int nttb200_mul_array_batch(nttb200_plan *plan, int32_t *c, const int32_t *a, const int32_t *b,
+                            size_t batch);                       /* c[i] = a[i]*b[i] mod q   */
+int nttb200_scalar_mul_array_batch(nttb200_plan *plan, int32_t *a, int32_t s, size_t batch);
+
+/* ---- host-side tables, reference layout (R/NTT/ntt256_tables.C) ---- */
+enum nttb200_table {
+  NTTB200_PSI_POWERS = 0, NTTB200_INV_PSI_POWERS, NTTB200_SCALED_INV_PSI_POWERS,
+  NTTB200_OMEGA_POWERS, NTTB200_OMEGA_POWERS_REV, NTTB200_INV_OMEGA_POWERS,
+  NTTB200_INV_OMEGA_POWERS_REV, NTTB200_MIXED_POWERS, NTTB200_MIXED_POWERS_REV,
+  NTTB200_INV_MIXED_POWERS, NTTB200_INV_MIXED_POWERS_REV, NTTB200_INV_PSI_POWERS_REV,
+  NTTB200_TABLE_COUNT
+};
+/* fills out[0..n) */
+int nttb200_make_table(int kind, uint32_t n, uint32_t q, uint32_t psi, uint32_t *out);
+uint32_t nttb200_find_psi(uint32_t n, uint32_t q);     /* smallest primitive 2n-th root, 0 if none */
+uint32_t nttb200_find_omega(uint32_t n, uint32_t q);   /* smallest primitive n-th root, 0 if none  */
+int nttb200_is_prime(uint32_t q);
+
+/* ---- pinned host buffers (replace the malloc'd DMA buffers of
+ * NTT_PCIECommunicationv2.c:120-131) ------------------------------------------- */
+void *nttb200_host_alloc(size_t bytes);
+void nttb200_host_free(void *p);
+/* device buffers, for callers that keep operands resident between calls */
+void *nttb200_dev_alloc(size_t bytes);
+void nttb200_dev_free(void *p);
+int nttb200_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes, void *stream);
+int nttb200_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes, void *stream);
+int nttb200_stream_sync(void *stream);
+
+/* ---- measurement helpers (used by bench.py; device-side, no host data) ---------- */
+/* runs `iters` dependent IMAD / IMAD.HI / IADD3 chains on every SM and returns the
+ * measured chip-wide rate in lane-ops per second (the INT32-pipe roofline
+ * denominator).  which: 0 = IMAD (mad.lo), 1 = IMAD.HI (mul.hi),
+ * 2 = IADD3/LOP3, 3 = the Shoup butterfly mix (3 IMAD + 2 ALU). */
+int nttb200_measure_int_peak(int which, double *lane_ops_per_s);
+/* number of kernels the last nttb200_polymul_batch* / ntt_batch* call launched */
+int nttb200_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTTB200_H */

@@ -1,0 +1,57 @@
+/*
+ * nttb200_legacy.h -- the reference's own C call surface, exported by libnttb200.so so
+ * that a program written against NTT_Software links against the GPU library unchanged
+ * (same names, same argument meaning; q = 12289 is hard-wired in the reference,
+ * R/NTT/ntt.C:18, R/NTT-RED/ntt_red.c:24).
+ *
+ * R/ = Multiplier_NTT_Based/NTT_Software/NTT_Software_Evaluations/NTT-256/
+ *
+ * Error behaviour: the reference functions are `void`; violated preconditions abort()
+ * through assert (R/NTT-RED/ntt_red.c:42).  The drop-ins keep `void` and likewise
+ * abort() -- after printing nttb200_last_error() to stderr -- when the GPU call fails
+ * (including "no CUDA device": there is no CPU fallback).
+ *
+ * Each call moves ONE polynomial over PCIe and back; that is the reference's calling
+ * convention, not the fast path.  Batch work belongs on nttb200_polymul_batch().
+ */
+#ifndef NTTB200_LEGACY_H
+#define NTTB200_LEGACY_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- products: c = a*b mod (x^256+1, 12289), inputs and result in [0, 12289) ------- */
+void ntt256_product1(int32_t *c, int32_t *a, int32_t *b);      /* R/NTT/ntt256.h:85, ntt256.C:5-13  */
+void ntt256_product4(int32_t *c, int32_t *a, int32_t *b);      /* R/NTT/ntt256.h:86, ntt256.C:16-24 */
+void ntt_red256_product1(int32_t *c, int32_t *a, int32_t *b);  /* R/NTT-RED/ntt_red256.h:87, ntt_red256.C:5-27  */
+void ntt_red256_product4(int32_t *c, int32_t *a, int32_t *b);  /* R/NTT-RED/ntt_red256.h:90, ntt_red256.C:30-52 */
+/* The reference documents "arrays a and b are modified" (R/NTT/ntt256.h:80): after
+ * ntt256_product1/4 they hold the psi-twisted forward NTT in bit-reversed order.  By
+ * default the drop-ins leave a and b untouched; nttb200_legacy_set_clobber(1) reproduces
+ * that post-state for ntt256_product1/4 (for the RED variants the post-state is an
+ * unreduced representative and is not reproduced). */
+void nttb200_legacy_set_clobber(int on);
+
+/* ---- generic-n transforms with the caller's table (R/NTT/ntt.h:71-183) ---------------- */
+void ntt_ct_rev2std_v1(int32_t *a, uint32_t n, const uint16_t *p);   /* ntt.h:71,  ntt.C:168-197 */
+void ntt_ct_rev2std(int32_t *a, uint32_t n, const uint16_t *p);      /* ntt.h:90,  ntt.C:216-243 */
+void mulntt_ct_rev2std(int32_t *a, uint32_t n, const uint16_t *p);   /* ntt.h:100, ntt.C:253-278 */
+void ntt_ct_std2rev(int32_t *a, uint32_t n, const uint16_t *p);      /* ntt.h:117, ntt.C:295-329 */
+void mulntt_ct_std2rev(int32_t *a, uint32_t n, const uint16_t *p);   /* ntt.h:127, ntt.C:342-371 */
+void ntt_gs_rev2std(int32_t *a, uint32_t n, const uint16_t *p);      /* ntt.h:143, ntt.C:387-416 */
+void nttmul_gs_rev2std(int32_t *a, uint32_t n, const uint16_t *p);   /* ntt.h:155, ntt.C:428-451 */
+void ntt_gs_std2rev(int32_t *a, uint32_t n, const uint16_t *p);      /* ntt.h:171, ntt.C:467-493 */
+void nttmul_gs_std2rev(int32_t *a, uint32_t n, const uint16_t *p);   /* ntt.h:183, ntt.C:505-525 */
+
+/* ---- elementwise (R/NTT/ntt.h:37-52) ------------------------------------------------- */
+void mul_array16(int32_t *a, uint32_t n, const uint16_t *p);                      /* ntt.C:119-125 */
+void mul_array(int32_t *c, uint32_t n, const int32_t *a, const int32_t *b);       /* ntt.C:131-137 */
+void scalar_mul_array(int32_t *a, uint32_t n, int32_t c);                         /* ntt.C:147-153 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTTB200_LEGACY_H */

@@ -1,0 +1,115 @@
+/*
+ * legacy.c -- the reference's C call surface (include/nttb200_legacy.h) as thin host
+ * wrappers over the nttb200_* C ABI: batch = 1 on a lazily created default plan
+ * (n = 256, q = 12289, psi = 1002 -- the parameters of R/NTT/ntt256_tables.h:20-24).
+ */
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "nttb200.h"
+#include "nttb200_legacy.h"
+
+#define LEGACY_Q 12289u
+
+static nttb200_plan *g_plan256;
+static pthread_once_t g_once = PTHREAD_ONCE_INIT;
+static int g_plan_rc;
+static int g_clobber;
+
+static void die(const char *what) {
+  fprintf(stderr, "nttb200 legacy surface: %s failed: %s\n", what, nttb200_last_error());
+  abort();
+}
+
+static void make_default_plan(void) { g_plan_rc = nttb200_plan_create(&g_plan256, 256, LEGACY_Q, 1002, 0); }
+
+static nttb200_plan *default_plan(void) {
+  pthread_once(&g_once, make_default_plan);
+  if (g_plan_rc != 0 || !g_plan256) die("nttb200_plan_create(256, 12289, 1002)");
+  return g_plan256;
+}
+
+void nttb200_legacy_set_clobber(int on) { g_clobber = on; }
+
+static void product(int32_t *c, int32_t *a, int32_t *b, int clobber) {
+  nttb200_plan *P = default_plan();
+  if (nttb200_polymul_batch(P, c, a, b, 1) != 0) die("nttb200_polymul_batch");
+  if (clobber) {
+    if (nttb200_ntt_batch(P, NTTB200_MULNTT_STD2REV, a, 1) != 0) die("nttb200_ntt_batch");
+    if (nttb200_ntt_batch(P, NTTB200_MULNTT_STD2REV, b, 1) != 0) die("nttb200_ntt_batch");
+  }
+}
+
+void ntt256_product1(int32_t *c, int32_t *a, int32_t *b) { product(c, a, b, g_clobber); }
+void ntt256_product4(int32_t *c, int32_t *a, int32_t *b) { product(c, a, b, g_clobber); }
+void ntt_red256_product1(int32_t *c, int32_t *a, int32_t *b) { product(c, a, b, 0); }
+void ntt_red256_product4(int32_t *c, int32_t *a, int32_t *b) { product(c, a, b, 0); }
+
+/* caller's 16-bit table -> the ABI's 32-bit table */
+static void table_transform(int32_t *a, uint32_t n, const uint16_t *p, int dataflow) {
+  uint32_t *p32 = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
+  if (!p32) die("malloc");
+  for (uint32_t i = 0; i < n; i++) p32[i] = p[i];
+  int rc = nttb200_ntt_table_batch(n, LEGACY_Q, dataflow, p32, a, 1);
+  free(p32);
+  if (rc != 0) die("nttb200_ntt_table_batch");
+}
+
+void ntt_ct_rev2std_v1(int32_t *a, uint32_t n, const uint16_t *p) {
+  /* v1 reads w_t^j from the psi-power table as p[j * (n/t)] (R/NTT/ntt.C:186): rebuild
+   * the level layout p'[t+j] the other entry points use, then run the same dataflow */
+  uint32_t *lvl = (uint32_t *)calloc(n ? n : 1, sizeof(uint32_t));
+  if (!lvl) die("calloc");
+  for (uint32_t t = 1, l = n; t < n; t <<= 1, l >>= 1)
+    for (uint32_t j = 0; j < t; j++) lvl[t + j] = j ? p[j * l] : 1u;
+  int rc = nttb200_ntt_table_batch(n, LEGACY_Q, NTTB200_DF_CT_REV2STD, lvl, a, 1);
+  free(lvl);
+  if (rc != 0) die("nttb200_ntt_table_batch");
+}
+/* The un-merged entry points skip the multiply of the j = 0 block (twiddle 1,
+ * R/NTT/ntt.C:313-317); their tables hold p[t] = 1 there, so running the merged dataflow
+ * with the caller's table gives the same canonical values. */
+void ntt_ct_rev2std(int32_t *a, uint32_t n, const uint16_t *p)    { table_transform(a, n, p, NTTB200_DF_CT_REV2STD); }
+void mulntt_ct_rev2std(int32_t *a, uint32_t n, const uint16_t *p) { table_transform(a, n, p, NTTB200_DF_CT_REV2STD); }
+void ntt_ct_std2rev(int32_t *a, uint32_t n, const uint16_t *p)    { table_transform(a, n, p, NTTB200_DF_CT_STD2REV); }
+void mulntt_ct_std2rev(int32_t *a, uint32_t n, const uint16_t *p) { table_transform(a, n, p, NTTB200_DF_CT_STD2REV); }
+void ntt_gs_rev2std(int32_t *a, uint32_t n, const uint16_t *p)    { table_transform(a, n, p, NTTB200_DF_GS_REV2STD); }
+void nttmul_gs_rev2std(int32_t *a, uint32_t n, const uint16_t *p) { table_transform(a, n, p, NTTB200_DF_GS_REV2STD); }
+void ntt_gs_std2rev(int32_t *a, uint32_t n, const uint16_t *p)    { table_transform(a, n, p, NTTB200_DF_GS_STD2REV); }
+void nttmul_gs_std2rev(int32_t *a, uint32_t n, const uint16_t *p) { table_transform(a, n, p, NTTB200_DF_GS_STD2REV); }
+
+/* elementwise: a length-n array is one row of an n-coefficient "plan"; these ops do not
+ * use the plan's roots, only its modulus, so any n is served through the 256-plan by
+ * treating the array as ceil(n/256) rows when n is a multiple of 256, else element-wise
+ * through a scratch row. */
+static void elementwise(int32_t *c, uint32_t n, const int32_t *a, const int32_t *b) {
+  nttb200_plan *P = default_plan();
+  uint32_t rows = (n + 255) / 256;
+  int32_t *ta = (int32_t *)calloc((size_t)rows * 256 * 3, sizeof(int32_t));
+  if (!ta) die("calloc");
+  int32_t *tb = ta + (size_t)rows * 256, *tc = tb + (size_t)rows * 256;
+  for (uint32_t i = 0; i < n; i++) { ta[i] = a[i]; tb[i] = b[i]; }
+  int rc = nttb200_mul_array_batch(P, tc, ta, tb, rows);
+  for (uint32_t i = 0; i < n && rc == 0; i++) c[i] = tc[i];
+  free(ta);
+  if (rc != 0) die("nttb200_mul_array_batch");
+}
+
+void mul_array(int32_t *c, uint32_t n, const int32_t *a, const int32_t *b) { elementwise(c, n, a, b); }
+
+void mul_array16(int32_t *a, uint32_t n, const uint16_t *p) {
+  int32_t *p32 = (int32_t *)malloc(sizeof(int32_t) * (n ? n : 1));
+  if (!p32) die("malloc");
+  for (uint32_t i = 0; i < n; i++) p32[i] = p[i];
+  elementwise(a, n, a, p32);
+  free(p32);
+}
+
+void scalar_mul_array(int32_t *a, uint32_t n, int32_t c) {
+  int32_t *cv = (int32_t *)malloc(sizeof(int32_t) * (n ? n : 1));
+  if (!cv) die("malloc");
+  for (uint32_t i = 0; i < n; i++) cv[i] = c;
+  elementwise(a, n, a, cv);
+  free(cv);
+}

@@ -1,0 +1,116 @@
+/*
+ * microbench.cu -- integer-pipe peak measurement (nttb200_measure_int_peak).
+ *
+ * MEASURED_PEAKS.json holds only HBM and bf16 numbers; the INT32 roofline denominator for
+ * the NTT kernels ("IMAD_peak must be measured") comes from these loops:
+ * 8 independent dependency chains per thread, inline PTX so nothing is folded away.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "modarith.cuh"
+#include "plan.h"
+
+namespace {
+
+constexpr int CHAINS = 8;
+constexpr int INNER = 64;
+
+template <int WHICH>
+__global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *sink, uint32_t a, uint32_t b, int iters) {
+  uint32_t x[CHAINS], y[CHAINS];
+#pragma unroll
+  for (int i = 0; i < CHAINS; i++) {
+    x[i] = threadIdx.x * 2654435761u + i * 40503u + blockIdx.x;
+    y[i] = x[i] ^ 0x9E3779B9u;
+  }
+  ModQ m;
+  m.q = 12289u; m.nq = 0u - 12289u; m.q2 = 2u * 12289u; m.qinv = a;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < INNER; r++) {
+#pragma unroll
+      for (int i = 0; i < CHAINS; i++) {
+        if (WHICH == 0) {
+          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(a), "r"(b));
+        } else if (WHICH == 1) {
+          asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(a), "r"(b));
+        } else if (WHICH == 2) {
+          asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(a));
+        } else if (WHICH == 3) {
+          /* the LAZY Cooley-Tukey butterfly: IMAD.HI + 2 IMAD + 2 IADD3 */
+          uint32_t t, T;
+          asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(t) : "r"(y[i]), "r"(b));
+          asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(T) : "r"(y[i]), "r"(a));
+          asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(T) : "r"(t), "r"(m.nq));
+          asm volatile("sub.u32 %0, %1, %2;" : "=r"(y[i]) : "r"(x[i]), "r"(T));
+          asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(T));
+        } else if (WHICH == 4) {
+          unsigned long long w;
+          asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(x[i]), "r"(a));
+          x[i] = (uint32_t)(w >> 32) ^ (uint32_t)w;
+        } else if (WHICH == 5) {
+          /* 1 IMAD : 1 IADD -- does the pair dual-issue across the fma and alu pipes? */
+          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(a), "r"(b));
+          asm volatile("add.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(a));
+        } else if (WHICH == 6) {
+          asm volatile("min.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i]));
+          asm volatile("add.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(a));
+        } else if (WHICH == 7) {
+          asm volatile("shfl.sync.bfly.b32 %0, %0, 1, 0x1f, 0xffffffff;" : "+r"(x[i]));
+        }
+      }
+    }
+  }
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < CHAINS; i++) acc ^= x[i] ^ y[i];
+  if (acc == 0x12345u) sink[0] = acc;
+}
+
+template <int WHICH>
+int run(double ops_per_inner, double *rate) {
+  int dev = 0, sms = 0;
+  NTT_CUDA(cudaGetDevice(&dev));
+  NTT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  uint32_t *sink = nullptr;
+  NTT_CUDA(cudaMalloc(&sink, 64));
+  const int grid = sms * 8, threads = 256, iters = 256;
+  cudaEvent_t e0, e1;
+  NTT_CUDA(cudaEventCreate(&e0));
+  NTT_CUDA(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    NTT_CUDA(cudaEventRecord(e0));
+    int_peak_kernel<WHICH><<<grid, threads>>>(sink, 0x9E3779B1u, 0x85EBCA77u, iters);
+    NTT_CUDA(cudaEventRecord(e1));
+    NTT_CUDA(cudaEventSynchronize(e1));
+    NTT_CUDA(cudaGetLastError());
+    float ms = 0;
+    NTT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    double ops = (double)grid * threads * iters * INNER * CHAINS * ops_per_inner;
+    double r = ops / (ms * 1e-3);
+    if (rep > 0 && r > best) best = r;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  *rate = best;
+  return 0;
+}
+}  // namespace
+
+extern "C" int nttb200_measure_int_peak(int which, double *lane_ops_per_s) {
+  if (!lane_ops_per_s) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
+  switch (which) {
+    case 0: return run<0>(1, lane_ops_per_s);   /* IMAD                         */
+    case 1: return run<1>(1, lane_ops_per_s);   /* IMAD.HI                      */
+    case 2: return run<2>(1, lane_ops_per_s);   /* IADD                         */
+    case 3: return run<3>(1, lane_ops_per_s);   /* butterflies / s (5 instr each) */
+    case 4: return run<4>(1, lane_ops_per_s);   /* IMAD.WIDE (+1 LOP)           */
+    case 5: return run<5>(2, lane_ops_per_s);   /* IMAD + IADD pairs, counted as 2 */
+    case 6: return run<6>(2, lane_ops_per_s);   /* IMNMX + IADD                 */
+    case 7: return run<7>(1, lane_ops_per_s);   /* SHFL                         */
+    default: return nttb200_fail(NTTB200_EPARAM, "unknown microbenchmark %d", which);
+  }
+}

@@ -1,0 +1,577 @@
+/*
+ * nttb200.cu -- runtime behind include/nttb200.h: plans, device tables, the device-resident
+ * and host-buffer (pinned ring, H2D / kernel / D2H overlap) entry points.
+ *
+ * This is the layer that stands where the reference's FPGA transfer path stood
+ * (Software_Hardware_Comunnicator/linux_app/NTT_PCIECommunicationv2.c:109-252): there, one
+ * polynomial pair per DMA round trip; here, a batch streamed through CUDA streams.
+ * There is no CPU compute path: without a CUDA device every computing call fails.
+ */
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "host_tables.h"
+#include "ntt_generic.cuh"
+#include "plan.h"
+
+/* per-arithmetic-class dispatchers (small_*.cu) */
+#define DECL_SMALL(name)                                                                          \
+  int launch_polymul_small_##name(const nttb200_plan *, uint32_t *, const uint32_t *, const uint32_t *, \
+                                  size_t, cudaStream_t);                                          \
+  int launch_ntt_small_##name(const nttb200_plan *, const DevTable &, int, int, uint32_t *, size_t, \
+                              cudaStream_t);                                                      \
+  int small_kernel_info_##name(const nttb200_plan *, int *, int *, int *);
+DECL_SMALL(lazy)
+DECL_SMALL(harvey)
+DECL_SMALL(canon)
+
+/* ------------------------------------------------------------------------------------ */
+/* errors, launch counter                                                                */
+/* ------------------------------------------------------------------------------------ */
+static thread_local char g_err[512] = "";
+static thread_local int g_launches = 0;
+static thread_local int g_device = -1;
+
+int nttb200_fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+void nttb200_count_launch(int k) { g_launches += k; }
+
+extern "C" const char *nttb200_last_error(void) { return g_err; }
+extern "C" int nttb200_version(void) { return NTTB200_VERSION; }
+extern "C" int nttb200_last_launch_count(void) { return g_launches; }
+
+extern "C" int nttb200_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return nttb200_fail(NTTB200_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  }
+  return n;
+}
+extern "C" int nttb200_set_device(int device) {
+  NTT_CUDA(cudaSetDevice(device));
+  g_device = device;
+  return 0;
+}
+extern "C" int nttb200_get_device(void) {
+  int d = -1;
+  if (cudaGetDevice(&d) != cudaSuccess) {
+    cudaGetLastError();
+    return NTTB200_ECUDA;
+  }
+  return d;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* plans                                                                                 */
+/* ------------------------------------------------------------------------------------ */
+static int upload_table(DevTable &t, const std::vector<uint32_t> &w, uint32_t q) {
+  t.h.resize(w.size());
+  for (size_t i = 0; i < w.size(); i++) t.h[i] = make_uint2(w[i], ht_shoup(w[i], q));
+  NTT_CUDA(cudaMalloc(&t.d, t.h.size() * sizeof(uint2)));
+  NTT_CUDA(cudaMemcpy(t.d, t.h.data(), t.h.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+  return 0;
+}
+static void free_table(DevTable &t) {
+  if (t.d) cudaFree(t.d);
+  t.d = nullptr;
+  t.h.clear();
+}
+
+static int pick_arith(uint32_t q, uint32_t logn) {
+  /* LAZY: GS values double per stage (q 2^(logn+1) < 2^32) and the pointwise REDC needs
+   * ((2 logn + 1) q)^2 < q 2^32 */
+  const unsigned long long gs = (unsigned long long)q << (logn + 1);
+  const unsigned long long ct = (unsigned long long)(2 * logn + 1);
+  if (gs < (1ull << 32) && ct * ct * q < (1ull << 32)) return ARITH_LAZY;
+  if (q < (1u << 30)) return ARITH_HARVEY;
+  return ARITH_CANON;
+}
+
+extern "C" int nttb200_plan_create(nttb200_plan **out, uint32_t n, uint32_t q, uint32_t psi,
+                                   uint32_t flags) {
+  if (!out) return nttb200_fail(NTTB200_EPARAM, "plan pointer is NULL");
+  *out = nullptr;
+  if (n < 8 || (n & (n - 1)) || n > (1u << 17))
+    return nttb200_fail(NTTB200_EPARAM, "n=%u: need a power of two in [8, 2^17]", n);
+  if (q >= (1u << 31) || q < 3 || !nttb200_is_prime(q))
+    return nttb200_fail(NTTB200_EPARAM, "q=%u: need an odd prime below 2^31", q);
+  const bool cyclic = (flags & NTTB200_PLAN_CYCLIC) != 0;
+  uint32_t omega;
+  if (cyclic) {
+    if ((q - 1) % n) return nttb200_fail(NTTB200_EPARAM, "q=%u: n=%u does not divide q-1", q, n);
+    omega = psi ? psi : nttb200_find_omega(n, q);
+    if (!omega || ht_powmod(omega, n / 2, q) != q - 1)
+      return nttb200_fail(NTTB200_EPARAM, "omega=%u is not a primitive %u-th root mod %u", omega, n, q);
+    psi = 0;
+  } else {
+    if ((uint64_t)(q - 1) % (2ull * n))
+      return nttb200_fail(NTTB200_EPARAM,
+                          "q=%u has no primitive %u-th root of unity (2n must divide q-1); "
+                          "use NTTB200_PLAN_CYCLIC for the psi-free surface", q, 2 * n);
+    if (!psi) psi = nttb200_find_psi(n, q);
+    if (!psi || psi >= q || ht_powmod(psi, n, q) != q - 1)
+      return nttb200_fail(NTTB200_EPARAM, "psi=%u is not a primitive %u-th root mod %u", psi, 2 * n, q);
+    omega = (uint32_t)((uint64_t)psi * psi % q);
+  }
+
+  int dev = 0;
+  int ndev = nttb200_device_count();
+  if (ndev <= 0) return nttb200_fail(NTTB200_ECUDA, "no CUDA device (there is no CPU fallback)");
+  if (g_device >= 0) NTT_CUDA(cudaSetDevice(g_device));
+  NTT_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  NTT_CUDA(cudaGetDeviceProperties(&prop, dev));
+
+  nttb200_plan *P = new (std::nothrow) nttb200_plan;
+  if (!P) return nttb200_fail(NTTB200_ENOMEM, "out of host memory");
+  P->n = n; P->logn = ht_log2(n); P->q = q; P->psi = psi; P->omega = omega; P->flags = flags;
+  P->n_inv = ht_invmod(n % q, q);
+  P->device = dev;
+  P->sm_count = prop.multiProcessorCount;
+  P->arith = pick_arith(q, P->logn);
+  P->kernel = (P->logn <= 10) ? PK_SMALL : PK_LARGE;
+  P->m.q = q; P->m.nq = 0u - q; P->m.q2 = 2u * q;
+  {
+    uint32_t inv = 1;                                   /* Newton: q^-1 mod 2^32 */
+    for (int i = 0; i < 5; i++) inv *= 2u - q * inv;
+    P->m.qinv = inv;
+  }
+
+  std::vector<uint32_t> w(n);
+  const uint32_t iomega = ht_invmod(omega, q);
+  int rc = 0;
+  ht_level_table(w.data(), n, q, 1, omega, 1);
+  rc = rc ? rc : upload_table(P->fwd_plain, w, q);
+  rc = rc ? rc : upload_table(P->inv_fwdroot, w, q);
+  ht_level_table(w.data(), n, q, 1, iomega, 1);
+  rc = rc ? rc : upload_table(P->inv_plain, w, q);
+  rc = rc ? rc : upload_table(P->fwd_invroot, w, q);
+  if (!cyclic) {
+    ht_level_table(w.data(), n, q, psi, omega, 1);
+    rc = rc ? rc : upload_table(P->fwd_mixed, w, q);
+    ht_level_table(w.data(), n, q, ht_invmod(psi, q), iomega, 1);
+    rc = rc ? rc : upload_table(P->inv_mixed, w, q);
+  }
+  if (rc) { nttb200_plan_destroy(P); return rc; }
+  static const char *an[] = {"lazy", "harvey", "canon"};
+  snprintf(P->desc, sizeof P->desc, "n=%u q=%u %s=%u kernel=%s arith=%s device=%d sms=%d", n, q,
+           cyclic ? "omega" : "psi", cyclic ? omega : psi,
+           P->kernel == PK_SMALL ? "fused-small(regs+smem)" : "large(multi-pass)", an[P->arith], dev,
+           P->sm_count);
+  *out = P;
+  return 0;
+}
+
+extern "C" void nttb200_plan_destroy(nttb200_plan *P) {
+  if (!P) return;
+  int cur = -1;
+  cudaGetDevice(&cur);
+  cudaSetDevice(P->device);
+  for (auto &s : P->slots) {
+    if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+    if (s.done) cudaEventDestroy(s.done);
+    cudaFree(s.d_a); cudaFree(s.d_b); cudaFree(s.d_c);
+  }
+  if (P->scratch) cudaFree(P->scratch);
+  free_table(P->fwd_mixed); free_table(P->inv_mixed);
+  free_table(P->fwd_plain); free_table(P->inv_plain);
+  free_table(P->fwd_invroot); free_table(P->inv_fwdroot);
+  if (cur >= 0) cudaSetDevice(cur);
+  delete P;
+}
+extern "C" uint32_t nttb200_plan_n(const nttb200_plan *P) { return P ? P->n : 0; }
+extern "C" uint32_t nttb200_plan_q(const nttb200_plan *P) { return P ? P->q : 0; }
+extern "C" uint32_t nttb200_plan_psi(const nttb200_plan *P) {
+  return P ? ((P->flags & NTTB200_PLAN_CYCLIC) ? P->omega : P->psi) : 0;
+}
+extern "C" int nttb200_plan_device(const nttb200_plan *P) { return P ? P->device : -1; }
+extern "C" const char *nttb200_plan_describe(const nttb200_plan *P) { return P ? P->desc : ""; }
+
+/* ------------------------------------------------------------------------------------ */
+/* dispatch                                                                              */
+/* ------------------------------------------------------------------------------------ */
+int launch_polymul_small(const nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b,
+                         size_t batch, cudaStream_t st) {
+  switch (P->arith) {
+    case ARITH_LAZY: return launch_polymul_small_lazy(P, c, a, b, batch, st);
+    case ARITH_HARVEY: return launch_polymul_small_harvey(P, c, a, b, batch, st);
+    default: return launch_polymul_small_canon(P, c, a, b, batch, st);
+  }
+}
+int launch_ntt_small(const nttb200_plan *P, const DevTable &tab, int dir, int scale, uint32_t *a,
+                     size_t batch, cudaStream_t st) {
+  switch (P->arith) {
+    case ARITH_LAZY: return launch_ntt_small_lazy(P, tab, dir, scale, a, batch, st);
+    case ARITH_HARVEY: return launch_ntt_small_harvey(P, tab, dir, scale, a, batch, st);
+    default: return launch_ntt_small_canon(P, tab, dir, scale, a, batch, st);
+  }
+}
+int small_kernel_info(const nttb200_plan *P, int *regs, int *smem_bytes, int *blocks_per_sm) {
+  switch (P->arith) {
+    case ARITH_LAZY: return small_kernel_info_lazy(P, regs, smem_bytes, blocks_per_sm);
+    case ARITH_HARVEY: return small_kernel_info_harvey(P, regs, smem_bytes, blocks_per_sm);
+    default: return small_kernel_info_canon(P, regs, smem_bytes, blocks_per_sm);
+  }
+}
+
+static int grid_1d(unsigned long long work, int threads, int sm_count) {
+  unsigned long long blocks = (work + threads - 1) / threads;
+  unsigned long long cap = (unsigned long long)sm_count * 16;
+  return (int)std::max<unsigned long long>(1, std::min(blocks, cap));
+}
+static int current_sms() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess)
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+int launch_generic_transform(uint32_t n, uint32_t logn, const ModQ &m, int dataflow, const uint2 *d_tab,
+                             uint32_t *a, size_t batch, cudaStream_t st) {
+  using namespace nttb200;
+  const unsigned long long pairs = (unsigned long long)batch * (n / 2);
+  const int grid = grid_1d(pairs, 256, current_sms());
+  const bool descending = (dataflow == DF_CT_STD2REV || dataflow == DF_GS_STD2REV);
+  for (uint32_t s = 0; s < logn; s++) {
+    const uint32_t lh = descending ? (logn - 1 - s) : s;
+    const uint32_t half = 1u << lh;
+    switch (dataflow) {
+      case DF_CT_STD2REV: generic_stage_kernel<DF_CT_STD2REV><<<grid, 256, 0, st>>>(a, d_tab, n, logn, half, lh, pairs, m); break;
+      case DF_GS_REV2STD: generic_stage_kernel<DF_GS_REV2STD><<<grid, 256, 0, st>>>(a, d_tab, n, logn, half, lh, pairs, m); break;
+      case DF_CT_REV2STD: generic_stage_kernel<DF_CT_REV2STD><<<grid, 256, 0, st>>>(a, d_tab, n, logn, half, lh, pairs, m); break;
+      case DF_GS_STD2REV: generic_stage_kernel<DF_GS_STD2REV><<<grid, 256, 0, st>>>(a, d_tab, n, logn, half, lh, pairs, m); break;
+      default: return nttb200_fail(NTTB200_EPARAM, "unknown dataflow %d", dataflow);
+    }
+    nttb200_count_launch(1);
+  }
+  NTT_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_pointwise(uint32_t *c, const uint32_t *a, const uint32_t *b, size_t count, const ModQ &m,
+                     uint32_t r2, cudaStream_t st) {
+  nttb200::pointwise_kernel<<<grid_1d(count, 256, current_sms()), 256, 0, st>>>(c, a, b, count, m, r2);
+  nttb200_count_launch(1);
+  NTT_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_scale(uint32_t *a, const uint2 *d_tab, uint2 sc, uint32_t n, size_t count, const ModQ &m,
+                 cudaStream_t st) {
+  nttb200::scale_kernel<<<grid_1d(count, 256, current_sms()), 256, 0, st>>>(a, d_tab, sc, n, count, m);
+  nttb200_count_launch(1);
+  NTT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static uint2 pair_of(uint64_t w, uint32_t q) {
+  w %= q;
+  return make_uint2((uint32_t)w, ht_shoup((uint32_t)w, q));
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static int polymul_dev(nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b, size_t batch,
+                       cudaStream_t st) {
+  if (batch == 0) return 0;
+  if (P->kernel == PK_SMALL) return launch_polymul_small(P, c, a, b, batch, st);
+  return launch_polymul_large(P, c, a, b, batch, st);
+}
+
+static int transform_dev(nttb200_plan *P, int transform, uint32_t *a, size_t batch, cudaStream_t st) {
+  if (batch == 0) return 0;
+  const bool cyclic = (P->flags & NTTB200_PLAN_CYCLIC) != 0;
+  const DevTable *tab = nullptr;
+  int dir = 0, scale = 0;
+  switch (transform) {
+    case NTTB200_NTT_STD2REV: tab = &P->fwd_plain; dir = 0; break;
+    case NTTB200_MULNTT_STD2REV: tab = &P->fwd_mixed; dir = 0; break;
+    case NTTB200_INTT_REV2STD: tab = &P->inv_plain; dir = 1; break;
+    case NTTB200_INTTMUL_REV2STD: tab = &P->inv_mixed; dir = 1; break;
+    case NTTB200_INTT_REV2STD_SCALED: tab = &P->inv_plain; dir = 1; scale = 1; break;
+    case NTTB200_INTTMUL_REV2STD_SCALED: tab = &P->inv_mixed; dir = 1; scale = 1; break;
+    case NTTB200_INTT_STD2REV: tab = &P->fwd_invroot; dir = 0; break;
+    case NTTB200_NTT_REV2STD: tab = &P->inv_fwdroot; dir = 1; break;
+    default: return nttb200_fail(NTTB200_EPARAM, "unknown transform %d", transform);
+  }
+  if (cyclic && (tab == &P->fwd_mixed || tab == &P->inv_mixed))
+    return nttb200_fail(NTTB200_EPARAM, "psi-merged transforms need a negacyclic plan");
+  if (P->kernel == PK_SMALL) return launch_ntt_small(P, *tab, dir, scale, a, batch, st);
+  return launch_ntt_large(P, *tab, dir, scale, a, batch, st);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* large n (first version): literal stage-per-launch dataflow on scratch copies           */
+/* ------------------------------------------------------------------------------------ */
+static int ensure_scratch(nttb200_plan *P, size_t polys) {
+  if (P->scratch_polys >= polys) return 0;
+  if (P->scratch) cudaFree(P->scratch);
+  P->scratch = nullptr; P->scratch_polys = 0;
+  NTT_CUDA(cudaMalloc(&P->scratch, polys * P->n * 2 * sizeof(uint32_t)));
+  P->scratch_polys = polys;
+  return 0;
+}
+
+int launch_polymul_large(nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b, size_t batch,
+                         cudaStream_t st) {
+  using namespace nttb200;
+  const bool cyclic = (P->flags & NTTB200_PLAN_CYCLIC) != 0;
+  const DevTable &fwd = cyclic ? P->fwd_plain : P->fwd_mixed;
+  const DevTable &inv = cyclic ? P->inv_plain : P->inv_mixed;
+  const size_t chunk = std::max<size_t>(1, std::min<size_t>(batch, (256u << 20) / (P->n * 8)));
+  int rc = ensure_scratch(P, chunk);
+  if (rc) return rc;
+  const uint64_t r1 = (1ull << 32) % P->q;
+  const uint32_t r2m = (uint32_t)(r1 * r1 % P->q);
+  for (size_t done = 0; done < batch; done += chunk) {
+    const size_t nb = std::min(chunk, batch - done);
+    const size_t words = nb * P->n;
+    uint32_t *ta = P->scratch, *tb = P->scratch + chunk * P->n;
+    NTT_CUDA(cudaMemcpyAsync(ta, a + done * P->n, words * 4, cudaMemcpyDeviceToDevice, st));
+    NTT_CUDA(cudaMemcpyAsync(tb, b + done * P->n, words * 4, cudaMemcpyDeviceToDevice, st));
+    if ((rc = launch_generic_transform(P->n, P->logn, P->m, DF_CT_STD2REV, fwd.d, ta, nb, st))) return rc;
+    if ((rc = launch_generic_transform(P->n, P->logn, P->m, DF_CT_STD2REV, fwd.d, tb, nb, st))) return rc;
+    uint32_t *tc = c + done * P->n;
+    if ((rc = launch_pointwise(tc, ta, tb, words, P->m, r2m, st))) return rc;
+    if ((rc = launch_generic_transform(P->n, P->logn, P->m, DF_GS_REV2STD, inv.d, tc, nb, st))) return rc;
+    if ((rc = launch_scale(tc, nullptr, pair_of(P->n_inv, P->q), P->n, words, P->m, st))) return rc;
+  }
+  return 0;
+}
+
+int launch_ntt_large(nttb200_plan *P, const DevTable &tab, int dir, int scale, uint32_t *a, size_t batch,
+                     cudaStream_t st) {
+  using namespace nttb200;
+  int rc = launch_generic_transform(P->n, P->logn, P->m, dir == 0 ? DF_CT_STD2REV : DF_GS_REV2STD, tab.d,
+                                    a, batch, st);
+  if (rc) return rc;
+  if (scale) rc = launch_scale(a, nullptr, pair_of(P->n_inv, P->q), P->n, batch * P->n, P->m, st);
+  return rc;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* public: device-resident                                                               */
+/* ------------------------------------------------------------------------------------ */
+extern "C" int nttb200_polymul_batch_dev(nttb200_plan *P, int32_t *c, const int32_t *a, const int32_t *b,
+                                         size_t batch, void *stream) {
+  if (!P || !c || !a || !b) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
+  g_launches = 0;
+  DeviceGuard guard(P->device);
+  return polymul_dev(P, (uint32_t *)c, (const uint32_t *)a, (const uint32_t *)b, batch,
+                     (cudaStream_t)stream);
+}
+
+extern "C" int nttb200_ntt_batch_dev(nttb200_plan *P, int transform, int32_t *a, size_t batch,
+                                     void *stream) {
+  if (!P || !a) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
+  g_launches = 0;
+  DeviceGuard guard(P->device);
+  return transform_dev(P, transform, (uint32_t *)a, batch, (cudaStream_t)stream);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* public: host buffers.  Ring of NSLOT device staging slots, each with its own stream:    */
+/* H2D(a,b) -> kernel -> D2H(c) of slot k overlaps the copies of slots k+-1.  cudaMemcpyAsync */
+/* from pinned memory (nttb200_host_alloc) is a true async DMA; pageable memory also works  */
+/* (the driver stages it).                                                                */
+/* ------------------------------------------------------------------------------------ */
+static const int NSLOT = 3;
+
+static int ensure_slots(nttb200_plan *P, bool need_b) {
+  if (!P->slots.empty()) return 0;
+  const size_t target_bytes = 8u << 20;                 /* per operand per slot */
+  P->slot_polys = std::max<size_t>(1, target_bytes / (P->n * sizeof(uint32_t)));
+  P->slots.resize(NSLOT);
+  for (auto &s : P->slots) {
+    NTT_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    NTT_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    NTT_CUDA(cudaMalloc(&s.d_a, P->slot_polys * P->n * sizeof(uint32_t)));
+    NTT_CUDA(cudaMalloc(&s.d_b, P->slot_polys * P->n * sizeof(uint32_t)));
+    NTT_CUDA(cudaMalloc(&s.d_c, P->slot_polys * P->n * sizeof(uint32_t)));
+  }
+  (void)need_b;
+  return 0;
+}
+
+extern "C" int nttb200_polymul_batch(nttb200_plan *P, int32_t *c, const int32_t *a, const int32_t *b,
+                                     size_t batch) {
+  if (!P || !c || !a || !b) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
+  g_launches = 0;
+  std::lock_guard<std::mutex> lock(P->mu);
+  DeviceGuard guard(P->device);
+  int rc = ensure_slots(P, true);
+  if (rc) return rc;
+  const size_t n = P->n;
+  size_t k = 0;
+  for (size_t done = 0; done < batch; done += P->slot_polys, k++) {
+    HostSlot &s = P->slots[k % NSLOT];
+    const size_t nb = std::min(P->slot_polys, batch - done);
+    const size_t bytes = nb * n * sizeof(uint32_t);
+    /* the slot's previous D2H is ordered before these copies by stream order */
+    NTT_CUDA(cudaMemcpyAsync(s.d_a, a + done * n, bytes, cudaMemcpyHostToDevice, s.stream));
+    NTT_CUDA(cudaMemcpyAsync(s.d_b, b + done * n, bytes, cudaMemcpyHostToDevice, s.stream));
+    if ((rc = polymul_dev(P, s.d_c, s.d_a, s.d_b, nb, s.stream))) return rc;
+    NTT_CUDA(cudaMemcpyAsync(c + done * n, s.d_c, bytes, cudaMemcpyDeviceToHost, s.stream));
+  }
+  for (auto &s : P->slots) NTT_CUDA(cudaStreamSynchronize(s.stream));
+  return 0;
+}
+
+extern "C" int nttb200_ntt_batch(nttb200_plan *P, int transform, int32_t *a, size_t batch) {
+  if (!P || !a) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
+  g_launches = 0;
+  std::lock_guard<std::mutex> lock(P->mu);
+  DeviceGuard guard(P->device);
+  int rc = ensure_slots(P, false);
+  if (rc) return rc;
+  const size_t n = P->n;
+  size_t k = 0;
+  for (size_t done = 0; done < batch; done += P->slot_polys, k++) {
+    HostSlot &s = P->slots[k % NSLOT];
+    const size_t nb = std::min(P->slot_polys, batch - done);
+    const size_t bytes = nb * n * sizeof(uint32_t);
+    NTT_CUDA(cudaMemcpyAsync(s.d_a, a + done * n, bytes, cudaMemcpyHostToDevice, s.stream));
+    if ((rc = transform_dev(P, transform, s.d_a, nb, s.stream))) return rc;
+    NTT_CUDA(cudaMemcpyAsync(a + done * n, s.d_a, bytes, cudaMemcpyDeviceToHost, s.stream));
+  }
+  for (auto &s : P->slots) NTT_CUDA(cudaStreamSynchronize(s.stream));
+  return 0;
+}
+
+extern "C" int nttb200_mul_array_batch(nttb200_plan *P, int32_t *c, const int32_t *a, const int32_t *b,
+                                       size_t batch) {
+  if (!P || !c || !a || !b) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
+  g_launches = 0;
+  std::lock_guard<std::mutex> lock(P->mu);
+  DeviceGuard guard(P->device);
+  int rc = ensure_slots(P, true);
+  if (rc) return rc;
+  const uint64_t r1 = (1ull << 32) % P->q;
+  const uint32_t r2 = (uint32_t)(r1 * r1 % P->q);
+  const size_t n = P->n;
+  size_t k = 0;
+  for (size_t done = 0; done < batch; done += P->slot_polys, k++) {
+    HostSlot &s = P->slots[k % NSLOT];
+    const size_t nb = std::min(P->slot_polys, batch - done);
+    const size_t bytes = nb * n * sizeof(uint32_t);
+    NTT_CUDA(cudaMemcpyAsync(s.d_a, a + done * n, bytes, cudaMemcpyHostToDevice, s.stream));
+    NTT_CUDA(cudaMemcpyAsync(s.d_b, b + done * n, bytes, cudaMemcpyHostToDevice, s.stream));
+    if ((rc = launch_pointwise(s.d_c, s.d_a, s.d_b, nb * n, P->m, r2, s.stream))) return rc;
+    NTT_CUDA(cudaMemcpyAsync(c + done * n, s.d_c, bytes, cudaMemcpyDeviceToHost, s.stream));
+  }
+  for (auto &s : P->slots) NTT_CUDA(cudaStreamSynchronize(s.stream));
+  return 0;
+}
+
+extern "C" int nttb200_scalar_mul_array_batch(nttb200_plan *P, int32_t *a, int32_t sc, size_t batch) {
+  if (!P || !a) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
+  if (sc < 0 || (uint32_t)sc >= P->q) return nttb200_fail(NTTB200_ERANGE, "scalar outside [0, q)");
+  g_launches = 0;
+  std::lock_guard<std::mutex> lock(P->mu);
+  DeviceGuard guard(P->device);
+  int rc = ensure_slots(P, false);
+  if (rc) return rc;
+  const size_t n = P->n;
+  size_t k = 0;
+  for (size_t done = 0; done < batch; done += P->slot_polys, k++) {
+    HostSlot &s = P->slots[k % NSLOT];
+    const size_t nb = std::min(P->slot_polys, batch - done);
+    const size_t bytes = nb * n * sizeof(uint32_t);
+    NTT_CUDA(cudaMemcpyAsync(s.d_a, a + done * n, bytes, cudaMemcpyHostToDevice, s.stream));
+    if ((rc = launch_scale(s.d_a, nullptr, pair_of((uint32_t)sc, P->q), P->n, nb * n, P->m, s.stream)))
+      return rc;
+    NTT_CUDA(cudaMemcpyAsync(a + done * n, s.d_a, bytes, cudaMemcpyDeviceToHost, s.stream));
+  }
+  for (auto &s : P->slots) NTT_CUDA(cudaStreamSynchronize(s.stream));
+  return 0;
+}
+
+/* Table-driven transform: the literal reference dataflow with the caller's table. */
+extern "C" int nttb200_ntt_table_batch(uint32_t n, uint32_t q, int dataflow, const uint32_t *p, int32_t *a,
+                                       size_t batch) {
+  if (!p || !a) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
+  if (n < 2 || (n & (n - 1)) || q < 3 || q >= (1u << 31) || !(q & 1))
+    return nttb200_fail(NTTB200_EPARAM, "bad (n=%u, q=%u)", n, q);
+  if (dataflow < 0 || dataflow > 3) return nttb200_fail(NTTB200_EPARAM, "unknown dataflow %d", dataflow);
+  if (nttb200_device_count() <= 0) return nttb200_fail(NTTB200_ECUDA, "no CUDA device (there is no CPU fallback)");
+  g_launches = 0;
+  if (batch == 0) return 0;
+  std::vector<uint2> h(n);
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t w = p[i] % q;
+    h[i] = make_uint2(w, ht_shoup(w, q));
+  }
+  ModQ m;
+  m.q = q; m.nq = 0u - q; m.q2 = 2u * q;
+  uint32_t inv = 1;
+  for (int i = 0; i < 5; i++) inv *= 2u - q * inv;
+  m.qinv = inv;
+  uint2 *d_tab = nullptr;
+  uint32_t *d_a = nullptr;
+  const size_t bytes = batch * n * sizeof(uint32_t);
+  int rc = 0;
+  cudaError_t e = cudaMalloc(&d_tab, n * sizeof(uint2));
+  if (e == cudaSuccess) e = cudaMalloc(&d_a, bytes);
+  if (e == cudaSuccess) e = cudaMemcpy(d_tab, h.data(), n * sizeof(uint2), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_a, a, bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) rc = launch_generic_transform(n, ht_log2(n), m, dataflow, d_tab, d_a, batch, 0);
+  if (e == cudaSuccess && rc == 0) e = cudaMemcpy(a, d_a, bytes, cudaMemcpyDeviceToHost);
+  cudaFree(d_tab);
+  cudaFree(d_a);
+  if (e != cudaSuccess) return nttb200_fail(NTTB200_ECUDA, "table transform: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* memory helpers                                                                        */
+/* ------------------------------------------------------------------------------------ */
+extern "C" void *nttb200_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    nttb200_fail(NTTB200_ENOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  return p;
+}
+extern "C" void nttb200_host_free(void *p) { if (p) cudaFreeHost(p); }
+extern "C" void *nttb200_dev_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+    nttb200_fail(NTTB200_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  return p;
+}
+extern "C" void nttb200_dev_free(void *p) { if (p) cudaFree(p); }
+extern "C" int nttb200_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream) {
+  NTT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return 0;
+}
+extern "C" int nttb200_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream) {
+  NTT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return 0;
+}
+extern "C" int nttb200_stream_sync(void *stream) {
+  NTT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}

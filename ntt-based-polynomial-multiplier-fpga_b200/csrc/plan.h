@@ -1,0 +1,83 @@
+/*
+ * plan.h -- internal definition of nttb200_plan shared by the runtime translation units.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <vector>
+
+#include "modarith.cuh"
+#include "nttb200.h"
+
+struct DevTable {
+  uint2 *d = nullptr;            /* device: n entries (w, floor(w 2^32/q)), reference level layout */
+  std::vector<uint2> h;          /* host mirror (entries < 64 feed the kernel-parameter block)     */
+};
+
+enum PlanKernel { PK_SMALL = 0, PK_LARGE = 1 };
+
+struct HostSlot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  uint32_t *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;
+};
+
+struct nttb200_plan {
+  uint32_t n = 0, logn = 0, q = 0, psi = 0, omega = 0, flags = 0;
+  uint32_t n_inv = 0;
+  int device = 0;
+  int arith = ARITH_LAZY;
+  int kernel = PK_SMALL;
+  int sm_count = 0;
+  ModQ m{};
+  char desc[160] = {0};
+
+  /* tables by role.  Product path: fwd = mixed_powers_rev, inv = inv_mixed_powers_rev
+   * (omega_powers_rev / inv_omega_powers_rev for CYCLIC plans). */
+  DevTable fwd_mixed, inv_mixed;          /* psi-merged                                 */
+  DevTable fwd_plain, inv_plain;          /* omega_powers_rev / inv_omega_powers_rev    */
+  DevTable fwd_invroot;                   /* inv_omega_powers_rev used as a FORWARD table */
+  DevTable inv_fwdroot;                   /* omega_powers_rev used as an INVERSE table    */
+
+  /* host-buffer path: ring of device staging slots */
+  std::mutex mu;
+  std::vector<HostSlot> slots;
+  size_t slot_polys = 0;
+
+  /* large-n scratch (device), sized for scratch_polys polynomials */
+  uint32_t *scratch = nullptr;
+  size_t scratch_polys = 0;
+};
+
+/* error plumbing (nttb200.cu) */
+int nttb200_fail(int code, const char *fmt, ...);
+#define NTT_CUDA(expr)                                                                    \
+  do {                                                                                    \
+    cudaError_t e_ = (expr);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return nttb200_fail(NTTB200_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                          __FILE__, __LINE__);                                            \
+  } while (0)
+
+void nttb200_count_launch(int k);
+
+/* dispatchers implemented in the kernel translation units */
+int launch_polymul_small(const nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b,
+                         size_t batch, cudaStream_t st);
+/* dir 0: forward CT std2rev with table `tab`; dir 1: inverse GS rev2std.
+ * scale: 0 = none, 1 = multiply by n^-1 (inverse only) */
+int launch_ntt_small(const nttb200_plan *P, const DevTable &tab, int dir, int scale, uint32_t *a,
+                     size_t batch, cudaStream_t st);
+int launch_generic_transform(uint32_t n, uint32_t logn, const ModQ &m, int dataflow, const uint2 *d_tab,
+                             uint32_t *a, size_t batch, cudaStream_t st);
+int launch_pointwise(uint32_t *c, const uint32_t *a, const uint32_t *b, size_t count, const ModQ &m,
+                     uint32_t r2, cudaStream_t st);
+int launch_scale(uint32_t *a, const uint2 *d_tab, uint2 sc, uint32_t n, size_t count, const ModQ &m,
+                 cudaStream_t st);
+int launch_polymul_large(nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b,
+                         size_t batch, cudaStream_t st);
+int launch_ntt_large(nttb200_plan *P, const DevTable &tab, int dir, int scale, uint32_t *a, size_t batch,
+                     cudaStream_t st);
+int small_kernel_info(const nttb200_plan *P, int *regs, int *smem_bytes, int *blocks_per_sm);

@@ -1,0 +1,279 @@
+"""GPU (B200): the CUDA path, called through the C ABI, bit-exact against
+  * the committed golden vectors produced by the compiled reference C,
+  * the CPU oracle on the same seeded inputs (sizes the oracle finishes in seconds),
+  * the compiled reference itself (oracle/_ref travels to the box) on a 2^16 batch,
+and, at BASELINE.json's full batch sizes, through size-independent properties
+(linearity, delta rows, commutativity, checksum against sampled oracle rows)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N, Q, PSI = 256, 12289, 1002
+SEED = 0x4E545442323030
+
+SMALL_CASES = [(8, 17), (16, 97), (32, 193), (64, 257), (128, 3329), (256, 12289), (256, 7681),
+               (512, 12289), (1024, 12289),
+               (256, 8380417), (1024, 8380417),          # Dilithium prime: HARVEY class
+               (256, 469762049), (1024, 998244353),      # 29/30-bit primes: HARVEY class
+               (256, 2013265921), (1024, 2013265921)]    # 31-bit prime: CANON class
+
+
+@pytest.fixture(scope="module")
+def plan256(gpu):
+    p = gpu.Plan(N, Q, PSI)
+    yield p
+    p.close()
+
+
+def test_native_library_is_the_one_running(gpu, plan256):
+    assert "fused-small" in plan256.describe() and "arith=lazy" in plan256.describe()
+    a = np.zeros((2, N), np.int32)
+    plan256.polymul(a, a)
+    assert gpu.last_launch_count() >= 1
+
+
+def test_golden_fixture_and_kats(golden, plan256):
+    assert (plan256.polymul(golden["fixture_a"], golden["fixture_b"])[0] == golden["fixture_c"]).all()
+    assert (plan256.polymul(golden["kat_a"], golden["kat_b"]) == golden["kat_c"]).all()
+
+
+def test_golden_random_rows(golden, plan256):
+    assert (plan256.polymul(golden["rand_a"], golden["rand_b"]) == golden["rand_c"]).all()
+
+
+def test_product_does_not_depend_on_psi(gpu, golden):
+    for psi in (0, 3, 1002, 10805):
+        p = gpu.Plan(N, Q, psi)
+        assert (p.polymul(golden["rand_a"][:8], golden["rand_b"][:8]) == golden["rand_c"][:8]).all()
+        p.close()
+
+
+@pytest.mark.parametrize("batch", [1, 2, 3, 15, 16, 17, 31, 33, 1000])
+def test_ragged_batches(plan256, oracle, batch):
+    a, b = oracle.random((batch, N), Q, SEED + batch), oracle.random((batch, N), Q, SEED - batch)
+    assert (plan256.polymul(a, b) == oracle.product(N, Q, a, b, 10, PSI)).all()
+
+
+def test_empty_batch(plan256):
+    out = plan256.polymul(np.zeros((0, N), np.int32), np.zeros((0, N), np.int32))
+    assert out.shape == (0, N)
+
+
+def test_inputs_are_left_untouched(plan256, oracle):
+    a, b = oracle.random((4, N), Q, 1), oracle.random((4, N), Q, 2)
+    a0, b0 = a.copy(), b.copy()
+    plan256.polymul(a, b)
+    assert (a == a0).all() and (b == b0).all()
+
+
+def test_config2_batch_2e16_vs_all_four_reference_variants(plan256, oracle, loader):
+    """BASELINE config 2: batch 2^16 at the reference default (n,q), bit-exact vs all four C variants."""
+    batch = 1 << 16
+    a, b = oracle.random((batch, N), Q, SEED + 2), oracle.random((batch, N), Q, SEED + 102)
+    a[0], b[0] = 0, 0
+    a[1], b[1] = Q - 1, Q - 1
+    a[2], b[2] = 0, 0
+    a[2][0], b[2][N - 1] = 1, 1
+    got = plan256.polymul(a, b)
+    if loader.reference_available():
+        ref = loader.Reference()
+        for v in (loader.REF_CT, loader.REF_GS, loader.REF_RED_CT, loader.REF_RED_GS):
+            assert (ref.product(a, b, v) == got).all(), v
+    else:                                   # never on the build box; keeps the test meaningful elsewhere
+        assert (oracle.product(N, Q, a[:4096], b[:4096], 10, PSI) == got[:4096]).all()
+    assert got.min() >= 0 and got.max() < Q
+
+
+@pytest.mark.parametrize("n,q", SMALL_CASES)
+def test_products_other_sizes_and_moduli(gpu, oracle, n, q):
+    batch = 67
+    p = gpu.Plan(n, q)
+    a, b = oracle.random((batch, n), q, SEED + n), oracle.random((batch, n), q, SEED + q)
+    a[0], b[0] = 0, 0
+    a[1], b[1] = q - 1, q - 1
+    a[2] = 0
+    a[2][0] = 1                                          # delta_0 * b = b
+    a[3], b[3] = 0, 0
+    a[3][n - 1], b[3][n - 1] = 1, 1                      # x^(n-1) x^(n-1) = -x^(n-2)
+    got = p.polymul(a, b)
+    want = oracle.product(n, q, a, b, 10)
+    assert (got == want).all(), p.describe()
+    assert (got[2] == b[2]).all()
+    assert got[3][n - 2] == q - 1 and got[3].sum() == q - 1
+    if n <= 256:
+        assert (oracle.product(n, q, a[:8], b[:8], 20) == got[:8]).all()     # O(n^2) definition
+    p.close()
+
+
+@pytest.mark.parametrize("n,q", [(256, 12289), (256, 7681), (1024, 12289), (512, 12289), (128, 3329),
+                                 (256, 998244353), (256, 2013265921)])
+def test_standalone_transforms_match_reference_functions(gpu, oracle, loader, n, q):
+    psi = 1002 if (n, q) == (256, 12289) else 0
+    p = gpu.Plan(n, q, psi)
+    psi = p.psi
+    a = oracle.random((37, n), q, SEED + 5 * n + q)
+    a[0] = 0
+    a[1] = q - 1
+    T = lambda k: oracle.table(k, n, q, psi)
+    checks = [
+        ("ntt_std2rev", "ntt_ct_std2rev", loader.OMEGA_POWERS_REV),
+        ("ntt_std2rev", "ntt_gs_std2rev", loader.OMEGA_POWERS),
+        ("mulntt_std2rev", "mulntt_ct_std2rev", loader.MIXED_POWERS_REV),
+        ("intt_rev2std", "ntt_gs_rev2std", loader.INV_OMEGA_POWERS_REV),
+        ("intt_rev2std", "ntt_ct_rev2std", loader.INV_OMEGA_POWERS),
+        ("inttmul_rev2std", "nttmul_gs_rev2std", loader.INV_MIXED_POWERS_REV),
+        ("intt_std2rev", "ntt_ct_std2rev", loader.INV_OMEGA_POWERS_REV),
+        ("intt_std2rev", "ntt_gs_std2rev", loader.INV_OMEGA_POWERS),
+        ("ntt_rev2std", "ntt_ct_rev2std", loader.OMEGA_POWERS),
+        ("ntt_rev2std", "ntt_gs_rev2std", loader.OMEGA_POWERS_REV),
+    ]
+    for kind, fn, tab in checks:
+        assert (p.transform(kind, a) == oracle.transform(fn, a, T(tab), q)).all(), (kind, fn)
+    ninv = pow(n, q - 2, q)
+    for kind, fn, tab in (("intt_rev2std_scaled", "ntt_gs_rev2std", loader.INV_OMEGA_POWERS_REV),
+                          ("inttmul_rev2std_scaled", "nttmul_gs_rev2std", loader.INV_MIXED_POWERS_REV)):
+        want = oracle.transform(fn, a, T(tab), q).astype(np.int64) * ninv % q
+        assert (p.transform(kind, a) == want).all(), kind
+    # round trip: intt(ntt(a)) = n * a   (R/NTT/ntt256.h:16-17)
+    back = p.transform("intt_rev2std", p.transform("ntt_std2rev", a))
+    assert (back == a.astype(np.int64) * n % q).all()
+    back = p.transform("inttmul_rev2std_scaled", p.transform("mulntt_std2rev", a))
+    assert (back == a).all()
+    p.close()
+
+
+def test_standalone_transforms_golden(golden, plan256):
+    a = golden["rand_a"][:16]
+    assert (plan256.transform("ntt_std2rev", a) == golden["transform_2"]).all()
+    assert (plan256.transform("ntt_std2rev", a) == golden["transform_3"]).all()
+    assert (plan256.transform("mulntt_std2rev", a) == golden["transform_9"]).all()
+    assert (plan256.transform("intt_rev2std", a) == golden["transform_5"]).all()
+    assert (plan256.transform("intt_rev2std", a) == golden["transform_4"]).all()
+    assert (plan256.transform("inttmul_rev2std", a) == golden["transform_10"]).all()
+    assert (plan256.transform("intt_std2rev", a) == golden["transform_6"]).all()
+    assert (plan256.transform("ntt_rev2std", a) == golden["transform_0"]).all()
+    assert (plan256.transform("ntt_rev2std", a) == golden["transform_1"]).all()
+
+
+def test_hw_golden_vectors_q7681(gpu, hw_golden):
+    """Verilog testbench vectors (q=7681, omega=0xf04): NTT_DOUT = gs_std2rev(NTT_DIN)."""
+    n, q, w = 256, 7681, int(hw_golden["PARAM"][2])
+    psi = int(hw_golden["PARAM"][4])
+    p = gpu.Plan(n, q, psi)
+    assert p.psi * p.psi % q == w
+    out = p.transform("ntt_std2rev", hw_golden["NTT_DIN"].astype(np.int32))
+    assert (out[0] == hw_golden["NTT_DOUT"]).all()
+    iout = p.transform("intt_std2rev", hw_golden["INTT_DIN"].astype(np.int32)).astype(np.int64)
+    assert (iout[0] * pow(n, q - 2, q) % q == hw_golden["INTT_DOUT"]).all()
+    p.close()
+
+
+@pytest.mark.parametrize("df,fn", [("ct_std2rev", "ntt_ct_std2rev"), ("gs_rev2std", "ntt_gs_rev2std"),
+                                    ("ct_rev2std", "ntt_ct_rev2std"), ("gs_std2rev", "ntt_gs_std2rev")])
+def test_table_driven_dataflows(gpu, oracle, df, fn):
+    """nttb200_ntt_table_batch: the reference dataflow with an ARBITRARY caller table."""
+    for n, q in ((256, 12289), (64, 257), (2048, 12289)):
+        tab = oracle.random((n,), q, SEED + n).astype(np.uint32)      # not even roots of unity
+        a = oracle.random((5, n), q, SEED + 7)
+        assert (gpu.ntt_table_batch(n, q, df, tab, a) == oracle.transform(fn, a, tab, q)).all(), (n, q)
+
+
+def test_legacy_surface(gpu, golden, oracle):
+    """The reference's own function names, one polynomial per call."""
+    fa, fb, fc = golden["fixture_a"], golden["fixture_b"], golden["fixture_c"]
+    for name in ("ntt256_product1", "ntt256_product4", "ntt_red256_product1", "ntt_red256_product4"):
+        c, a_after, b_after = gpu.legacy.product(name, fa, fb)
+        assert (c == fc).all(), name
+        assert (a_after == fa).all() and (b_after == fb).all()
+    # opt-in reference post-state of a, b
+    c, a_after, b_after = gpu.legacy.product("ntt256_product1", golden["rand_a"][4], golden["rand_b"][4], clobber=True)
+    assert (c == golden["rand_c"][4]).all()
+    assert (a_after == golden["clobber_a_after_product1"]).all()
+    assert (b_after == golden["clobber_b_after_product1"]).all()
+    a = golden["rand_a"][0:16]
+    names = {0: ("ntt_ct_rev2std", 3), 1: ("ntt_gs_rev2std", 4), 2: ("ntt_ct_std2rev", 4), 3: ("ntt_gs_std2rev", 3),
+             4: ("ntt_ct_rev2std", 5), 5: ("ntt_gs_rev2std", 6), 6: ("ntt_ct_std2rev", 6), 7: ("ntt_gs_std2rev", 5),
+             8: ("mulntt_ct_rev2std", 7), 9: ("mulntt_ct_std2rev", 8), 10: ("nttmul_gs_rev2std", 10),
+             11: ("nttmul_gs_std2rev", 9), 12: ("ntt_ct_rev2std_v1", 0)}
+    for tid, (fn, kind) in names.items():
+        got = gpu.legacy.transform(fn, a[5], golden[f"table_{kind}"])
+        assert (got == golden[f"transform_{tid}"][5]).all(), fn
+    x, y = golden["rand_a"][7], golden["rand_b"][7]
+    assert (gpu.legacy.mul_array(x, y) == x.astype(np.int64) * y % Q).all()
+    assert (gpu.legacy.mul_array16(x, golden["table_0"]) == x.astype(np.int64) * golden["table_0"] % Q).all()
+    assert (gpu.legacy.scalar_mul_array(x, 12241) == x.astype(np.int64) * 12241 % Q).all()
+
+
+def test_elementwise_batch(gpu, oracle):
+    for n, q in ((256, 12289), (1024, 2013265921)):
+        p = gpu.Plan(n, q)
+        a, b = oracle.random((9, n), q, 3), oracle.random((9, n), q, 4)
+        assert (p.mul_array(a, b) == a.astype(np.int64) * b % q).all()
+        assert (p.scalar_mul_array(a, q - 2) == a.astype(np.int64) * (q - 2) % q).all()
+        p.close()
+
+
+def test_cyclic_plan_q3329(gpu, oracle):
+    """q=3329 (Kyber): no 512-th root of unity -> the psi-free surface, product mod x^256 - 1."""
+    with pytest.raises(gpu.NttError):
+        gpu.Plan(256, 3329)
+    p = gpu.Plan(256, 3329, cyclic=True)
+    a, b = oracle.random((33, 256), 3329, 5), oracle.random((33, 256), 3329, 6)
+    assert (p.polymul(a, b) == oracle.product(256, 3329, a, b, 30)).all()
+    p.close()
+
+
+def _dev_buffers(torch, *arrays):
+    return [torch.from_numpy(x).cuda() for x in arrays]
+
+
+@pytest.mark.parametrize("n,q,logb", [(256, 12289, 20), (256, 7681, 20), (1024, 12289, 18)])
+def test_full_size_batches_properties(gpu, oracle, n, q, logb):
+    """BASELINE configs 3/4 at full batch, device-resident: sampled rows against the oracle plus
+    size-independent properties (commutativity, linearity in a, delta rows)."""
+    import torch
+    batch = 1 << logb
+    p = gpu.Plan(n, q)
+    g = torch.Generator(device="cuda").manual_seed(1234 + n + q)
+    a = torch.randint(0, q, (batch, n), dtype=torch.int32, device="cuda", generator=g)
+    b = torch.randint(0, q, (batch, n), dtype=torch.int32, device="cuda", generator=g)
+    a[0].zero_(); b[1].fill_(q - 1); a[1].fill_(q - 1)
+    a[2].zero_(); a[2, 0] = 1
+    c = torch.empty_like(a)
+    st = torch.cuda.current_stream().cuda_stream
+    p.polymul_dev(c.data_ptr(), a.data_ptr(), b.data_ptr(), batch, st)
+    torch.cuda.synchronize()
+    assert int(c.min()) >= 0 and int(c.max()) < q
+    assert bool((c[0] == 0).all()) and bool((c[2] == b[2]).all())
+    idx = np.unique(np.concatenate([np.arange(0, 8), np.random.default_rng(1).integers(0, batch, 2048),
+                                    np.arange(batch - 8, batch)]))
+    ti = torch.from_numpy(idx).cuda()
+    want = oracle.product(n, q, a[ti].cpu().numpy(), b[ti].cpu().numpy(), 10)
+    assert (c[ti].cpu().numpy() == want).all()
+    # commutativity on the whole batch
+    c2 = torch.empty_like(a)
+    p.polymul_dev(c2.data_ptr(), b.data_ptr(), a.data_ptr(), batch, st)
+    torch.cuda.synchronize()
+    assert bool((c == c2).all())
+    # linearity: (a + a') * b = a*b + a'*b  with a' = a rolled by one row
+    a2 = torch.roll(a, 1, 0)
+    s = ((a.long() + a2.long()) % q).int()
+    cs = torch.empty_like(a)
+    p.polymul_dev(cs.data_ptr(), s.data_ptr(), b.data_ptr(), batch, st)
+    p.polymul_dev(c2.data_ptr(), a2.data_ptr(), b.data_ptr(), batch, st)
+    torch.cuda.synchronize()
+    assert bool((cs.long() == (c.long() + c2.long()) % q).all())
+    p.close()
+
+
+def test_kernels_cross_check_fused_vs_literal_dataflow(gpu, oracle):
+    """The fused register/smem kernel against the one-stage-per-launch literal dataflow
+    kernels (both on the GPU), n=1024."""
+    n, q = 1024, 12289
+    p = gpu.Plan(n, q)
+    a = oracle.random((300, n), q, 77)
+    fused = p.transform("mulntt_std2rev", a)
+    literal = gpu.ntt_table_batch(n, q, "ct_std2rev", gpu.make_table("mixed_powers_rev", n, q, p.psi), a)
+    assert (fused == literal).all()
+    p.close()
