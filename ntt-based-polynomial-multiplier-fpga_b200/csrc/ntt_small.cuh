@@ -487,6 +487,7 @@ ntt_small_kernel(const __grid_constant__ SmallParams<SmallGeom<L>::R> P) {
         for (int k = 0; k < Gm::NV; k++) {
           if (k & (1 << (Gm::R - 1))) x[k] = csub(x[k], m.q);          /* diff branch: < 2q */
           else if (ARITH == ARITH_LAZY) x[k] = reduce_any(x[k], one_p, m);
+          else if (ARITH == ARITH_HARVEY) x[k] = csub(x[k], m.q);      /* sum branch: < 2q  */
         }
       }
       __syncwarp();
