@@ -1,0 +1,156 @@
+/*
+ * large_dispatch.inl -- instantiates the multi-pass kernels of ntt_large.cuh (n = 2^11 ..
+ * 2^17, rows of 256 coefficients) for ONE arithmetic class (LARGE_ARITH) and defines its
+ * dispatch functions.  Included by large_lazy.cu, large_harvey.cu and large_canon.cu.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+#include "ntt_large.cuh"
+#include "plan.h"
+
+namespace {
+using namespace nttb200;
+
+constexpr int LR = 8;           /* row length 2^LR */
+constexpr int ROW_WARPS = 8;
+
+inline uint2 lshoup_pair(uint64_t w, uint32_t q) {
+  w %= q;
+  return make_uint2((uint32_t)w, (uint32_t)((w << 32) / q));
+}
+
+void fill_common(LargeParams &p, const nttb200_plan *P, const DevTable *fwd, const DevTable *inv,
+                 size_t batch) {
+  p.tab = fwd ? fwd->d : nullptr;
+  p.tab_inv = inv ? inv->d : nullptr;
+  p.batch = batch;
+  p.logn = P->logn;
+  p.nops = 1;
+  p.m = P->m;
+  p.one = lshoup_pair(1, P->q);
+  p.last_x = p.one;
+  p.last_y = inv ? inv->h[1] : p.one;
+}
+
+template <int K1>
+int cols_fwd(const nttb200_plan *P, LargeParams &p, cudaStream_t st) {
+  using G = ColGeom<K1>;
+  auto kernel = large_cols_fwd_kernel<K1, LARGE_ARITH>;
+  if (G::SMEM_BYTES > 48 * 1024)
+    NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+  const unsigned long long grid = p.batch * p.nops * (1ull << (P->logn - K1 - 5));
+  if (grid > 0x7fffffffull) return nttb200_fail(NTTB200_EPARAM, "batch too large for one launch");
+  kernel<<<(unsigned)grid, G::WARPS * 32, G::SMEM_BYTES, st>>>(p);
+  nttb200_count_launch(1);
+  NTT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int K1>
+int cols_inv(const nttb200_plan *P, LargeParams &p, cudaStream_t st) {
+  using G = ColGeom<K1>;
+  auto kernel = large_cols_inv_kernel<K1, LARGE_ARITH>;
+  if (G::SMEM_BYTES > 48 * 1024)
+    NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+  const unsigned long long grid = p.batch * (1ull << (P->logn - K1 - 5));
+  if (grid > 0x7fffffffull) return nttb200_fail(NTTB200_EPARAM, "batch too large for one launch");
+  kernel<<<(unsigned)grid, G::WARPS * 32, G::SMEM_BYTES, st>>>(p);
+  nttb200_count_launch(1);
+  NTT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+#define LARGE_K1_SWITCH(fn, ...)                                                   \
+  switch (P->logn - LR) {                                                          \
+    case 3: return fn<3>(__VA_ARGS__);                                             \
+    case 4: return fn<4>(__VA_ARGS__);                                             \
+    case 5: return fn<5>(__VA_ARGS__);                                             \
+    case 6: return fn<6>(__VA_ARGS__);                                             \
+    case 7: return fn<7>(__VA_ARGS__);                                             \
+    case 8: return fn<8>(__VA_ARGS__);                                             \
+    case 9: return fn<9>(__VA_ARGS__);                                             \
+    default: return nttb200_fail(NTTB200_EPARAM, "multi-pass kernels cover 2^11 <= n <= 2^17"); \
+  }
+
+int cols_fwd_any(const nttb200_plan *P, LargeParams &p, cudaStream_t st) { LARGE_K1_SWITCH(cols_fwd, P, p, st) }
+int cols_inv_any(const nttb200_plan *P, LargeParams &p, cudaStream_t st) { LARGE_K1_SWITCH(cols_inv, P, p, st) }
+
+unsigned long long row_grid(const nttb200_plan *P, size_t batch) {
+  using Gm = SmallGeom<LR>;
+  const unsigned long long groups = (batch + ROW_WARPS * Gm::PPW - 1) / (ROW_WARPS * Gm::PPW);
+  return groups << (P->logn - LR);
+}
+
+int rows_polymul(const nttb200_plan *P, LargeParams &p, cudaStream_t st) {
+  using Gm = SmallGeom<LR>;
+  auto kernel = large_rows_polymul_kernel<LR, LARGE_ARITH, ROW_WARPS>;
+  const int smem = ROW_WARPS * 2 * Gm::PPW * Gm::STRIDE * (int)sizeof(uint32_t);
+  NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const unsigned long long grid = row_grid(P, p.batch);
+  if (grid > 0x7fffffffull) return nttb200_fail(NTTB200_EPARAM, "batch too large for one launch");
+  kernel<<<(unsigned)grid, ROW_WARPS * 32, smem, st>>>(p);
+  nttb200_count_launch(1);
+  NTT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int DIR>
+int rows_ntt(const nttb200_plan *P, LargeParams &p, cudaStream_t st) {
+  using Gm = SmallGeom<LR>;
+  auto kernel = large_rows_ntt_kernel<LR, LARGE_ARITH, ROW_WARPS, DIR>;
+  const int smem = ROW_WARPS * Gm::PPW * Gm::STRIDE * (int)sizeof(uint32_t);
+  const unsigned long long grid = row_grid(P, p.batch);
+  if (grid > 0x7fffffffull) return nttb200_fail(NTTB200_EPARAM, "batch too large for one launch");
+  kernel<<<(unsigned)grid, ROW_WARPS * 32, smem, st>>>(p);
+  nttb200_count_launch(1);
+  NTT_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
+#define LARGE_CAT2(a, b) a##b
+#define LARGE_CAT(a, b) LARGE_CAT2(a, b)
+
+/* one batch chunk of the product: ta/tb = scratch for a', b' (c' reuses ta) */
+int LARGE_CAT(launch_polymul_large_chunk_, LARGE_NAME)(const nttb200_plan *P, uint32_t *c, const uint32_t *a,
+                                                       const uint32_t *b, uint32_t *ta, uint32_t *tb,
+                                                       size_t batch, cudaStream_t st) {
+  const bool cyclic = (P->flags & NTTB200_PLAN_CYCLIC) != 0;
+  const DevTable &fwd = cyclic ? P->fwd_plain : P->fwd_mixed;
+  const DevTable &inv = cyclic ? P->inv_plain : P->inv_mixed;
+  LargeParams p{};
+  fill_common(p, P, &fwd, &inv, batch);
+  int rc;
+  p.src[0] = a; p.src[1] = b; p.dst[0] = ta; p.dst[1] = tb; p.nops = 2;
+  if ((rc = cols_fwd_any(P, p, st))) return rc;
+  p.src[0] = ta; p.src[1] = tb; p.dst[0] = ta; p.dst[1] = nullptr; p.nops = 1;
+  if ((rc = rows_polymul(P, p, st))) return rc;
+  /* n^-1 * 2^32: the 2^32 cancels the Montgomery 2^-32 of the pointwise product */
+  const uint64_t fs = (uint64_t)P->n_inv * ((1ull << 32) % P->q) % P->q;
+  p.last_x = lshoup_pair(fs, P->q);
+  p.last_y = lshoup_pair(fs * inv.h[1].x, P->q);
+  p.src[0] = ta; p.dst[0] = c;
+  return cols_inv_any(P, p, st);
+}
+
+/* standalone transform in place on a: dir 0 = forward CT std->rev with `tab`, dir 1 = inverse
+ * GS rev->std; scale = multiply by n^-1 (inverse only).  Canonical output. */
+int LARGE_CAT(launch_ntt_large_, LARGE_NAME)(const nttb200_plan *P, const DevTable &tab, int dir, int scale,
+                                             uint32_t *a, size_t batch, cudaStream_t st) {
+  LargeParams p{};
+  fill_common(p, P, dir == 0 ? &tab : nullptr, dir == 1 ? &tab : nullptr, batch);
+  p.src[0] = a; p.dst[0] = a;
+  int rc;
+  if (dir == 0) {
+    if ((rc = cols_fwd_any(P, p, st))) return rc;
+    return rows_ntt<0>(P, p, st);
+  }
+  if ((rc = rows_ntt<1>(P, p, st))) return rc;
+  if (scale) {
+    p.last_x = lshoup_pair(P->n_inv, P->q);
+    p.last_y = lshoup_pair((uint64_t)P->n_inv * tab.h[1].x, P->q);
+  }
+  return cols_inv_any(P, p, st);
+}

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -321,8 +322,30 @@ static int transform_dev(nttb200_plan *P, int transform, uint32_t *a, size_t bat
 }
 
 /* ------------------------------------------------------------------------------------ */
-/* large n (first version): literal stage-per-launch dataflow on scratch copies           */
+/* large n: multi-pass kernels (ntt_large.cuh), batch processed in chunks whose scratch     */
+/* (a', b' between the passes) stays L2-resident                                          */
 /* ------------------------------------------------------------------------------------ */
+#define DECL_LARGE(name)                                                                          \
+  int launch_polymul_large_chunk_##name(const nttb200_plan *, uint32_t *, const uint32_t *,       \
+                                        const uint32_t *, uint32_t *, uint32_t *, size_t, cudaStream_t); \
+  int launch_ntt_large_##name(const nttb200_plan *, const DevTable &, int, int, uint32_t *, size_t, \
+                              cudaStream_t);
+DECL_LARGE(lazy)
+DECL_LARGE(harvey)
+DECL_LARGE(canon)
+
+static size_t large_scratch_budget() {
+  /* bytes of scratch (a' + b') per chunk; default 32 MiB = a quarter of the 126 MB L2 */
+  static size_t v = 0;
+  if (!v) {
+    const char *e = getenv("NTTB200_LARGE_SCRATCH_MB");
+    long mb = e ? atol(e) : 32;
+    if (mb < 1) mb = 1;
+    v = (size_t)mb << 20;
+  }
+  return v;
+}
+
 static int ensure_scratch(nttb200_plan *P, size_t polys) {
   if (P->scratch_polys >= polys) return 0;
   if (P->scratch) cudaFree(P->scratch);
@@ -334,39 +357,31 @@ static int ensure_scratch(nttb200_plan *P, size_t polys) {
 
 int launch_polymul_large(nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b, size_t batch,
                          cudaStream_t st) {
-  using namespace nttb200;
-  const bool cyclic = (P->flags & NTTB200_PLAN_CYCLIC) != 0;
-  const DevTable &fwd = cyclic ? P->fwd_plain : P->fwd_mixed;
-  const DevTable &inv = cyclic ? P->inv_plain : P->inv_mixed;
-  const size_t chunk = std::max<size_t>(1, std::min<size_t>(batch, (256u << 20) / (P->n * 8)));
+  /* the scratch is per plan: concurrent device-resident calls on one plan must use one stream */
+  const size_t chunk = std::max<size_t>(1, std::min<size_t>(batch, large_scratch_budget() / (P->n * 8ull)));
   int rc = ensure_scratch(P, chunk);
   if (rc) return rc;
-  const uint64_t r1 = (1ull << 32) % P->q;
-  const uint32_t r2m = (uint32_t)(r1 * r1 % P->q);
+  uint32_t *ta = P->scratch, *tb = P->scratch + chunk * P->n;
   for (size_t done = 0; done < batch; done += chunk) {
     const size_t nb = std::min(chunk, batch - done);
-    const size_t words = nb * P->n;
-    uint32_t *ta = P->scratch, *tb = P->scratch + chunk * P->n;
-    NTT_CUDA(cudaMemcpyAsync(ta, a + done * P->n, words * 4, cudaMemcpyDeviceToDevice, st));
-    NTT_CUDA(cudaMemcpyAsync(tb, b + done * P->n, words * 4, cudaMemcpyDeviceToDevice, st));
-    if ((rc = launch_generic_transform(P->n, P->logn, P->m, DF_CT_STD2REV, fwd.d, ta, nb, st))) return rc;
-    if ((rc = launch_generic_transform(P->n, P->logn, P->m, DF_CT_STD2REV, fwd.d, tb, nb, st))) return rc;
-    uint32_t *tc = c + done * P->n;
-    if ((rc = launch_pointwise(tc, ta, tb, words, P->m, r2m, st))) return rc;
-    if ((rc = launch_generic_transform(P->n, P->logn, P->m, DF_GS_REV2STD, inv.d, tc, nb, st))) return rc;
-    if ((rc = launch_scale(tc, nullptr, pair_of(P->n_inv, P->q), P->n, words, P->m, st))) return rc;
+    const size_t o = done * P->n;
+    switch (P->arith) {
+      case ARITH_LAZY: rc = launch_polymul_large_chunk_lazy(P, c + o, a + o, b + o, ta, tb, nb, st); break;
+      case ARITH_HARVEY: rc = launch_polymul_large_chunk_harvey(P, c + o, a + o, b + o, ta, tb, nb, st); break;
+      default: rc = launch_polymul_large_chunk_canon(P, c + o, a + o, b + o, ta, tb, nb, st); break;
+    }
+    if (rc) return rc;
   }
   return 0;
 }
 
 int launch_ntt_large(nttb200_plan *P, const DevTable &tab, int dir, int scale, uint32_t *a, size_t batch,
                      cudaStream_t st) {
-  using namespace nttb200;
-  int rc = launch_generic_transform(P->n, P->logn, P->m, dir == 0 ? DF_CT_STD2REV : DF_GS_REV2STD, tab.d,
-                                    a, batch, st);
-  if (rc) return rc;
-  if (scale) rc = launch_scale(a, nullptr, pair_of(P->n_inv, P->q), P->n, batch * P->n, P->m, st);
-  return rc;
+  switch (P->arith) {
+    case ARITH_LAZY: return launch_ntt_large_lazy(P, tab, dir, scale, a, batch, st);
+    case ARITH_HARVEY: return launch_ntt_large_harvey(P, tab, dir, scale, a, batch, st);
+    default: return launch_ntt_large_canon(P, tab, dir, scale, a, batch, st);
+  }
 }
 
 /* ------------------------------------------------------------------------------------ */

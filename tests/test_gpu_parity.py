@@ -106,6 +106,84 @@ def test_products_other_sizes_and_moduli(gpu, oracle, n, q):
     p.close()
 
 
+LARGE_CASES = [(2048, 12289), (4096, 40961), (8192, 65537), (16384, 65537),      # LAZY class
+               (2048, 8380417), (32768, 786433), (65536, 786433), (65536, 469762049),  # HARVEY class
+               (2048, 2013265921), (65536, 2013265921), (131072, 2013265921)]     # CANON class
+
+
+@pytest.mark.parametrize("n,q", LARGE_CASES)
+def test_large_n_multipass_products(gpu, oracle, n, q):
+    """n > 1024: column pass / row pass / column pass (ntt_large.cuh) against the oracle's
+    merged CT-fwd/GS-inv pipeline; ragged batch (odd, not a multiple of the CTA's 16 rows)."""
+    batch = 21 if n <= 16384 else 5
+    p = gpu.Plan(n, q)
+    assert "large(multi-pass)" in p.describe()
+    a, b = oracle.random((batch, n), q, SEED + n), oracle.random((batch, n), q, SEED + q)
+    a[0], b[0] = 0, 0
+    a[1], b[1] = q - 1, q - 1
+    a[2] = 0
+    a[2][0] = 1
+    a[3], b[3] = 0, 0
+    a[3][n - 1], b[3][n - 1] = 1, 1
+    got = p.polymul(a, b)
+    want = oracle.product(n, q, a, b, 10)
+    assert (got == want).all(), p.describe()
+    assert (got[2] == b[2]).all()
+    assert got[3][n - 2] == q - 1 and int(got[3].astype(np.int64).sum()) == q - 1
+    assert gpu.last_launch_count() == 3
+    p.close()
+
+
+@pytest.mark.parametrize("n,q", [(2048, 12289), (16384, 65537), (65536, 469762049), (65536, 2013265921)])
+def test_large_n_standalone_transforms(gpu, oracle, loader, n, q):
+    p = gpu.Plan(n, q)
+    psi = p.psi
+    a = oracle.random((3, n), q, SEED + 3 * n + q)
+    a[1] = q - 1
+    T = lambda k: oracle.table(k, n, q, psi)
+    checks = [
+        ("ntt_std2rev", "ntt_ct_std2rev", loader.OMEGA_POWERS_REV),
+        ("mulntt_std2rev", "mulntt_ct_std2rev", loader.MIXED_POWERS_REV),
+        ("intt_rev2std", "ntt_gs_rev2std", loader.INV_OMEGA_POWERS_REV),
+        ("inttmul_rev2std", "nttmul_gs_rev2std", loader.INV_MIXED_POWERS_REV),
+        ("intt_std2rev", "ntt_ct_std2rev", loader.INV_OMEGA_POWERS_REV),
+        ("ntt_rev2std", "ntt_gs_rev2std", loader.OMEGA_POWERS_REV),
+    ]
+    for kind, fn, tab in checks:
+        assert (p.transform(kind, a) == oracle.transform(fn, a, T(tab), q)).all(), (kind, fn)
+    back = p.transform("inttmul_rev2std_scaled", p.transform("mulntt_std2rev", a))
+    assert (back == a).all()
+    p.close()
+
+
+def test_config5_full_batch_properties(gpu, oracle):
+    """BASELINE config 5: n=2^16, 31-bit prime, batch 2^10, device-resident: sampled rows against
+    the oracle, delta rows, commutativity over the whole batch."""
+    import torch
+    n, q, batch = 65536, 2013265921, 1 << 10
+    p = gpu.Plan(n, q)
+    g = torch.Generator(device="cuda").manual_seed(99)
+    a = torch.randint(0, q, (batch, n), dtype=torch.int32, device="cuda", generator=g)
+    b = torch.randint(0, q, (batch, n), dtype=torch.int32, device="cuda", generator=g)
+    a[0].zero_(); a[1].fill_(q - 1); b[1].fill_(q - 1)
+    a[2].zero_(); a[2, 0] = 1
+    c = torch.empty_like(a)
+    st = torch.cuda.current_stream().cuda_stream
+    p.polymul_dev(c.data_ptr(), a.data_ptr(), b.data_ptr(), batch, st)
+    torch.cuda.synchronize()
+    assert int(c.min()) >= 0 and int(c.max()) < q
+    assert bool((c[0] == 0).all()) and bool((c[2] == b[2]).all())
+    idx = np.array([1, 3, 63, 64, 65, 500, batch - 1])
+    ti = torch.from_numpy(idx).cuda()
+    want = oracle.product(n, q, a[ti].cpu().numpy(), b[ti].cpu().numpy(), 10)
+    assert (c[ti].cpu().numpy() == want).all()
+    c2 = torch.empty_like(a)
+    p.polymul_dev(c2.data_ptr(), b.data_ptr(), a.data_ptr(), batch, st)
+    torch.cuda.synchronize()
+    assert bool((c == c2).all())
+    p.close()
+
+
 @pytest.mark.parametrize("n,q", [(256, 12289), (256, 7681), (1024, 12289), (512, 12289), (128, 3329),
                                  (256, 998244353), (256, 2013265921)])
 def test_standalone_transforms_match_reference_functions(gpu, oracle, loader, n, q):
