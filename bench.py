@@ -44,6 +44,11 @@ WORKLOADS = {
     "c4": (1024, 12289, 0, 18, "BASELINE configs[3] (Falcon/NewHope-like): n=1024 q=12289 batch 2^18"),
     "c5": (65536, 2013265921, 0, 10, "BASELINE configs[4]: n=2^16 q=2013265921 batch 2^10, multi-pass"),
 }
+# DRAM bytes (read + write) per launch of the dominant kernel, from `ncu --set full` captures
+# committed under profiles/ (a profiler run is never a bench value; this is the traffic only)
+TRAFFIC_NCU = {"c2": 175037696}
+TRAFFIC_SRC = {"c2": "profiles/r1_c2_polymul_n256_v1_ncu_full.txt: dram__bytes_read.sum 134.29 MB + "
+                     "dram__bytes_write.sum 40.75 MB per launch (algorithmic 201.3 MB; part of c stays dirty in L2)"}
 SEED = 0x4E545442323030
 L2_BYTES = 126 * 1000 * 1000
 
@@ -343,13 +348,24 @@ def main() -> int:
 
     peak_gbs, peak_src = measured_peaks()
     alg_bytes = 12 * n * batch                      # read a, read b, write c (int32 API)
-    achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
+    # n <= 1024: one fused kernel per step.  n > 1024: the step is a pipeline of 3 kernels per
+    # L2-resident batch chunk; the roofline is then stated for the whole pipeline (step time).
+    roof_ms = per_launch_ms if launches_per_step == 1 else min(launch_ms, ms_local / args.steps)
+    achieved = alg_bytes / (roof_ms * 1e-3) / 1e9
     logn = n.bit_length() - 1
-    modmuls = 3 * (n // 2) * logn + n               # M
+    bflies = 3 * (n // 2) * logn
+    modmuls = bflies + n                            # M
+    # fmaheavy issue slots per product as the kernels are written: Shoup butterfly = IMAD.HI
+    # (2 slots: measured half rate) + 2 IMAD; pointwise Montgomery = 2 IMAD.HI + 2 IMAD; the
+    # n^-1 scaling costs one extra Shoup multiplication on the sum branch of the last stage
+    slots = 4 * bflies + 6 * n + 4 * (n // 2)
     imad_peak = mod.measure_int_peak(0)
     imadhi_peak = mod.measure_int_peak(1)
     bfly_peak = mod.measure_int_peak(3)
-    int_achieved = (batch / (per_launch_ms * 1e-3)) * 3 * modmuls
+    rate = batch / (roof_ms * 1e-3)
+    int_achieved = rate * 3 * modmuls
+    slot_achieved = rate * slots
+    traffic = TRAFFIC_NCU.get(args.workload)
 
     line = {
         "metric": "polymul/s", "value": value, "unit": "polymul/s", "n_gpus": world,
@@ -367,15 +383,22 @@ def main() -> int:
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
-                     "kernel": "polymul_small_kernel" if n <= 1024 else "large multi-pass",
-                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms},
-        "int_roofline": {"bound": "imad-issue", "achieved": int_achieved, "peak": imad_peak,
-                         "unit": "IMAD lane-ops/s", "frac": int_achieved / imad_peak if imad_peak else None,
-                         "imad_per_polymul": 3 * modmuls, "imad_hi_peak": imadhi_peak,
-                         "lazy_butterflies_per_s_peak": bfly_peak,
-                         "note": "3 IMAD-class issues per modmul (Shoup), M = 3(n/2)log2(n)+n modmuls; peak "
-                                 "measured live by nttb200_measure_int_peak"},
+                     "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "polymul_small_kernel" if n <= 1024 else
+                               "large_cols_fwd + large_rows_polymul + large_cols_inv (whole step)",
+                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": roof_ms,
+                     "traffic_source": TRAFFIC_SRC.get(args.workload)},
+        "int_roofline": {"bound": "fmaheavy-issue (binding for this path: ncu sm__pipe_fmaheavy is the "
+                                  "top unit, see profiles/)",
+                         "achieved": slot_achieved, "peak": imad_peak, "unit": "IMAD-slot lane-ops/s",
+                         "frac": slot_achieved / imad_peak if imad_peak else None,
+                         "slots_per_polymul": slots,
+                         "survey_3_per_modmul": {"achieved": int_achieved, "imad_per_polymul": 3 * modmuls,
+                                                 "frac": int_achieved / imad_peak if imad_peak else None},
+                         "imad_hi_peak": imadhi_peak, "lazy_butterflies_per_s_peak": bfly_peak,
+                         "note": "peak = independent IMAD chains on every SM, measured live "
+                                 "(nttb200_measure_int_peak); IMAD.HI measured at half that rate so it "
+                                 "counts 2 slots: butterfly 4, pointwise 6, n^-1 scale 4 per pair"},
         "parity_ok": parity_ok,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

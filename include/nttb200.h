@@ -59,6 +59,9 @@ typedef struct nttb200_plan nttb200_plan;
                                   R/NTT/ntt256.h:28,37 + R/NTT/ntt.h:52).  `psi` is then read
                                   as omega (0 = smallest primitive n-th root).            */
 
+#define NTTB200_PLAN_NO_PLANTARD 2u /* diagnostics: products of half-word moduli (q <= 12385) use the
+                                      generic Shoup/Montgomery kernel instead of the Plantard one */
+
 /* n: power of two, 8 <= n <= 2^17.  q: odd prime < 2^31 with 2n | q-1 (n | q-1 when
  * CYCLIC).  psi: primitive 2n-th root of unity mod q, or 0 for the smallest one -- the
  * rule of Generator_Params/generate_params.C:25-44.  The reference's own tables use

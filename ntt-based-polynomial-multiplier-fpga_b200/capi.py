@@ -26,6 +26,7 @@ TABLES = {
     "inv_psi_powers_rev": 11,
 }
 PLAN_CYCLIC = 1
+PLAN_NO_PLANTARD = 2
 
 
 class NttError(RuntimeError):
@@ -181,9 +182,10 @@ def host_alloc(shape) -> _Pinned:
 class Plan:
     """One (n, q, psi) parameter set on the current CUDA device."""
 
-    def __init__(self, n: int, q: int, psi: int = 0, cyclic: bool = False) -> None:
+    def __init__(self, n: int, q: int, psi: int = 0, cyclic: bool = False, no_plantard: bool = False) -> None:
         h = C.c_void_p()
-        _check(lib().nttb200_plan_create(C.byref(h), n, q, psi, PLAN_CYCLIC if cyclic else 0))
+        flags = (PLAN_CYCLIC if cyclic else 0) | (PLAN_NO_PLANTARD if no_plantard else 0)
+        _check(lib().nttb200_plan_create(C.byref(h), n, q, psi, flags))
         self._h = h
         self.n, self.q = n, q
         self.psi = int(lib().nttb200_plan_psi(h))

@@ -58,6 +58,50 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *sink, uint32_t 
           asm volatile("add.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(a));
         } else if (WHICH == 7) {
           asm volatile("shfl.sync.bfly.b32 %0, %0, 1, 0x1f, 0xffffffff;" : "+r"(x[i]));
+        } else if (WHICH == 8) {
+          /* IMAD.WIDE with a 64-bit addend, result high word feeds the next one */
+          unsigned long long w, c;
+          asm volatile("mov.b64 %0, {%1, %2};" : "=l"(c) : "r"(b), "r"(y[i]));
+          asm volatile("mad.wide.s32 %0, %1, %2, %3;" : "=l"(w) : "r"(x[i]), "r"(a), "l"(c));
+          x[i] = (uint32_t)(w >> 32);
+        } else if (WHICH == 9) {
+          /* Plantard butterfly: p = Y*w~ ; T = hi(p*q + 2^31) ; X' = X+T ; Y' = X-T */
+          uint32_t p;
+          unsigned long long w;
+          asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(p) : "r"(y[i]), "r"(a));
+          unsigned long long half;
+          asm volatile("mov.b64 %0, {%1, %2};" : "=l"(half) : "r"(b), "r"(0));
+          asm volatile("mad.wide.s32 %0, %1, %2, %3;" : "=l"(w) : "r"(p), "r"(m.q), "l"(half));
+          uint32_t T = (uint32_t)(w >> 32);
+          asm volatile("sub.u32 %0, %1, %2;" : "=r"(y[i]) : "r"(x[i]), "r"(T));
+          asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(T));
+        } else if (WHICH == 10) {
+          /* signed Shoup with the add folded: s = Y*w + X ; t = hi(Y*w') ; X' = t*(-q) + s ; Y' = 2X - X' */
+          uint32_t s2, t, xn;
+          asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(s2) : "r"(y[i]), "r"(a), "r"(x[i]));
+          asm volatile("mul.hi.s32 %0, %1, %2;" : "=r"(t) : "r"(y[i]), "r"(b));
+          asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(xn) : "r"(t), "r"(m.nq), "r"(s2));
+          asm volatile("{ .reg .u32 tt; add.u32 tt, %1, %1; sub.u32 %0, tt, %2; }" : "=r"(y[i]) : "r"(x[i]), "r"(xn));
+          x[i] = xn;
+        } else if (WHICH == 11) {
+          /* Plantard butterfly, half-word form: 2 IMAD + 2 arithmetic shifts + 2 adds */
+          uint32_t p, u;
+          asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(p) : "r"(y[i]), "r"(a));
+          asm volatile("shr.s32 %0, %0, 16;" : "+r"(p));
+          asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(u) : "r"(p), "r"(m.q), "r"(m.q2));
+          asm volatile("shr.s32 %0, %0, 16;" : "+r"(u));
+          asm volatile("sub.u32 %0, %1, %2;" : "=r"(y[i]) : "r"(x[i]), "r"(u));
+          asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(u));
+        } else if (WHICH == 13) {
+          /* unsigned Plantard butterfly (q < 2^16): p = Y*w~ ; T = hi(p*q) in [0,q) ; Y' = X-T+q ; X' = X+T */
+          uint32_t p, T;
+          asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(p) : "r"(y[i]), "r"(a));
+          asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(T) : "r"(p), "r"(m.q));
+          asm volatile("{ .reg .u32 tt; sub.u32 tt, %1, %2; add.u32 %0, tt, %3; }" : "=r"(y[i]) : "r"(x[i]), "r"(T), "r"(m.q));
+          asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(T));
+        } else if (WHICH == 12) {
+          asm volatile("shr.s32 %0, %0, 1;" : "+r"(x[i]));
+          asm volatile("add.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(a));
         }
       }
     }
@@ -111,6 +155,12 @@ extern "C" int nttb200_measure_int_peak(int which, double *lane_ops_per_s) {
     case 5: return run<5>(2, lane_ops_per_s);   /* IMAD + IADD pairs, counted as 2 */
     case 6: return run<6>(2, lane_ops_per_s);   /* IMNMX + IADD                 */
     case 7: return run<7>(1, lane_ops_per_s);   /* SHFL                         */
+    case 8: return run<8>(1, lane_ops_per_s);   /* IMAD.WIDE.S32 with 64-bit addend */
+    case 9: return run<9>(1, lane_ops_per_s);   /* Plantard butterflies / s (IMAD + IMAD.WIDE + 2 IADD) */
+    case 10: return run<10>(1, lane_ops_per_s); /* signed Shoup butterflies / s, add folded        */
+    case 11: return run<11>(1, lane_ops_per_s); /* half-word Plantard butterflies / s              */
+    case 13: return run<13>(1, lane_ops_per_s); /* unsigned Plantard butterflies / s (IMAD + IMAD.HI + 2 IADD3) */
+    case 12: return run<12>(2, lane_ops_per_s); /* SHF + IADD pairs, counted as 2                  */
     default: return nttb200_fail(NTTB200_EPARAM, "unknown microbenchmark %d", which);
   }
 }

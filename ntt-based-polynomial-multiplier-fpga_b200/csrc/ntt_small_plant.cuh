@@ -1,0 +1,355 @@
+/*
+ * ntt_small_plant.cuh -- fused product kernel for HALF-WORD moduli (q <= 12385: 12289, 7681,
+ * 3329 ...), n = 2^L <= 1024.  Same dataflow and layouts as ntt_small.cuh (CT forward
+ * std->rev with psi folded in, pointwise, GS inverse rev->std with n^-1 folded into the last
+ * stage; R/NTT/ntt.C:342-371, 131-137, 428-451) but a cheaper modular multiplication:
+ *
+ *   Plantard word-size multiplication by a constant w, stored as
+ *        w~ = ((-w 2^32) mod q) * q^-1  mod 2^32 :
+ *        T = umulhi(Y * w~, q)           (IMAD + IMAD.HI.U32 = 3 fmaheavy issue slots)
+ *   gives  T = Y w mod q  EXACTLY CANONICAL in [0, q)  whenever  Y * q < 2^32.
+ *   [p = Y w~ mod 2^32 satisfies p q = Y W + k 2^32 with W = (-w 2^32) mod q, so
+ *    k = floor(p q / 2^32) when 0 <= Y W < 2^32, k == Y w (mod q) and 0 <= k < q.]
+ *
+ * Against the Shoup multiplication of modarith.cuh (IMAD.HI + 2 IMAD = 4 slots, result in
+ * [0,2q), two table words per twiddle) this is 3 slots, a canonical result and ONE table
+ * word: the butterfly is IMAD, IMAD.HI, IADD3, IADD3 and -- measured with
+ * nttb200_measure_int_peak(13) vs (3) -- runs 1.31x faster on the B200 integer pipe,
+ * which is the unit that binds this kernel (profiles/).  The lane twiddles held in
+ * registers halve, which is what leaves room for the next tile's operands to be
+ * prefetched into shared memory with cp.async (128-bit, fully coalesced) while the current
+ * tile is being transformed.
+ *
+ * Values are kept lazily in [0, b q) with the integer bound b of every register known AT
+ * COMPILE TIME from closed forms (see "compile-time value bounds" below): a CT stage adds 1
+ * to b, a GS sum doubles it, every product resets it to 1, and a single IADD+IMNMX
+ * conditional subtraction is inserted exactly where a bound would pass the cap; all
+ * multiplication inputs stay below PLANT_LIMB q = 28 q  (28 q^2 < 2^32 for q <= 12385).
+ */
+#pragma once
+#include <stdint.h>
+#include "ntt_small.cuh"
+
+namespace nttb200 {
+
+constexpr int PLANT_LIMB = 28;
+constexpr uint32_t PLANT_QMAX = 12385;     /* 28 * q * q < 2^32 */
+
+template <int R>
+struct PlantParams {
+  const uint32_t *a;
+  const uint32_t *b;
+  uint32_t *c;
+  const uint32_t *tw_fwd;    /* device level table of w~, n entries           */
+  const uint32_t *tw_inv;
+  unsigned long long batch;
+  uint32_t q, qinv;
+  uint32_t last_x;           /* (-n^-1 2^32)~ : multiplier of the sum branch of the last stage */
+  uint32_t last_y;           /* (-n^-1 2^32 p_inv[1])~ : multiplier of its diff branch         */
+  uint32_t qmul[16];         /* i * q, so that "+ b q" is a constant-bank operand         */
+  uint32_t ufwd[1 << R];     /* entries [1, 2^R) of the forward level table (w~)          */
+  uint32_t uinv[1 << R];
+};
+
+__device__ __forceinline__ uint32_t plant_mul(uint32_t y, uint32_t wt, uint32_t q) {
+  return __umulhi(y * wt, q);
+}
+
+/* ---- compile-time value bounds ----------------------------------------------------------
+ * Every register holds a value in [0, b q) with b known at compile time from closed forms:
+ *   forward CT      b = (stages done) + 1, the same for every register (<= 11 <= PLANT_LIMB)
+ *   inverse GS      inside a register phase, at the stage on register bit `bit`, the two legs
+ *                   of a butterfly share their history h = r & (2^bit - 1):
+ *                     h != 0: last product at stage p = msb(h), then bit-1-p sums:  2^(bit-1-p)
+ *                     h == 0: only sums since the phase input bound b_in:           b_in 2^bit
+ *                   capped at PLANT_CAP = 8 by ONE conditional subtraction of 8q on a sum whose
+ *                   inputs already were at the cap (so d = X - Y + b q < 16 q <= 28 q always).
+ */
+constexpr int PLANT_CAP = 8;
+
+__host__ __device__ constexpr int pl_min(int a, int b) { return a < b ? a : b; }
+__host__ __device__ constexpr int pl_msb(int h) { int p = -1; while (h) { p++; h >>= 1; } return p; }
+/* bound of both legs of the GS butterfly on register bit `bit` of register r */
+__host__ __device__ constexpr int pl_gs_bound(int r, int bit, int b_in) {
+  const int h = r & ((1 << bit) - 1);
+  if (h == 0) return pl_min(b_in << bit, PLANT_CAP);
+  return pl_min(1 << (bit - 1 - pl_msb(h)), PLANT_CAP);
+}
+/* worst bound of any register after a GS register phase of `bits` stages */
+__host__ __device__ constexpr int pl_gs_phase_out(int bits, int b_in) {
+  return pl_min(b_in << bits, PLANT_CAP);
+}
+/* pointwise a*b needs ba*bb <= PLANT_LIMB: halve the larger bound until it does */
+struct PlPointwise { int na, nb; int ha[4], hb[4]; };
+__host__ __device__ constexpr PlPointwise pl_pointwise_plan(int b) {
+  PlPointwise p{0, 0, {0, 0, 0, 0}, {0, 0, 0, 0}};
+  int ba = b, bb = b;
+  while (ba * bb > PLANT_LIMB) {
+    if (ba >= bb) { ba = (ba + 1) / 2; p.ha[p.na++] = ba; }
+    else { bb = (bb + 1) / 2; p.hb[p.nb++] = bb; }
+  }
+  return p;
+}
+
+/* per-lane twiddles of the layout-2 phase, one word each */
+template <int L>
+struct LaneTw1 {
+  using Gm = SmallGeom<L>;
+  static constexpr int PER_ROW = (1 << Gm::H) - 1;
+  uint32_t w[(1 << Gm::G) * (PER_ROW > 0 ? PER_ROW : 1)];
+  __device__ __forceinline__ void load(const uint32_t *tab, int l) {
+#pragma unroll
+    for (int g = 0; g < (1 << Gm::G); g++) {
+      const int row = (g << Gm::H) | l;
+#pragma unroll
+      for (int m = 0; m < Gm::H; m++) {
+        const uint32_t *src = tab + (1 << (Gm::R + m)) + (row << m);
+        if (m == 0) {
+          w[g * PER_ROW + 0] = __ldg(src);
+        } else if (m == 1) {
+          uint2 v = __ldg(reinterpret_cast<const uint2 *>(src));
+          w[g * PER_ROW + 1] = v.x;
+          w[g * PER_ROW + 2] = v.y;
+        } else {
+#pragma unroll
+          for (int u = 0; u < (1 << m); u += 4) {
+            uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + u));
+            w[g * PER_ROW + ((1 << m) - 1) + u + 0] = v.x;
+            w[g * PER_ROW + ((1 << m) - 1) + u + 1] = v.y;
+            w[g * PER_ROW + ((1 << m) - 1) + u + 2] = v.z;
+            w[g * PER_ROW + ((1 << m) - 1) + u + 3] = v.w;
+          }
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ uint32_t get(int g, int m, int u) const {
+    return w[g * PER_ROW + ((1 << m) - 1) + u];
+  }
+};
+
+/* CT butterfly: T = Y w mod q in [0,q); X' = X + T, Y' = X - T + q  (bounds grow by 1) */
+__device__ __forceinline__ void pl_ct(uint32_t &X, uint32_t &Y, uint32_t wt, uint32_t q) {
+  const uint32_t T = plant_mul(Y, wt, q);
+  Y = X - T + q;
+  X = X + T;
+}
+/* GS butterfly on two legs < b q: X' = X + Y (capped), Y' = (X - Y) w mod q in [0,q) */
+template <int B, typename PT>
+__device__ __forceinline__ void pl_gs(uint32_t &X, uint32_t &Y, uint32_t wt, const PT &P) {
+  const uint32_t d = X - Y + P.qmul[B];
+  uint32_t s = X + Y;
+  if (2 * B > PLANT_CAP) s = csub(s, P.qmul[PLANT_CAP]);
+  X = s;
+  Y = plant_mul(d, wt, P.q);
+}
+template <typename PT>
+__device__ __forceinline__ void pl_gs_b(int b, uint32_t &X, uint32_t &Y, uint32_t wt, const PT &P) {
+  switch (b) {                                     /* b is a compile-time constant after unrolling */
+    case 1: pl_gs<1>(X, Y, wt, P); break;
+    case 2: pl_gs<2>(X, Y, wt, P); break;
+    case 4: pl_gs<4>(X, Y, wt, P); break;
+    default: pl_gs<8>(X, Y, wt, P); break;
+  }
+}
+
+template <int L>
+__device__ __forceinline__ void pl_fwd_cols(uint32_t (&x)[SmallGeom<L>::NV],
+                                            const PlantParams<SmallGeom<L>::R> &P) {
+  using Gm = SmallGeom<L>;
+#pragma unroll
+  for (int s = 0; s < Gm::R; s++) {
+    const int kb = Gm::R - 1 - s;
+#pragma unroll
+    for (int k = 0; k < Gm::NV; k++) {
+      if (k & (1 << kb)) continue;
+      pl_ct(x[k], x[k | (1 << kb)], P.ufwd[(1 << s) + (k >> (kb + 1))], P.q);
+    }
+  }
+}
+template <int L>
+__device__ __forceinline__ void pl_fwd_rows(uint32_t (&x)[SmallGeom<L>::NV], const LaneTw1<L> &tw,
+                                            const PlantParams<SmallGeom<L>::R> &P) {
+  using Gm = SmallGeom<L>;
+#pragma unroll
+  for (int lv = 0; lv < Gm::H; lv++) {
+    const int bit = Gm::H - 1 - lv;
+#pragma unroll
+    for (int r = 0; r < Gm::NV; r++) {
+      if (r & (1 << bit)) continue;
+      const int g = r >> Gm::H;
+      const int u = (r & (Gm::T - 1)) >> (bit + 1);
+      pl_ct(x[r], x[r | (1 << bit)], tw.get(g, lv, u), P.q);
+    }
+  }
+}
+/* inverse, layout 2 (register bits 0..H-1 of r_lo; the g bit of r is not a history bit) */
+template <int L>
+__device__ __forceinline__ void pl_inv_rows(uint32_t (&x)[SmallGeom<L>::NV], const LaneTw1<L> &tw,
+                                            const PlantParams<SmallGeom<L>::R> &P) {
+  using Gm = SmallGeom<L>;
+#pragma unroll
+  for (int bit = 0; bit < Gm::H; bit++) {
+    const int lv = Gm::H - 1 - bit;
+#pragma unroll
+    for (int r = 0; r < Gm::NV; r++) {
+      if (r & (1 << bit)) continue;
+      const int g = r >> Gm::H;
+      const int u = (r & (Gm::T - 1)) >> (bit + 1);
+      pl_gs_b(pl_gs_bound(r & (Gm::T - 1), bit, 1), x[r], x[r | (1 << bit)], tw.get(g, lv, u), P);
+    }
+  }
+}
+/* inverse, layout 1; inputs < B_IN q; the last stage multiplies both branches (n^-1 folded
+ * in), so the outputs are canonical */
+template <int L, int B_IN>
+__device__ __forceinline__ void pl_inv_cols(uint32_t (&x)[SmallGeom<L>::NV],
+                                            const PlantParams<SmallGeom<L>::R> &P) {
+  using Gm = SmallGeom<L>;
+#pragma unroll
+  for (int kb = 0; kb < Gm::R; kb++) {
+    const int t = 1 << (Gm::R - 1 - kb);
+#pragma unroll
+    for (int k = 0; k < Gm::NV; k++) {
+      if (k & (1 << kb)) continue;
+      const int k2 = k | (1 << kb);
+      const int b = pl_gs_bound(k, kb, B_IN);
+      if (kb < Gm::R - 1) {
+        pl_gs_b(b, x[k], x[k2], P.uinv[t + (k >> (kb + 1))], P);
+      } else {
+        const uint32_t d = x[k] - x[k2] + P.qmul[b];
+        const uint32_t s = x[k] + x[k2];
+        x[k2] = plant_mul(d, P.last_y, P.q);
+        x[k] = plant_mul(s, P.last_x, P.q);
+      }
+    }
+  }
+}
+
+/* cp.async (LDGSTS) 16-byte copy global -> shared */
+__device__ __forceinline__ void cp_async16(uint32_t *smem_dst, const uint32_t *gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int L>
+struct PlantGeom {
+  using Gm = SmallGeom<L>;
+  /* words per polynomial in the prefetch buffer: 16-byte aligned rows, and consecutive
+   * polynomials of a warp land on different banks for the layout-1 reads */
+  static constexpr int PSTRIDE = Gm::N + ((Gm::T >= 32) ? 0 : ((Gm::T % 4 == 0) ? Gm::T : 4));
+  static constexpr int CHUNKS = Gm::N / 4;                    /* 16-byte chunks per polynomial */
+  static constexpr int ITERS = (Gm::PPW * CHUNKS + 31) / 32;   /* cp.async per lane per operand */
+  /* per warp: prefetch a, prefetch b, transposition a, transposition b */
+  static constexpr int WARP_WORDS = 2 * Gm::PPW * PSTRIDE + 2 * Gm::PPW * Gm::STRIDE;
+};
+
+template <int L>
+__device__ __forceinline__ void plant_prefetch(uint32_t *pa, uint32_t *pb, const uint32_t *ga, const uint32_t *gb,
+                                               unsigned long long tile, unsigned long long batch, int lane) {
+  using Gm = SmallGeom<L>;
+  using Pg = PlantGeom<L>;
+#pragma unroll
+  for (int i = 0; i < Pg::ITERS; i++) {
+    const int c = i * 32 + lane;
+    const int sub = c / Pg::CHUNKS;
+    const int cc = c % Pg::CHUNKS;
+    const unsigned long long poly = tile * Gm::PPW + sub;
+    if (sub < Gm::PPW && poly < batch) {
+      const size_t go = ((size_t)poly << L) + cc * 4;
+      cp_async16(pa + sub * Pg::PSTRIDE + cc * 4, ga + go);
+      cp_async16(pb + sub * Pg::PSTRIDE + cc * 4, gb + go);
+    }
+  }
+}
+
+/* =====================================================================================
+ * Fused product kernel, half-word moduli.
+ * ===================================================================================== */
+template <int L, int WARPS, int MINB, bool TWREG>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
+  using Gm = SmallGeom<L>;
+  using Pg = PlantGeom<L>;
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int sub = lane / Gm::T;
+  const int l = lane % Gm::T;
+  uint32_t *pf_a = smem + warp * Pg::WARP_WORDS;
+  uint32_t *pf_b = pf_a + Gm::PPW * Pg::PSTRIDE;
+  uint32_t *sm_a = pf_b + Gm::PPW * Pg::PSTRIDE + sub * Gm::STRIDE;
+  uint32_t *sm_b = sm_a + Gm::PPW * Gm::STRIDE;
+  const uint32_t q = P.q;
+
+  const unsigned long long ntiles = (P.batch + Gm::PPW - 1) / Gm::PPW;
+  const unsigned long long wstride = (unsigned long long)gridDim.x * WARPS;
+  unsigned long long tile = (unsigned long long)blockIdx.x * WARPS + warp;
+  if (tile < ntiles) plant_prefetch<L>(pf_a, pf_b, P.a, P.b, tile, P.batch, lane);
+
+  LaneTw1<L> twf, twi;
+  if (TWREG) {
+    twf.load(P.tw_fwd, l);
+    twi.load(P.tw_inv, l);
+  }
+
+  for (; tile < ntiles; tile += wstride) {
+    const unsigned long long poly = tile * Gm::PPW + sub;
+    const bool live = poly < P.batch;
+
+    uint32_t xa[Gm::NV], xb[Gm::NV];
+    cp_async_wait_all();
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < Gm::NV; k++) {
+      xa[k] = pf_a[sub * Pg::PSTRIDE + (k << Gm::H) + l];
+      xb[k] = pf_b[sub * Pg::PSTRIDE + (k << Gm::H) + l];
+    }
+    __syncwarp();                                     /* prefetch buffers are free again */
+    if (tile + wstride < ntiles) plant_prefetch<L>(pf_a, pf_b, P.a, P.b, tile + wstride, P.batch, lane);
+
+    pl_fwd_cols<L>(xa, P);
+    pl_fwd_cols<L>(xb, P);
+    if (Gm::H > 0) {
+      store_cols<L>(xa, sm_a, l);
+      store_cols<L>(xb, sm_b, l);
+      __syncwarp();
+      load_rows<L>(xa, sm_a, l);
+      load_rows<L>(xb, sm_b, l);
+      if (!TWREG) twf.load(P.tw_fwd, l);
+      pl_fwd_rows<L>(xa, twf, P);
+      pl_fwd_rows<L>(xb, twf, P);
+    }
+
+    /* pointwise product (mul_array, R/NTT/ntt.C:131-137) as a Plantard product of two
+     * variables: umulhi(a b q^-1, q) = -a b 2^-32 mod q, canonical, needs a b < 2^32;
+     * the constant -2^32 is cancelled by last_x / last_y */
+    constexpr PlPointwise pw = pl_pointwise_plan(L + 1);    /* both operands < (L+1) q here */
+#pragma unroll
+    for (int k = 0; k < Gm::NV; k++) {
+      uint32_t av = xa[k], bv = xb[k];
+      if (pw.na > 0) av = csub(av, P.qmul[pw.ha[0]]);
+      if (pw.na > 1) av = csub(av, P.qmul[pw.ha[1]]);
+      if (pw.na > 2) av = csub(av, P.qmul[pw.ha[2]]);
+      if (pw.nb > 0) bv = csub(bv, P.qmul[pw.hb[0]]);
+      if (pw.nb > 1) bv = csub(bv, P.qmul[pw.hb[1]]);
+      if (pw.nb > 2) bv = csub(bv, P.qmul[pw.hb[2]]);
+      xa[k] = __umulhi(av * bv * P.qinv, q);
+    }
+
+    if (Gm::H > 0) {
+      if (!TWREG) twi.load(P.tw_inv, l);
+      pl_inv_rows<L>(xa, twi, P);
+      __syncwarp();                                   /* all lanes done reading sm_a */
+      store_rows<L>(xa, sm_a, l);
+      __syncwarp();
+      load_cols<L>(xa, sm_a, l);
+    }
+    pl_inv_cols<L, pl_gs_phase_out(Gm::H, 1)>(xa, P);
+    if (live) gstore_cols<L>(xa, P.c + (poly << L), l);
+    __syncwarp();                                     /* smem reuse by the next tile */
+  }
+}
+
+}  // namespace nttb200

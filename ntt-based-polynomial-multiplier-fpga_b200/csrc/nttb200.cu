@@ -79,17 +79,26 @@ extern "C" int nttb200_get_device(void) {
 /* ------------------------------------------------------------------------------------ */
 /* plans                                                                                 */
 /* ------------------------------------------------------------------------------------ */
-static int upload_table(DevTable &t, const std::vector<uint32_t> &w, uint32_t q) {
+static int upload_table(DevTable &t, const std::vector<uint32_t> &w, uint32_t q, uint32_t plant_qinv = 0) {
   t.h.resize(w.size());
   for (size_t i = 0; i < w.size(); i++) t.h[i] = make_uint2(w[i], ht_shoup(w[i], q));
   NTT_CUDA(cudaMalloc(&t.d, t.h.size() * sizeof(uint2)));
   NTT_CUDA(cudaMemcpy(t.d, t.h.data(), t.h.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+  if (plant_qinv) {
+    t.h1.resize(w.size());
+    for (size_t i = 0; i < w.size(); i++) t.h1[i] = nttb200_plant_form(w[i], q, plant_qinv);
+    NTT_CUDA(cudaMalloc(&t.d1, t.h1.size() * sizeof(uint32_t)));
+    NTT_CUDA(cudaMemcpy(t.d1, t.h1.data(), t.h1.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
   return 0;
 }
 static void free_table(DevTable &t) {
   if (t.d) cudaFree(t.d);
+  if (t.d1) cudaFree(t.d1);
   t.d = nullptr;
+  t.d1 = nullptr;
   t.h.clear();
+  t.h1.clear();
 }
 
 static int pick_arith(uint32_t q, uint32_t logn) {
@@ -152,27 +161,30 @@ extern "C" int nttb200_plan_create(nttb200_plan **out, uint32_t n, uint32_t q, u
     P->m.qinv = inv;
   }
 
+  /* half-word moduli: the product kernel uses Plantard arithmetic (ntt_small_plant.cuh) */
+  P->plant = (P->kernel == PK_SMALL) && q <= 12385u && !(flags & NTTB200_PLAN_NO_PLANTARD);
+  const uint32_t pq = P->plant ? P->m.qinv : 0;
   std::vector<uint32_t> w(n);
   const uint32_t iomega = ht_invmod(omega, q);
   int rc = 0;
   ht_level_table(w.data(), n, q, 1, omega, 1);
-  rc = rc ? rc : upload_table(P->fwd_plain, w, q);
+  rc = rc ? rc : upload_table(P->fwd_plain, w, q, cyclic ? pq : 0);
   rc = rc ? rc : upload_table(P->inv_fwdroot, w, q);
   ht_level_table(w.data(), n, q, 1, iomega, 1);
-  rc = rc ? rc : upload_table(P->inv_plain, w, q);
+  rc = rc ? rc : upload_table(P->inv_plain, w, q, cyclic ? pq : 0);
   rc = rc ? rc : upload_table(P->fwd_invroot, w, q);
   if (!cyclic) {
     ht_level_table(w.data(), n, q, psi, omega, 1);
-    rc = rc ? rc : upload_table(P->fwd_mixed, w, q);
+    rc = rc ? rc : upload_table(P->fwd_mixed, w, q, pq);
     ht_level_table(w.data(), n, q, ht_invmod(psi, q), iomega, 1);
-    rc = rc ? rc : upload_table(P->inv_mixed, w, q);
+    rc = rc ? rc : upload_table(P->inv_mixed, w, q, pq);
   }
   if (rc) { nttb200_plan_destroy(P); return rc; }
   static const char *an[] = {"lazy", "harvey", "canon"};
-  snprintf(P->desc, sizeof P->desc, "n=%u q=%u %s=%u kernel=%s arith=%s device=%d sms=%d", n, q,
+  snprintf(P->desc, sizeof P->desc, "n=%u q=%u %s=%u kernel=%s arith=%s%s device=%d sms=%d", n, q,
            cyclic ? "omega" : "psi", cyclic ? omega : psi,
-           P->kernel == PK_SMALL ? "fused-small(regs+smem)" : "large(multi-pass)", an[P->arith], dev,
-           P->sm_count);
+           P->kernel == PK_SMALL ? "fused-small(regs+smem)" : "large(multi-pass)", an[P->arith],
+           P->plant ? "+plantard(product)" : "", dev, P->sm_count);
   *out = P;
   return 0;
 }
@@ -207,6 +219,9 @@ extern "C" const char *nttb200_plan_describe(const nttb200_plan *P) { return P ?
 /* ------------------------------------------------------------------------------------ */
 int launch_polymul_small(const nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b,
                          size_t batch, cudaStream_t st) {
+  /* the Plantard kernel prefetches with 16-byte cp.async: operands must be 16-byte aligned */
+  if (P->plant && (((uintptr_t)a | (uintptr_t)b) & 15u) == 0)
+    return launch_polymul_small_plant(P, c, a, b, batch, st);
   switch (P->arith) {
     case ARITH_LAZY: return launch_polymul_small_lazy(P, c, a, b, batch, st);
     case ARITH_HARVEY: return launch_polymul_small_harvey(P, c, a, b, batch, st);
@@ -222,6 +237,7 @@ int launch_ntt_small(const nttb200_plan *P, const DevTable &tab, int dir, int sc
   }
 }
 int small_kernel_info(const nttb200_plan *P, int *regs, int *smem_bytes, int *blocks_per_sm) {
+  if (P->plant) return small_kernel_info_plant(P, regs, smem_bytes, blocks_per_sm);
   switch (P->arith) {
     case ARITH_LAZY: return small_kernel_info_lazy(P, regs, smem_bytes, blocks_per_sm);
     case ARITH_HARVEY: return small_kernel_info_harvey(P, regs, smem_bytes, blocks_per_sm);

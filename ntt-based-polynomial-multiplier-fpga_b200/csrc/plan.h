@@ -14,7 +14,15 @@
 struct DevTable {
   uint2 *d = nullptr;            /* device: n entries (w, floor(w 2^32/q)), reference level layout */
   std::vector<uint2> h;          /* host mirror (entries < 64 feed the kernel-parameter block)     */
+  uint32_t *d1 = nullptr;        /* device: the same table in Plantard form w~ (half-word moduli)  */
+  std::vector<uint32_t> h1;
 };
+
+/* Plantard form of a constant: ((-w 2^32) mod q) * q^-1 mod 2^32  (ntt_small_plant.cuh) */
+static inline uint32_t nttb200_plant_form(uint32_t w, uint32_t q, uint32_t qinv) {
+  const uint64_t W = (q - (((uint64_t)(w % q)) << 32) % q) % q;
+  return (uint32_t)W * qinv;
+}
 
 enum PlanKernel { PK_SMALL = 0, PK_LARGE = 1 };
 
@@ -30,6 +38,7 @@ struct nttb200_plan {
   int device = 0;
   int arith = ARITH_LAZY;
   int kernel = PK_SMALL;
+  bool plant = false;            /* half-word modulus: products run the Plantard kernel             */
   int sm_count = 0;
   ModQ m{};
   char desc[160] = {0};
@@ -81,3 +90,6 @@ int launch_polymul_large(nttb200_plan *P, uint32_t *c, const uint32_t *a, const 
 int launch_ntt_large(nttb200_plan *P, const DevTable &tab, int dir, int scale, uint32_t *a, size_t batch,
                      cudaStream_t st);
 int small_kernel_info(const nttb200_plan *P, int *regs, int *smem_bytes, int *blocks_per_sm);
+int launch_polymul_small_plant(const nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b,
+                               size_t batch, cudaStream_t st);
+int small_kernel_info_plant(const nttb200_plan *P, int *regs, int *smem_bytes, int *blocks_per_sm);

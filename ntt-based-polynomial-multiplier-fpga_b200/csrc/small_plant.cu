@@ -1,0 +1,105 @@
+/* n <= 1024 fused product kernel for half-word moduli (Plantard arithmetic, ntt_small_plant.cuh) */
+#include <cuda_runtime.h>
+#include <stdlib.h>
+
+#include "ntt_small_plant.cuh"
+#include "plan.h"
+
+namespace {
+using namespace nttb200;
+
+template <int L> struct PlantCfg {
+  static constexpr int WARPS = (L >= 9) ? 4 : 8;
+  static constexpr bool TWREG = (L <= 8);
+};
+/* resident CTAs per SM the kernel is compiled for (register cap).  Measured on B200 (c2:
+ * 996 vs 939 M polymul/s, c3: 1095 vs 1026, c4: 218 vs 213): 2 CTAs with 127 registers beat 3
+ * CTAs with 80 registers and a small spill.  NTTB200_PLANT_MINB=2|3 overrides (tuning knob). */
+int plant_minb(int L) {
+  static int env = -1;
+  if (env < 0) {
+    const char *e = getenv("NTTB200_PLANT_MINB");
+    env = e ? atoi(e) : 0;
+  }
+  if (env == 2 || env == 3) return env;
+  (void)L;
+  return 2;
+}
+
+template <int L, int MINB>
+int run_plant(const nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b, size_t batch,
+              cudaStream_t st) {
+  using Gm = SmallGeom<L>;
+  using Pg = PlantGeom<L>;
+  using Cfg = PlantCfg<L>;
+  const bool cyclic = (P->flags & NTTB200_PLAN_CYCLIC) != 0;
+  const DevTable &fwd = cyclic ? P->fwd_plain : P->fwd_mixed;
+  const DevTable &inv = cyclic ? P->inv_plain : P->inv_mixed;
+  PlantParams<Gm::R> p{};
+  p.a = a; p.b = b; p.c = c; p.batch = batch;
+  p.tw_fwd = fwd.d1; p.tw_inv = inv.d1;
+  p.q = P->q; p.qinv = P->m.qinv;
+  const uint32_t q = P->q;
+  /* -n^-1 2^32: cancels the -2^-32 of the Plantard pointwise product */
+  const uint64_t fs = (q - (uint64_t)P->n_inv * ((1ull << 32) % q) % q) % q;
+  p.last_x = nttb200_plant_form((uint32_t)fs, q, p.qinv);
+  p.last_y = nttb200_plant_form((uint32_t)(fs * inv.h[1].x % q), q, p.qinv);
+  for (int i = 0; i < (int)(sizeof p.qmul / sizeof p.qmul[0]); i++) p.qmul[i] = (uint32_t)i * q;
+  for (int i = 0; i < (1 << Gm::R); i++) {
+    p.ufwd[i] = (size_t)i < fwd.h1.size() ? fwd.h1[i] : 0;
+    p.uinv[i] = (size_t)i < inv.h1.size() ? inv.h1[i] : 0;
+  }
+  auto kernel = polymul_plant_kernel<L, Cfg::WARPS, MINB, Cfg::TWREG>;
+  const int smem = Cfg::WARPS * Pg::WARP_WORDS * (int)sizeof(uint32_t);
+  int per_sm = 0;
+  NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  NTT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, Cfg::WARPS * 32, smem));
+  if (per_sm < 1) return nttb200_fail(NTTB200_ECUDA, "plant kernel does not fit on an SM");
+  const unsigned long long tiles = (batch + Gm::PPW - 1) / Gm::PPW;
+  const unsigned long long want = (tiles + Cfg::WARPS - 1) / Cfg::WARPS;
+  const unsigned long long cap = (unsigned long long)P->sm_count * per_sm;
+  const int grid = (int)(want < cap ? (want ? want : 1) : cap);
+  kernel<<<grid, Cfg::WARPS * 32, smem, st>>>(p);
+  nttb200_count_launch(1);
+  NTT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int L, int MINB>
+int info_plant(int *regs, int *smem_bytes, int *blocks_per_sm) {
+  using Pg = PlantGeom<L>;
+  using Cfg = PlantCfg<L>;
+  auto kernel = polymul_plant_kernel<L, Cfg::WARPS, MINB, Cfg::TWREG>;
+  cudaFuncAttributes at;
+  NTT_CUDA(cudaFuncGetAttributes(&at, kernel));
+  const int smem = Cfg::WARPS * Pg::WARP_WORDS * (int)sizeof(uint32_t);
+  NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int per_sm = 0;
+  NTT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, Cfg::WARPS * 32, smem));
+  *regs = at.numRegs; *smem_bytes = smem; *blocks_per_sm = per_sm;
+  return 0;
+}
+}  // namespace
+
+#define PLANT_SWITCH(expr_of_L)                      \
+  switch (P->logn) {                                 \
+    case 3: { constexpr int L = 3; expr_of_L; }      \
+    case 4: { constexpr int L = 4; expr_of_L; }      \
+    case 5: { constexpr int L = 5; expr_of_L; }      \
+    case 6: { constexpr int L = 6; expr_of_L; }      \
+    case 7: { constexpr int L = 7; expr_of_L; }      \
+    case 8: { constexpr int L = 8; expr_of_L; }      \
+    case 9: { constexpr int L = 9; expr_of_L; }      \
+    case 10: { constexpr int L = 10; expr_of_L; }    \
+    default: return nttb200_fail(NTTB200_EPARAM, "small kernels cover 8 <= n <= 1024"); \
+  }
+
+int launch_polymul_small_plant(const nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b,
+                               size_t batch, cudaStream_t st) {
+  if (plant_minb(P->logn) == 2) { PLANT_SWITCH(return (run_plant<L, 2>(P, c, a, b, batch, st))) }
+  PLANT_SWITCH(return (run_plant<L, 3>(P, c, a, b, batch, st)))
+}
+int small_kernel_info_plant(const nttb200_plan *P, int *regs, int *smem_bytes, int *blocks_per_sm) {
+  if (plant_minb(P->logn) == 2) { PLANT_SWITCH(return (info_plant<L, 2>(regs, smem_bytes, blocks_per_sm))) }
+  PLANT_SWITCH(return (info_plant<L, 3>(regs, smem_bytes, blocks_per_sm)))
+}

@@ -27,7 +27,7 @@ def plan256(gpu):
 
 
 def test_native_library_is_the_one_running(gpu, plan256):
-    assert "fused-small" in plan256.describe() and "arith=lazy" in plan256.describe()
+    assert "fused-small" in plan256.describe() and "plantard" in plan256.describe()
     a = np.zeros((2, N), np.int32)
     plan256.polymul(a, a)
     assert gpu.last_launch_count() >= 1
@@ -83,6 +83,27 @@ def test_config2_batch_2e16_vs_all_four_reference_variants(plan256, oracle, load
     else:                                   # never on the build box; keeps the test meaningful elsewhere
         assert (oracle.product(N, Q, a[:4096], b[:4096], 10, PSI) == got[:4096]).all()
     assert got.min() >= 0 and got.max() < Q
+
+
+@pytest.mark.parametrize("n,q", [(8, 17), (16, 97), (32, 193), (64, 257), (128, 3329), (256, 12289),
+                                 (256, 7681), (512, 12289), (1024, 12289), (512, 10753), (1024, 10753)])
+def test_half_word_moduli_plantard_vs_shoup_kernels(gpu, oracle, n, q):
+    """q <= 12385: the product runs the Plantard kernel (ntt_small_plant.cuh); the same plan with
+    NTTB200_PLAN_NO_PLANTARD runs the Shoup/Montgomery kernel.  Both against the oracle, with
+    worst-case rows (all q-1: every lazy bound is attained) and ragged batch sizes."""
+    pl, sh = gpu.Plan(n, q), gpu.Plan(n, q, no_plantard=True)
+    assert "plantard" in pl.describe() and "plantard" not in sh.describe()
+    for batch in (1, 2, 31, 32, 33, 257, 1031):
+        a, b = oracle.random((batch, n), q, SEED + n + batch), oracle.random((batch, n), q, SEED + q + batch)
+        a[0], b[0] = q - 1, q - 1
+        if batch > 2:
+            a[1] = q - 1
+            b[2] = q - 1
+        want = oracle.product(n, q, a, b, 10)
+        assert (pl.polymul(a, b) == want).all(), (pl.describe(), batch)
+        assert (sh.polymul(a, b) == want).all(), (sh.describe(), batch)
+    pl.close()
+    sh.close()
 
 
 @pytest.mark.parametrize("n,q", SMALL_CASES)
