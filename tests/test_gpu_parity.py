@@ -86,7 +86,7 @@ def test_config2_batch_2e16_vs_all_four_reference_variants(plan256, oracle, load
 
 
 @pytest.mark.parametrize("n,q", [(8, 17), (16, 97), (32, 193), (64, 257), (128, 3329), (256, 12289),
-                                 (256, 7681), (512, 12289), (1024, 12289), (512, 10753), (1024, 10753)])
+                                 (256, 7681), (512, 12289), (1024, 12289), (256, 10753), (128, 12289)])
 def test_half_word_moduli_plantard_vs_shoup_kernels(gpu, oracle, n, q):
     """q <= 12385: the product runs the Plantard kernel (ntt_small_plant.cuh); the same plan with
     NTTB200_PLAN_NO_PLANTARD runs the Shoup/Montgomery kernel.  Both against the oracle, with
