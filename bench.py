@@ -46,9 +46,9 @@ WORKLOADS = {
 }
 # DRAM bytes (read + write) per launch of the dominant kernel, from `ncu --set full` captures
 # committed under profiles/ (a profiler run is never a bench value; this is the traffic only)
-TRAFFIC_NCU = {"c2": 175037696}
-TRAFFIC_SRC = {"c2": "profiles/r1_c2_polymul_n256_v1_ncu_full.txt: dram__bytes_read.sum 134.29 MB + "
-                     "dram__bytes_write.sum 40.75 MB per launch (algorithmic 201.3 MB; part of c stays dirty in L2)"}
+TRAFFIC_NCU = {"c2": 170409728}
+TRAFFIC_SRC = {"c2": "profiles/r1_c2_polymul_plant_n256_v2_ncu_full.txt: dram__bytes_read.sum 134.26 MB + "
+                     "dram__bytes_write.sum 36.15 MB per launch (algorithmic 201.3 MB; part of c stays dirty in L2)"}
 SEED = 0x4E545442323030
 L2_BYTES = 126 * 1000 * 1000
 
@@ -358,7 +358,11 @@ def main() -> int:
     # fmaheavy issue slots per product as the kernels are written: Shoup butterfly = IMAD.HI
     # (2 slots: measured half rate) + 2 IMAD; pointwise Montgomery = 2 IMAD.HI + 2 IMAD; the
     # n^-1 scaling costs one extra Shoup multiplication on the sum branch of the last stage
-    slots = 4 * bflies + 6 * n + 4 * (n // 2)
+    plantard = "plantard" in plan.describe()
+    if plantard:      # IMAD + IMAD.HI per butterfly (3), 2 IMAD + IMAD.HI pointwise (4), 3 per n^-1 scale
+        slots = 3 * bflies + 4 * n + 3 * (n // 2)
+    else:
+        slots = 4 * bflies + 6 * n + 4 * (n // 2)
     imad_peak = mod.measure_int_peak(0)
     imadhi_peak = mod.measure_int_peak(1)
     bfly_peak = mod.measure_int_peak(3)
@@ -384,7 +388,7 @@ def main() -> int:
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "polymul_small_kernel" if n <= 1024 else
+                     "kernel": ("polymul_plant_kernel" if plantard else "polymul_small_kernel") if n <= 1024 else
                                "large_cols_fwd + large_rows_polymul + large_cols_inv (whole step)",
                      "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": roof_ms,
                      "traffic_source": TRAFFIC_SRC.get(args.workload)},
@@ -398,7 +402,9 @@ def main() -> int:
                          "imad_hi_peak": imadhi_peak, "lazy_butterflies_per_s_peak": bfly_peak,
                          "note": "peak = independent IMAD chains on every SM, measured live "
                                  "(nttb200_measure_int_peak); IMAD.HI measured at half that rate so it "
-                                 "counts 2 slots: butterfly 4, pointwise 6, n^-1 scale 4 per pair"},
+                                 "counts 2 slots. Shoup kernels: butterfly 4, pointwise 6, n^-1 scale 4 per "
+                                 "pair; Plantard kernel (q<=12385): butterfly 3, pointwise 4, scale 3",
+                         "arith": "plantard" if plantard else "shoup"},
         "parity_ok": parity_ok,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -34,7 +34,8 @@ class NttError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(PKG_DIR, "libnttb200.so")
+    """The in-tree library; NTTB200_LIB points tuning experiments at another build of it."""
+    return os.environ.get("NTTB200_LIB") or os.path.join(PKG_DIR, "libnttb200.so")
 
 
 def build_library(jobs: int = 8) -> str:

@@ -32,6 +32,12 @@
 
 namespace nttb200 {
 
+#ifndef PLANT_OPAQUE
+#define PLANT_OPAQUE 1      /* tuning experiments, see DESIGN.md "what did not work" */
+#endif
+#ifndef PLANT_ADD3
+#define PLANT_ADD3 0
+#endif
 constexpr int PLANT_LIMB = 28;
 constexpr uint32_t PLANT_QMAX = 12385;     /* 28 * q * q < 2^32 */
 
@@ -47,12 +53,30 @@ struct PlantParams {
   uint32_t last_x;           /* (-n^-1 2^32)~ : multiplier of the sum branch of the last stage */
   uint32_t last_y;           /* (-n^-1 2^32 p_inv[1])~ : multiplier of its diff branch         */
   uint32_t qmul[16];         /* i * q, so that "+ b q" is a constant-bank operand         */
+  uint32_t zero;             /* always 0 (see add_alu)                                    */
   uint32_t ufwd[1 << R];     /* entries [1, 2^R) of the forward level table (w~)          */
   uint32_t uinv[1 << R];
 };
 
 __device__ __forceinline__ uint32_t plant_mul(uint32_t y, uint32_t wt, uint32_t q) {
-  return __umulhi(y * wt, q);
+  uint32_t t = __umulhi(y * wt, q);
+#if PLANT_OPAQUE
+  /* keep ptxas from folding the following add into the IMAD.HI (its addend is a 64-bit
+   * register pair: the fold costs two extra moves per butterfly) */
+  asm("" : "+r"(t));
+#endif
+  return t;
+}
+/* a + b as a THREE-input add (z is a kernel parameter that is always 0): ptxas turns plain
+ * two-input adds into IMAD.IADD to "balance" the pipes, but the fmaheavy pipe is the one
+ * that binds this kernel; a three-input add can only be an ALU-pipe IADD3 */
+__device__ __forceinline__ uint32_t add_alu(uint32_t a, uint32_t b, uint32_t z) {
+#if PLANT_ADD3
+  return a + b + z;
+#else
+  (void)z;
+  return a + b;
+#endif
 }
 
 /* ---- compile-time value bounds ----------------------------------------------------------
@@ -129,16 +153,16 @@ struct LaneTw1 {
 };
 
 /* CT butterfly: T = Y w mod q in [0,q); X' = X + T, Y' = X - T + q  (bounds grow by 1) */
-__device__ __forceinline__ void pl_ct(uint32_t &X, uint32_t &Y, uint32_t wt, uint32_t q) {
+__device__ __forceinline__ void pl_ct(uint32_t &X, uint32_t &Y, uint32_t wt, uint32_t q, uint32_t z) {
   const uint32_t T = plant_mul(Y, wt, q);
   Y = X - T + q;
-  X = X + T;
+  X = add_alu(X, T, z);
 }
 /* GS butterfly on two legs < b q: X' = X + Y (capped), Y' = (X - Y) w mod q in [0,q) */
 template <int B, typename PT>
 __device__ __forceinline__ void pl_gs(uint32_t &X, uint32_t &Y, uint32_t wt, const PT &P) {
   const uint32_t d = X - Y + P.qmul[B];
-  uint32_t s = X + Y;
+  uint32_t s = add_alu(X, Y, P.zero);
   if (2 * B > PLANT_CAP) s = csub(s, P.qmul[PLANT_CAP]);
   X = s;
   Y = plant_mul(d, wt, P.q);
@@ -163,7 +187,7 @@ __device__ __forceinline__ void pl_fwd_cols(uint32_t (&x)[SmallGeom<L>::NV],
 #pragma unroll
     for (int k = 0; k < Gm::NV; k++) {
       if (k & (1 << kb)) continue;
-      pl_ct(x[k], x[k | (1 << kb)], P.ufwd[(1 << s) + (k >> (kb + 1))], P.q);
+      pl_ct(x[k], x[k | (1 << kb)], P.ufwd[(1 << s) + (k >> (kb + 1))], P.q, P.zero);
     }
   }
 }
@@ -179,7 +203,7 @@ __device__ __forceinline__ void pl_fwd_rows(uint32_t (&x)[SmallGeom<L>::NV], con
       if (r & (1 << bit)) continue;
       const int g = r >> Gm::H;
       const int u = (r & (Gm::T - 1)) >> (bit + 1);
-      pl_ct(x[r], x[r | (1 << bit)], tw.get(g, lv, u), P.q);
+      pl_ct(x[r], x[r | (1 << bit)], tw.get(g, lv, u), P.q, P.zero);
     }
   }
 }
@@ -218,7 +242,7 @@ __device__ __forceinline__ void pl_inv_cols(uint32_t (&x)[SmallGeom<L>::NV],
         pl_gs_b(b, x[k], x[k2], P.uinv[t + (k >> (kb + 1))], P);
       } else {
         const uint32_t d = x[k] - x[k2] + P.qmul[b];
-        const uint32_t s = x[k] + x[k2];
+        const uint32_t s = add_alu(x[k], x[k2], P.zero);
         x[k2] = plant_mul(d, P.last_y, P.q);
         x[k] = plant_mul(s, P.last_x, P.q);
       }
@@ -335,7 +359,11 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
       if (pw.nb > 0) bv = csub(bv, P.qmul[pw.hb[0]]);
       if (pw.nb > 1) bv = csub(bv, P.qmul[pw.hb[1]]);
       if (pw.nb > 2) bv = csub(bv, P.qmul[pw.hb[2]]);
-      xa[k] = __umulhi(av * bv * P.qinv, q);
+      uint32_t v = __umulhi(av * bv * P.qinv, q);
+#if PLANT_OPAQUE
+      asm("" : "+r"(v));
+#endif
+      xa[k] = v;
     }
 
     if (Gm::H > 0) {

@@ -426,11 +426,19 @@ extern "C" int nttb200_ntt_batch_dev(nttb200_plan *P, int transform, int32_t *a,
 /* from pinned memory (nttb200_host_alloc) is a true async DMA; pageable memory also works  */
 /* (the driver stages it).                                                                */
 /* ------------------------------------------------------------------------------------ */
-static const int NSLOT = 3;
+static int env_int(const char *name, int dflt, int lo, int hi) {
+  const char *e = getenv(name);
+  if (!e) return dflt;
+  int v = atoi(e);
+  return v < lo ? lo : (v > hi ? hi : v);
+}
+/* ring depth and bytes per operand per slot (NTTB200_NSLOT / NTTB200_SLOT_MB: tuning knobs) */
+static int nslot() { static int v = env_int("NTTB200_NSLOT", 3, 1, 8); return v; }
+#define NSLOT nslot()
 
 static int ensure_slots(nttb200_plan *P, bool need_b) {
   if (!P->slots.empty()) return 0;
-  const size_t target_bytes = 8u << 20;                 /* per operand per slot */
+  const size_t target_bytes = (size_t)env_int("NTTB200_SLOT_MB", 8, 1, 256) << 20;   /* per operand per slot */
   P->slot_polys = std::max<size_t>(1, target_bytes / (P->n * sizeof(uint32_t)));
   P->slots.resize(NSLOT);
   for (auto &s : P->slots) {
