@@ -200,6 +200,11 @@ extern "C" void nttb200_plan_destroy(nttb200_plan *P) {
     cudaFree(s.d_a); cudaFree(s.d_b); cudaFree(s.d_c);
   }
   if (P->scratch) cudaFree(P->scratch);
+  for (auto &ln : P->lanes) {
+    if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamDestroy(ln.stream); }
+    if (ln.done) cudaEventDestroy(ln.done);
+  }
+  if (P->fork) cudaEventDestroy(P->fork);
   free_table(P->fwd_mixed); free_table(P->inv_mixed);
   free_table(P->fwd_plain); free_table(P->inv_plain);
   free_table(P->fwd_invroot); free_table(P->inv_fwdroot);
@@ -341,6 +346,7 @@ static int transform_dev(nttb200_plan *P, int transform, uint32_t *a, size_t bat
 /* large n: multi-pass kernels (ntt_large.cuh), batch processed in chunks whose scratch     */
 /* (a', b' between the passes) stays L2-resident                                          */
 /* ------------------------------------------------------------------------------------ */
+static int env_int(const char *name, int dflt, int lo, int hi);
 #define DECL_LARGE(name)                                                                          \
   int launch_polymul_large_chunk_##name(const nttb200_plan *, uint32_t *, const uint32_t *,       \
                                         const uint32_t *, uint32_t *, uint32_t *, size_t, cudaStream_t); \
@@ -350,24 +356,30 @@ DECL_LARGE(lazy)
 DECL_LARGE(harvey)
 DECL_LARGE(canon)
 
+/* The batch is cut into chunks; chunk i runs its three kernels on internal stream i % LANES
+ * with its own scratch (a', b'; c' over a'), so the column pass of one chunk overlaps the row
+ * pass of the previous one (tails and launch gaps are filled) while each chunk's scratch is
+ * small enough to stay in the 126 MB L2 between its passes.
+ * NTTB200_LARGE_SCRATCH_MB = scratch bytes per lane (default 32), NTTB200_LARGE_LANES (default 3). */
 static size_t large_scratch_budget() {
-  /* bytes of scratch (a' + b') per chunk; default 32 MiB = a quarter of the 126 MB L2 */
-  static size_t v = 0;
-  if (!v) {
-    const char *e = getenv("NTTB200_LARGE_SCRATCH_MB");
-    long mb = e ? atol(e) : 32;
-    if (mb < 1) mb = 1;
-    v = (size_t)mb << 20;
-  }
+  static size_t v = (size_t)env_int("NTTB200_LARGE_SCRATCH_MB", 32, 1, 65536) << 20;
   return v;
 }
+static int large_lanes() { static int v = env_int("NTTB200_LARGE_LANES", 3, 1, 8); return v; }
 
-static int ensure_scratch(nttb200_plan *P, size_t polys) {
-  if (P->scratch_polys >= polys) return 0;
+static int ensure_scratch(nttb200_plan *P, size_t polys, int lanes) {
+  if (P->scratch_polys >= polys && (int)P->lanes.size() >= lanes) return 0;
   if (P->scratch) cudaFree(P->scratch);
   P->scratch = nullptr; P->scratch_polys = 0;
-  NTT_CUDA(cudaMalloc(&P->scratch, polys * P->n * 2 * sizeof(uint32_t)));
+  NTT_CUDA(cudaMalloc(&P->scratch, (size_t)lanes * polys * P->n * 2 * sizeof(uint32_t)));
   P->scratch_polys = polys;
+  while ((int)P->lanes.size() < lanes) {
+    LargeLane ln;
+    NTT_CUDA(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+    NTT_CUDA(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+    P->lanes.push_back(ln);
+  }
+  if (!P->fork) NTT_CUDA(cudaEventCreateWithFlags(&P->fork, cudaEventDisableTiming));
   return 0;
 }
 
@@ -375,18 +387,33 @@ int launch_polymul_large(nttb200_plan *P, uint32_t *c, const uint32_t *a, const 
                          cudaStream_t st) {
   /* the scratch is per plan: concurrent device-resident calls on one plan must use one stream */
   const size_t chunk = std::max<size_t>(1, std::min<size_t>(batch, large_scratch_budget() / (P->n * 8ull)));
-  int rc = ensure_scratch(P, chunk);
+  const size_t nchunks = (batch + chunk - 1) / chunk;
+  const int lanes = (int)std::min<size_t>((size_t)large_lanes(), nchunks);
+  int rc = ensure_scratch(P, chunk, lanes);
   if (rc) return rc;
-  uint32_t *ta = P->scratch, *tb = P->scratch + chunk * P->n;
-  for (size_t done = 0; done < batch; done += chunk) {
+  if (lanes > 1) {                      /* fork: the lanes start after everything queued on st */
+    NTT_CUDA(cudaEventRecord(P->fork, st));
+    for (int l = 0; l < lanes; l++) NTT_CUDA(cudaStreamWaitEvent(P->lanes[l].stream, P->fork, 0));
+  }
+  size_t k = 0;
+  for (size_t done = 0; done < batch; done += chunk, k++) {
     const size_t nb = std::min(chunk, batch - done);
     const size_t o = done * P->n;
+    const int l = (int)(k % lanes);
+    cudaStream_t ls = lanes > 1 ? P->lanes[l].stream : st;
+    uint32_t *ta = P->scratch + (size_t)l * chunk * P->n * 2, *tb = ta + chunk * P->n;
     switch (P->arith) {
-      case ARITH_LAZY: rc = launch_polymul_large_chunk_lazy(P, c + o, a + o, b + o, ta, tb, nb, st); break;
-      case ARITH_HARVEY: rc = launch_polymul_large_chunk_harvey(P, c + o, a + o, b + o, ta, tb, nb, st); break;
-      default: rc = launch_polymul_large_chunk_canon(P, c + o, a + o, b + o, ta, tb, nb, st); break;
+      case ARITH_LAZY: rc = launch_polymul_large_chunk_lazy(P, c + o, a + o, b + o, ta, tb, nb, ls); break;
+      case ARITH_HARVEY: rc = launch_polymul_large_chunk_harvey(P, c + o, a + o, b + o, ta, tb, nb, ls); break;
+      default: rc = launch_polymul_large_chunk_canon(P, c + o, a + o, b + o, ta, tb, nb, ls); break;
     }
     if (rc) return rc;
+  }
+  if (lanes > 1) {                      /* join */
+    for (int l = 0; l < lanes; l++) {
+      NTT_CUDA(cudaEventRecord(P->lanes[l].done, P->lanes[l].stream));
+      NTT_CUDA(cudaStreamWaitEvent(st, P->lanes[l].done, 0));
+    }
   }
   return 0;
 }

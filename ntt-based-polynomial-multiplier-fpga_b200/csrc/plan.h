@@ -32,6 +32,11 @@ struct HostSlot {
   uint32_t *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;
 };
 
+struct LargeLane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+};
+
 struct nttb200_plan {
   uint32_t n = 0, logn = 0, q = 0, psi = 0, omega = 0, flags = 0;
   uint32_t n_inv = 0;
@@ -55,9 +60,11 @@ struct nttb200_plan {
   std::vector<HostSlot> slots;
   size_t slot_polys = 0;
 
-  /* large-n scratch (device), sized for scratch_polys polynomials */
+  /* large-n: internal stream lanes, each with scratch for scratch_polys polynomials */
   uint32_t *scratch = nullptr;
   size_t scratch_polys = 0;
+  std::vector<LargeLane> lanes;
+  cudaEvent_t fork = nullptr;
 };
 
 /* error plumbing (nttb200.cu) */
