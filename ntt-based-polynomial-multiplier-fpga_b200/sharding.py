@@ -26,6 +26,10 @@ def init_distributed(backend: str):
     rank, world, _ = env_rank_world()
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29511")
+    # bench.py prints exactly one JSON line on stdout: keep NCCL's "NCCL version ..." banner
+    # (NCCL_DEBUG=VERSION/INFO in some environments) out of it
+    if not os.environ.get("NTTB200_KEEP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     if world > 1 and not dist.is_initialized():
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return dist
