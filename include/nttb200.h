@@ -163,6 +163,11 @@ void nttb200_dev_free(void *p);
 int nttb200_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes, void *stream);
 int nttb200_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes, void *stream);
 int nttb200_stream_sync(void *stream);
+/* streams for callers without the CUDA runtime (the Terasic-ABI shim): create / destroy /
+ * query (1 = all work done, 0 = still running, < 0 = error) */
+void *nttb200_stream_create(void);
+void nttb200_stream_destroy(void *stream);
+int nttb200_stream_query(void *stream);
 
 /* ---- measurement helpers (used by bench.py; device-side, no host data) ---------- */
 /* runs `iters` dependent IMAD / IMAD.HI / IADD3 chains on every SM and returns the

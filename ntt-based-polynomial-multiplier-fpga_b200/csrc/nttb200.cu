@@ -637,6 +637,21 @@ extern "C" int nttb200_memcpy_d2h(void *dst, const void *src, size_t bytes, void
   NTT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   return 0;
 }
+extern "C" void *nttb200_stream_create(void) {
+  cudaStream_t s = nullptr;
+  if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) {
+    nttb200_fail(NTTB200_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  return (void *)s;
+}
+extern "C" void nttb200_stream_destroy(void *stream) { if (stream) cudaStreamDestroy((cudaStream_t)stream); }
+extern "C" int nttb200_stream_query(void *stream) {
+  cudaError_t e = cudaStreamQuery((cudaStream_t)stream);
+  if (e == cudaSuccess) return 1;
+  if (e == cudaErrorNotReady) { return 0; }
+  return nttb200_fail(NTTB200_ECUDA, "cudaStreamQuery: %s", cudaGetErrorString(e));
+}
 extern "C" int nttb200_stream_sync(void *stream) {
   NTT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return 0;
