@@ -134,6 +134,32 @@ enum nttb200_dataflow {
 int nttb200_ntt_table_batch(uint32_t n, uint32_t q, int dataflow, const uint32_t *p, int32_t *a,
                             size_t batch);
 
+/* ---- exact emulation of the Longa-Naehrig ("RED") surface, q = 12289 hard-wired as in the
+ * reference (R/NTT-RED/ntt_red.c:24): signed, UNREDUCED 32-bit outputs, bit-identical to
+ * ntt_red_{ct,gs}_{rev2std,std2rev} / mulntt_red_ct_* / nttmul_red_gs_* (ntt_red.c:244-554)
+ * run with the caller's table p (n entries, already multiplied by 1/3 as the reference's
+ * tables are).  skip_j0 = 1 for the un-merged entry points, which do the j = 0 butterflies
+ * without a multiplication.  `dataflow` as enum nttb200_dataflow. */
+int nttb200_red_ntt_table_batch(uint32_t n, int dataflow, int skip_j0, const int32_t *p, int32_t *a,
+                                size_t batch);
+enum nttb200_red_op {
+  NTTB200_RED_NORMALIZE = 0,      /* normalize               ntt_red.c:72-82   */
+  NTTB200_RED_NORMALIZE_INV3 = 1, /* normalize_inv3          ntt_red.c:87-97   */
+  NTTB200_RED_SHIFT = 2,          /* shift_array             ntt_red.c:103-111 */
+  NTTB200_RED_REDUCE = 3,         /* reduce_array            ntt_red.c:124-130 */
+  NTTB200_RED_REDUCE_TWICE = 4,   /* reduce_array_twice      ntt_red.c:138-144 */
+  NTTB200_RED_CORRECT = 5,        /* correct                 ntt_red.c:150-169 */
+  NTTB200_RED_MUL_RED = 6,        /* mul_reduce_array[16]    ntt_red.c:197-211: c[i] = mul_red(a[i], b[i]) */
+  NTTB200_RED_SCALAR_MUL_RED = 7  /* scalar_mul_reduce_array ntt_red.c:217-223 */
+};
+/* c may alias a; b is read by MUL_RED only, scalar by SCALAR_MUL_RED only */
+int nttb200_red_elementwise_batch(int op, int32_t *c, const int32_t *a, const int32_t *b, int32_t scalar,
+                                  size_t count);
+/* in-place bit-reversal permutation of every row (bitrev_shuffle, R/NTT/ntt.C:27-44) and the
+ * table-driven variant (shuffle_with_table, ntt.C:50-59: npairs swaps a[p[i][0]] <-> a[p[i][1]]) */
+int nttb200_bitrev_shuffle_batch(int32_t *a, uint32_t n, size_t batch);
+int nttb200_shuffle_with_table(int32_t *a, size_t words, const uint16_t *pairs, uint32_t npairs);
+
 /* ---- elementwise surface (R/NTT/ntt.C:119-153), batched, host buffers ----------- */
 int nttb200_mul_array_batch(nttb200_plan *plan, int32_t *c, const int32_t *a, const int32_t *b,
                             size_t batch);                       /* c[i] = a[i]*b[i] mod q   */

@@ -51,6 +51,30 @@ void mul_array16(int32_t *a, uint32_t n, const uint16_t *p);                    
 void mul_array(int32_t *c, uint32_t n, const int32_t *a, const int32_t *b);       /* ntt.C:131-137 */
 void scalar_mul_array(int32_t *a, uint32_t n, int32_t c);                         /* ntt.C:147-153 */
 
+/* ---- permutations (R/NTT/ntt.h:23-30) ------------------------------------------------------ */
+void bitrev_shuffle(int32_t *a, uint32_t n);                                   /* ntt.C:27-44 */
+void shuffle_with_table(int32_t *a, const uint16_t p[][2], uint32_t n);          /* ntt.C:50-59 */
+
+/* ---- Longa-Naehrig surface (R/NTT-RED/ntt_red.h:65-284), exact: the transforms return the
+ * same UNREDUCED signed values as the reference (R/NTT-RED/ntt_red256.h:18) ------------------ */
+void normalize(int32_t *a, uint32_t n);                                        /* ntt_red.c:72-82   */
+void normalize_inv3(int32_t *a, uint32_t n);                                   /* ntt_red.c:87-97   */
+void shift_array(int32_t *a, uint32_t n);                                      /* ntt_red.c:103-111 */
+void reduce_array(int32_t *a, uint32_t n);                                     /* ntt_red.c:124-130 */
+void reduce_array_twice(int32_t *a, uint32_t n);                               /* ntt_red.c:138-144 */
+void correct(int32_t *a, uint32_t n);                                          /* ntt_red.c:150-169 */
+void mul_reduce_array16(int32_t *a, uint32_t n, const int16_t *p);             /* ntt_red.c:197-203 */
+void mul_reduce_array(int32_t *c, uint32_t n, const int32_t *a, const int32_t *b);   /* ntt_red.c:205-211 */
+void scalar_mul_reduce_array(int32_t *a, uint32_t n, int32_t c);               /* ntt_red.c:217-223 */
+void ntt_red_ct_rev2std(int32_t *a, uint32_t n, const int16_t *p);             /* ntt_red.c:244-270 */
+void mulntt_red_ct_rev2std(int32_t *a, uint32_t n, const int16_t *p);          /* ntt_red.c:280-305 */
+void ntt_red_ct_std2rev(int32_t *a, uint32_t n, const int16_t *p);             /* ntt_red.c:321-355 */
+void mulntt_red_ct_std2rev(int32_t *a, uint32_t n, const int16_t *p);          /* ntt_red.c:368-400 */
+void ntt_red_gs_rev2std(int32_t *a, uint32_t n, const int16_t *p);             /* ntt_red.c:414-443 */
+void nttmul_red_gs_rev2std(int32_t *a, uint32_t n, const int16_t *p);          /* ntt_red.c:456-480 */
+void ntt_red_gs_std2rev(int32_t *a, uint32_t n, const int16_t *p);             /* ntt_red.c:495-520 */
+void nttmul_red_gs_std2rev(int32_t *a, uint32_t n, const int16_t *p);          /* ntt_red.c:534-554 */
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,6 +105,23 @@ def lib() -> C.CDLL:
     L.mul_array.restype = None
     L.scalar_mul_array.argtypes = [i32p, C.c_uint32, C.c_int32]
     L.scalar_mul_array.restype = None
+    for nm in ("ntt_red_ct_rev2std", "mulntt_red_ct_rev2std", "ntt_red_ct_std2rev", "mulntt_red_ct_std2rev",
+               "ntt_red_gs_rev2std", "nttmul_red_gs_rev2std", "ntt_red_gs_std2rev", "nttmul_red_gs_std2rev",
+               "mul_reduce_array16", "shuffle_with_table"):
+        getattr(L, nm).argtypes = [i32p, C.c_uint32, vp] if nm != "shuffle_with_table" else [i32p, vp, C.c_uint32]
+        getattr(L, nm).restype = None
+    for nm in ("normalize", "normalize_inv3", "shift_array", "reduce_array", "reduce_array_twice", "correct",
+               "bitrev_shuffle"):
+        getattr(L, nm).argtypes = [i32p, C.c_uint32]
+        getattr(L, nm).restype = None
+    L.mul_reduce_array.argtypes = [i32p, C.c_uint32, i32p, i32p]
+    L.mul_reduce_array.restype = None
+    L.scalar_mul_reduce_array.argtypes = [i32p, C.c_uint32, C.c_int32]
+    L.scalar_mul_reduce_array.restype = None
+    L.nttb200_red_ntt_table_batch.argtypes = [C.c_uint32, C.c_int, C.c_int, i32p, i32p, sz]
+    L.nttb200_red_elementwise_batch.argtypes = [C.c_int, i32p, i32p, i32p, C.c_int32, sz]
+    L.nttb200_bitrev_shuffle_batch.argtypes = [i32p, C.c_uint32, sz]
+    L.nttb200_shuffle_with_table.argtypes = [i32p, sz, vp, C.c_uint32]
     L.nttb200_legacy_set_clobber.argtypes = [C.c_int]
     L.nttb200_legacy_set_clobber.restype = None
     _lib = L
@@ -268,6 +285,20 @@ class legacy:
         x = np.ascontiguousarray(a, dtype=np.int32).copy()
         p = np.ascontiguousarray(table16, dtype=np.uint16)
         getattr(lib(), name)(_ptr(x), x.shape[0], _ptr(p))
+        return x
+
+    @staticmethod
+    def red_transform(name: str, a: np.ndarray, table16: np.ndarray) -> np.ndarray:
+        """ntt_red_* / mulntt_red_* / nttmul_red_* with the caller's int16 table; unreduced output."""
+        x = np.ascontiguousarray(a, dtype=np.int32).copy()
+        p = np.ascontiguousarray(table16, dtype=np.int16)
+        getattr(lib(), name)(_ptr(x), x.shape[0], _ptr(p))
+        return x
+
+    @staticmethod
+    def red_helper(name: str, a: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(a, dtype=np.int32).copy()
+        getattr(lib(), name)(_ptr(x), x.shape[0])
         return x
 
     @staticmethod

@@ -113,3 +113,55 @@ void scalar_mul_array(int32_t *a, uint32_t n, int32_t c) {
   elementwise(a, n, a, cv);
   free(cv);
 }
+
+/* ---- permutations ------------------------------------------------------------------------ */
+void bitrev_shuffle(int32_t *a, uint32_t n) {
+  if (nttb200_bitrev_shuffle_batch(a, n, 1) != 0) die("nttb200_bitrev_shuffle_batch");
+}
+void shuffle_with_table(int32_t *a, const uint16_t p[][2], uint32_t n) {
+  /* the reference does not pass the array length: it is the largest index in the table + 1 */
+  size_t words = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    if ((size_t)p[i][0] + 1 > words) words = (size_t)p[i][0] + 1;
+    if ((size_t)p[i][1] + 1 > words) words = (size_t)p[i][1] + 1;
+  }
+  if (words && nttb200_shuffle_with_table(a, words, &p[0][0], n) != 0) die("nttb200_shuffle_with_table");
+}
+
+/* ---- Longa-Naehrig surface, exact ------------------------------------------------------------ */
+static void red_op(int op, int32_t *c, const int32_t *a, const int32_t *b, int32_t sc, uint32_t n) {
+  if (nttb200_red_elementwise_batch(op, c, a, b, sc, n) != 0) die("nttb200_red_elementwise_batch");
+}
+void normalize(int32_t *a, uint32_t n) { red_op(NTTB200_RED_NORMALIZE, a, a, NULL, 0, n); }
+void normalize_inv3(int32_t *a, uint32_t n) { red_op(NTTB200_RED_NORMALIZE_INV3, a, a, NULL, 0, n); }
+void shift_array(int32_t *a, uint32_t n) { red_op(NTTB200_RED_SHIFT, a, a, NULL, 0, n); }
+void reduce_array(int32_t *a, uint32_t n) { red_op(NTTB200_RED_REDUCE, a, a, NULL, 0, n); }
+void reduce_array_twice(int32_t *a, uint32_t n) { red_op(NTTB200_RED_REDUCE_TWICE, a, a, NULL, 0, n); }
+void correct(int32_t *a, uint32_t n) { red_op(NTTB200_RED_CORRECT, a, a, NULL, 0, n); }
+void mul_reduce_array(int32_t *c, uint32_t n, const int32_t *a, const int32_t *b) {
+  red_op(NTTB200_RED_MUL_RED, c, a, b, 0, n);
+}
+void scalar_mul_reduce_array(int32_t *a, uint32_t n, int32_t c) { red_op(NTTB200_RED_SCALAR_MUL_RED, a, a, NULL, c, n); }
+void mul_reduce_array16(int32_t *a, uint32_t n, const int16_t *p) {
+  int32_t *p32 = (int32_t *)malloc(sizeof(int32_t) * (n ? n : 1));
+  if (!p32) die("malloc");
+  for (uint32_t i = 0; i < n; i++) p32[i] = p[i];
+  red_op(NTTB200_RED_MUL_RED, a, a, p32, 0, n);
+  free(p32);
+}
+static void red_transform(int32_t *a, uint32_t n, const int16_t *p, int dataflow, int skip_j0) {
+  int32_t *p32 = (int32_t *)malloc(sizeof(int32_t) * (n ? n : 1));
+  if (!p32) die("malloc");
+  for (uint32_t i = 0; i < n; i++) p32[i] = p[i];
+  int rc = nttb200_red_ntt_table_batch(n, dataflow, skip_j0, p32, a, 1);
+  free(p32);
+  if (rc != 0) die("nttb200_red_ntt_table_batch");
+}
+void ntt_red_ct_rev2std(int32_t *a, uint32_t n, const int16_t *p)    { red_transform(a, n, p, NTTB200_DF_CT_REV2STD, 1); }
+void mulntt_red_ct_rev2std(int32_t *a, uint32_t n, const int16_t *p) { red_transform(a, n, p, NTTB200_DF_CT_REV2STD, 0); }
+void ntt_red_ct_std2rev(int32_t *a, uint32_t n, const int16_t *p)    { red_transform(a, n, p, NTTB200_DF_CT_STD2REV, 1); }
+void mulntt_red_ct_std2rev(int32_t *a, uint32_t n, const int16_t *p) { red_transform(a, n, p, NTTB200_DF_CT_STD2REV, 0); }
+void ntt_red_gs_rev2std(int32_t *a, uint32_t n, const int16_t *p)    { red_transform(a, n, p, NTTB200_DF_GS_REV2STD, 1); }
+void nttmul_red_gs_rev2std(int32_t *a, uint32_t n, const int16_t *p) { red_transform(a, n, p, NTTB200_DF_GS_REV2STD, 0); }
+void ntt_red_gs_std2rev(int32_t *a, uint32_t n, const int16_t *p)    { red_transform(a, n, p, NTTB200_DF_GS_STD2REV, 1); }
+void nttmul_red_gs_std2rev(int32_t *a, uint32_t n, const int16_t *p) { red_transform(a, n, p, NTTB200_DF_GS_STD2REV, 0); }

@@ -609,6 +609,120 @@ extern "C" int nttb200_ntt_table_batch(uint32_t n, uint32_t q, int dataflow, con
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* exact emulation of the reference's RED surface and the permutation helpers (q = 12289)   */
+/* ------------------------------------------------------------------------------------ */
+template <typename F>
+static int with_device_copy(void *host, size_t bytes, F &&body) {
+  if (nttb200_device_count() <= 0) return nttb200_fail(NTTB200_ECUDA, "no CUDA device (there is no CPU fallback)");
+  void *d = nullptr;
+  cudaError_t e = cudaMalloc(&d, bytes ? bytes : 1);
+  if (e == cudaSuccess) e = cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice);
+  int rc = 0;
+  if (e == cudaSuccess) rc = body(d);
+  if (e == cudaSuccess && rc == 0) e = cudaGetLastError();
+  if (e == cudaSuccess && rc == 0) e = cudaMemcpy(host, d, bytes, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return nttb200_fail(NTTB200_ECUDA, "%s", cudaGetErrorString(e));
+  return rc;
+}
+
+extern "C" int nttb200_red_ntt_table_batch(uint32_t n, int dataflow, int skip_j0, const int32_t *p, int32_t *a,
+                                           size_t batch) {
+  using namespace nttb200;
+  if (!p || !a) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
+  if (n < 2 || (n & (n - 1))) return nttb200_fail(NTTB200_EPARAM, "n=%u is not a power of two", n);
+  if (dataflow < 0 || dataflow > 3) return nttb200_fail(NTTB200_EPARAM, "unknown dataflow %d", dataflow);
+  g_launches = 0;
+  if (batch == 0) return 0;
+  const uint32_t logn = ht_log2(n);
+  return with_device_copy(a, batch * n * sizeof(int32_t), [&](void *d_a) -> int {
+    int32_t *d_tab = nullptr;
+    NTT_CUDA(cudaMalloc(&d_tab, n * sizeof(int32_t)));
+    cudaError_t e = cudaMemcpy(d_tab, p, n * sizeof(int32_t), cudaMemcpyHostToDevice);
+    const unsigned long long pairs = (unsigned long long)batch * (n / 2);
+    const int grid = grid_1d(pairs, 256, current_sms());
+    const bool descending = (dataflow == DF_CT_STD2REV || dataflow == DF_GS_STD2REV);
+    for (uint32_t s = 0; s < logn && e == cudaSuccess; s++) {
+      const uint32_t lh = descending ? (logn - 1 - s) : s;
+      const uint32_t half = 1u << lh;
+      int32_t *x = (int32_t *)d_a;
+      switch (dataflow) {
+        case DF_CT_STD2REV: generic_red_stage_kernel<DF_CT_STD2REV><<<grid, 256>>>(x, d_tab, n, logn, half, lh, pairs, skip_j0); break;
+        case DF_GS_REV2STD: generic_red_stage_kernel<DF_GS_REV2STD><<<grid, 256>>>(x, d_tab, n, logn, half, lh, pairs, skip_j0); break;
+        case DF_CT_REV2STD: generic_red_stage_kernel<DF_CT_REV2STD><<<grid, 256>>>(x, d_tab, n, logn, half, lh, pairs, skip_j0); break;
+        default: generic_red_stage_kernel<DF_GS_STD2REV><<<grid, 256>>>(x, d_tab, n, logn, half, lh, pairs, skip_j0); break;
+      }
+      nttb200_count_launch(1);
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(d_tab);
+    if (e != cudaSuccess) return nttb200_fail(NTTB200_ECUDA, "RED transform: %s", cudaGetErrorString(e));
+    return 0;
+  });
+}
+
+extern "C" int nttb200_red_elementwise_batch(int op, int32_t *c, const int32_t *a, const int32_t *b, int32_t scalar,
+                                             size_t count) {
+  using namespace nttb200;
+  if (!c || !a || (op == RED_OP_MUL_RED && !b)) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
+  if (op < 0 || op > RED_OP_SCALAR_MUL_RED) return nttb200_fail(NTTB200_EPARAM, "unknown RED op %d", op);
+  if (nttb200_device_count() <= 0) return nttb200_fail(NTTB200_ECUDA, "no CUDA device (there is no CPU fallback)");
+  g_launches = 0;
+  if (count == 0) return 0;
+  const size_t bytes = count * sizeof(int32_t);
+  int32_t *d_a = nullptr, *d_b = nullptr;
+  cudaError_t e = cudaMalloc(&d_a, bytes);
+  if (e == cudaSuccess) e = cudaMemcpy(d_a, a, bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && op == RED_OP_MUL_RED) {
+    e = cudaMalloc(&d_b, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(d_b, b, bytes, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess) {
+    red_elementwise_kernel<<<grid_1d(count, 256, current_sms()), 256>>>(op, d_a, d_a, d_b, scalar, count);
+    nttb200_count_launch(1);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(c, d_a, bytes, cudaMemcpyDeviceToHost);
+  cudaFree(d_a);
+  cudaFree(d_b);
+  if (e != cudaSuccess) return nttb200_fail(NTTB200_ECUDA, "RED elementwise: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int nttb200_bitrev_shuffle_batch(int32_t *a, uint32_t n, size_t batch) {
+  if (!a) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
+  if (n == 0 || (n & (n - 1))) return nttb200_fail(NTTB200_EPARAM, "n=%u is not a power of two", n);
+  g_launches = 0;
+  if (batch == 0 || n < 4) return nttb200_device_count() > 0 ? 0 : nttb200_fail(NTTB200_ECUDA, "no CUDA device (there is no CPU fallback)");
+  const unsigned long long total = (unsigned long long)batch * n;
+  return with_device_copy(a, total * sizeof(int32_t), [&](void *d) -> int {
+    nttb200::bitrev_shuffle_kernel<<<grid_1d(total, 256, current_sms()), 256>>>((uint32_t *)d, ht_log2(n), total);
+    nttb200_count_launch(1);
+    return 0;
+  });
+}
+
+extern "C" int nttb200_shuffle_with_table(int32_t *a, size_t words, const uint16_t *pairs, uint32_t npairs) {
+  if (!a || (!pairs && npairs)) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
+  for (uint32_t i = 0; i < 2 * npairs; i++)
+    if (pairs[i] >= words) return nttb200_fail(NTTB200_EPARAM, "swap index %u outside the array", pairs[i]);
+  g_launches = 0;
+  return with_device_copy(a, words * sizeof(int32_t), [&](void *d) -> int {
+    uint16_t *d_p = nullptr;
+    NTT_CUDA(cudaMalloc(&d_p, (npairs ? npairs : 1) * 2 * sizeof(uint16_t)));
+    cudaError_t e = cudaMemcpy(d_p, pairs, npairs * 2 * sizeof(uint16_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+      nttb200::shuffle_table_kernel<<<1, 32>>>((uint32_t *)d, d_p, npairs);
+      nttb200_count_launch(1);
+      e = cudaDeviceSynchronize();
+    }
+    cudaFree(d_p);
+    if (e != cudaSuccess) return nttb200_fail(NTTB200_ECUDA, "shuffle: %s", cudaGetErrorString(e));
+    return 0;
+  });
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* memory helpers                                                                        */
 /* ------------------------------------------------------------------------------------ */
 extern "C" void *nttb200_host_alloc(size_t bytes) {

@@ -304,6 +304,105 @@ def test_legacy_surface(gpu, golden, oracle):
     assert (gpu.legacy.scalar_mul_array(x, 12241) == x.astype(np.int64) * 12241 % Q).all()
 
 
+RED_TRANSFORMS = {   # golden transform id -> (reference function, red table kind); R/NTT-RED/ntt_red256.h:21-70
+    100: ("ntt_red_ct_rev2std", 3), 101: ("ntt_red_gs_rev2std", 4), 102: ("ntt_red_ct_std2rev", 4),
+    103: ("ntt_red_gs_std2rev", 3), 104: ("ntt_red_ct_rev2std", 5), 105: ("ntt_red_gs_rev2std", 6),
+    106: ("ntt_red_ct_std2rev", 6), 107: ("ntt_red_gs_std2rev", 5), 108: ("mulntt_red_ct_rev2std", 7),
+    109: ("mulntt_red_ct_std2rev", 8), 110: ("nttmul_red_gs_rev2std", 10), 111: ("nttmul_red_gs_std2rev", 9)}
+
+
+def test_red_surface_exact_unreduced_outputs(gpu, golden, oracle):
+    """The Longa-Naehrig functions return UNREDUCED signed int32 values (ntt_red256.h:18); the GPU
+    emulation must reproduce them bit for bit: golden outputs of the compiled reference, then the
+    oracle's restatement on other sizes and on worst-case inputs."""
+    cin = golden["red_transform_in"]
+    for tid, (fn, kind) in RED_TRANSFORMS.items():
+        for r in (0, 5, 15):
+            got = gpu.legacy.red_transform(fn, cin[r], golden[f"red_table_{kind}"])
+            assert (got == golden[f"transform_{tid}"][r]).all(), fn
+    # batch entry point, other sizes, extreme admissible inputs (|a| <= 21499, ntt_red.h:169-173)
+    L = gpu.lib()
+    for n in (8, 64, 256, 1024):
+        psi = oracle.psi(n, Q, 0)
+        a = oracle.random((9, n), 2 * 21499 + 1, SEED + n).astype(np.int32) - 21499
+        a[0] = 21499
+        a[1] = -21499
+        for df, name, skip0, kind in ((0, "ct_std2rev", 1, 4), (0, "mulntt_ct_std2rev", 0, 8),
+                                      (1, "gs_rev2std", 1, 6), (1, "nttmul_gs_rev2std", 0, 10),
+                                      (2, "ct_rev2std", 1, 3), (2, "mulntt_ct_rev2std", 0, 7),
+                                      (3, "gs_std2rev", 1, 5), (3, "nttmul_gs_std2rev", 0, 9)):
+            tab = oracle.red_table(kind, n, psi).astype(np.int32)
+            x = a.copy()
+            assert L.nttb200_red_ntt_table_batch(n, df, skip0, tab.ctypes.data, x.ctypes.data, x.shape[0]) == 0
+            assert (x == oracle.red_transform(name, a, tab)).all(), (n, name)
+
+
+def test_red_helpers_and_permutations(gpu, golden, oracle):
+    rng = np.random.default_rng(5)
+    x = rng.integers(-(1 << 30), 1 << 30, 1000).astype(np.int32)
+    x[:4] = (0, -1, 12288, -12289)
+    Qc = 12289
+    assert (gpu.legacy.red_helper("normalize", x) == x.astype(np.int64) % Qc).all()
+    assert (gpu.legacy.red_helper("normalize_inv3", x) == x.astype(np.int64) * 8193 % Qc).all()
+    red = lambda v: 3 * (v & 4095) - (v >> 12)
+    assert (gpu.legacy.red_helper("reduce_array", x) == red(x.astype(np.int64))).all()
+    assert (gpu.legacy.red_helper("reduce_array_twice", x) == red(red(x.astype(np.int64)))).all()
+    c = rng.integers(0, Qc, 777).astype(np.int32)
+    assert (gpu.legacy.red_helper("shift_array", c) == np.where(c > 6144, c - Qc, c)).all()
+    r = rng.integers(-Qc, 2 * Qc, 777).astype(np.int32)
+    assert (gpu.legacy.red_helper("correct", r) == r.astype(np.int64) % Qc).all()
+    a, b = cen(rng, 500), cen(rng, 500)
+    z = a.astype(np.int64) * b
+    want = (3 * (z & 4095) - (z >> 12)).astype(np.int32)
+    L = gpu.lib()
+    out = np.zeros_like(a)
+    L.mul_reduce_array(out.ctypes.data, a.size, a.ctypes.data, b.ctypes.data)
+    assert (out == want).all()
+    y = a.copy()
+    L.scalar_mul_reduce_array(y.ctypes.data, y.size, 8822)       # ntt_red256_rescale8
+    z = a.astype(np.int64) * 8822
+    assert (y == 3 * (z & 4095) - (z >> 12)).all()
+    t16 = golden["red_table_0"][:256].astype(np.int16)
+    y = a[:256].copy()
+    L.mul_reduce_array16(y.ctypes.data, 256, t16.ctypes.data)
+    z = a[:256].astype(np.int64) * t16
+    assert (y == 3 * (z & 4095) - (z >> 12)).all()
+    # the reference's optimized product, composed from the exact pieces (ntt_red256.C:5-27)
+    fa, fb = golden["fixture_a"].astype(np.int32), golden["fixture_b"].astype(np.int32)
+    lg = gpu.legacy
+    def fwd(v):
+        v = lg.red_helper("shift_array", v)
+        L.mul_reduce_array16(v.ctypes.data, 256, golden["red_table_0"].astype(np.int16).ctypes.data)
+        v = lg.red_transform("ntt_red_ct_std2rev", v, golden["red_table_4"])
+        return lg.red_helper("reduce_array", v)
+    ha, hb = fwd(fa.copy()), fwd(fb.copy())
+    hc = np.zeros(256, np.int32)
+    L.mul_reduce_array(hc.ctypes.data, 256, ha.ctypes.data, hb.ctypes.data)
+    hc = lg.red_helper("reduce_array_twice", hc)
+    hc = lg.red_transform("ntt_red_ct_rev2std", hc, golden["red_table_5"])
+    L.mul_reduce_array16(hc.ctypes.data, 256, golden["red_table_2"].astype(np.int16).ctypes.data)
+    hc = lg.red_helper("correct", lg.red_helper("reduce_array_twice", hc))
+    assert (hc == golden["fixture_c"]).all()
+    # permutations
+    for n in (2, 8, 256, 4096):
+        v = rng.integers(0, 1 << 30, n).astype(np.int32)
+        bits = n.bit_length() - 1
+        rev = np.array([int(format(i, f"0{bits}b")[::-1], 2) for i in range(n)])
+        assert (gpu.legacy.red_helper("bitrev_shuffle", v) == v[rev]).all()
+    v = rng.integers(0, 1 << 30, 64).astype(np.int32)
+    pairs = np.array([[1, 32], [2, 16], [3, 48], [5, 40]], dtype=np.uint16)
+    w = v.copy()
+    L.shuffle_with_table(w.ctypes.data, pairs.ctypes.data, len(pairs))
+    e = v.copy()
+    for j, k in pairs:
+        e[j], e[k] = e[k], e[j]
+    assert (w == e).all()
+
+
+def cen(rng, n):
+    return rng.integers(-6144, 6145, n).astype(np.int32)
+
+
 def test_elementwise_batch(gpu, oracle):
     for n, q in ((256, 12289), (1024, 2013265921)):
         p = gpu.Plan(n, q)
