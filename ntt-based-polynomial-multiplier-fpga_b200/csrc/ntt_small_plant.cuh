@@ -35,6 +35,9 @@ namespace nttb200 {
 #ifndef PLANT_OPAQUE
 #define PLANT_OPAQUE 1      /* tuning experiments, see DESIGN.md "what did not work" */
 #endif
+#ifndef PLANT_MULHI
+#define PLANT_MULHI 3
+#endif
 #ifndef PLANT_ADD3
 #define PLANT_ADD3 0
 #endif
@@ -58,11 +61,24 @@ struct PlantParams {
   uint32_t uinv[1 << R];
 };
 
+/* floor(p q / 2^32).  Written as mul.wide + unpack rather than mul.hi: ptxas folds an add that
+ * follows an IMAD.HI into its addend and, when the product has two such consumers (every
+ * value in the GS network: X + Y and X - Y), DUPLICATES the 2-slot IMAD.HI -- 32 extra per
+ * n=256 product.  IMAD.WIDE has the same issue cost and is left alone (-10 % fmaheavy slots,
+ * +6..9 % throughput measured). */
+__device__ __forceinline__ uint32_t mulhi_nofold(uint32_t p, uint32_t q) {
+#if PLANT_MULHI == 3
+  uint32_t hi, lo;
+  asm("{ .reg .u64 w; mul.wide.u32 w, %2, %3; mov.b64 {%1, %0}, w; }" : "=r"(hi), "=r"(lo) : "r"(p), "r"(q));
+  (void)lo;
+  return hi;
+#else
+  return __umulhi(p, q);
+#endif
+}
 __device__ __forceinline__ uint32_t plant_mul(uint32_t y, uint32_t wt, uint32_t q) {
-  uint32_t t = __umulhi(y * wt, q);
+  uint32_t t = mulhi_nofold(y * wt, q);
 #if PLANT_OPAQUE
-  /* keep ptxas from folding the following add into the IMAD.HI (its addend is a 64-bit
-   * register pair: the fold costs two extra moves per butterfly) */
   asm("" : "+r"(t));
 #endif
   return t;
@@ -359,7 +375,7 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
       if (pw.nb > 0) bv = csub(bv, P.qmul[pw.hb[0]]);
       if (pw.nb > 1) bv = csub(bv, P.qmul[pw.hb[1]]);
       if (pw.nb > 2) bv = csub(bv, P.qmul[pw.hb[2]]);
-      uint32_t v = __umulhi(av * bv * P.qinv, q);
+      uint32_t v = mulhi_nofold(av * bv * P.qinv, q);
 #if PLANT_OPAQUE
       asm("" : "+r"(v));
 #endif

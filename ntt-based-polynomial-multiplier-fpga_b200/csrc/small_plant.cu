@@ -8,8 +8,11 @@
 namespace {
 using namespace nttb200;
 
+#ifndef PLANT_WARPS
+#define PLANT_WARPS 8
+#endif
 template <int L> struct PlantCfg {
-  static constexpr int WARPS = (L >= 9) ? 4 : 8;
+  static constexpr int WARPS = (L >= 9) ? 4 : PLANT_WARPS;
   static constexpr bool TWREG = (L <= 8);
 };
 /* resident CTAs per SM the kernel is compiled for (register cap).  Measured on B200 (c2:
