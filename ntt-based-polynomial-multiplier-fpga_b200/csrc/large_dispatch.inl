@@ -13,7 +13,7 @@
 namespace {
 using namespace nttb200;
 
-constexpr int LR = 8;           /* row length 2^LR */
+constexpr int LR = LARGE_LR;    /* row length 2^LR */
 constexpr int ROW_WARPS = 8;
 
 inline uint2 lshoup_pair(uint64_t w, uint32_t q) {

@@ -47,6 +47,8 @@ struct LargeParams {
   uint2 one;                  /* (1, floor(2^32/q)): Shoup pair that only reduces            */
 };
 
+constexpr int LARGE_LR = 8;       /* rows of 2^8 coefficients: fixed, so row strides are immediates */
+
 template <int K1>
 struct ColGeom {
   static constexpr int RA = (K1 <= 4) ? K1 : (K1 + 1) / 2;   /* stages of the phase on the high row bits */
@@ -79,14 +81,14 @@ large_cols_fwd_kernel(const __grid_constant__ LargeParams P) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
-  const uint32_t lr = P.logn - K1;                        /* log2 of the row length */
-  const uint32_t tiles = 1u << (lr - 5);
+  constexpr int lr = LARGE_LR;                            /* log2 of the row length */
+  constexpr uint32_t tiles = 1u << (lr - 5);
   const unsigned long long unit = blockIdx.x;
   const uint32_t tile = (uint32_t)(unit & (tiles - 1));
   const unsigned long long po = unit >> (lr - 5);
-  const uint32_t op = (uint32_t)(po % P.nops);
-  const unsigned long long poly = po / P.nops;
-  const size_t base = ((size_t)poly << P.logn) + tile * 32 + lane;
+  const uint32_t op = (P.nops == 2) ? (uint32_t)(po & 1) : 0u;
+  const unsigned long long poly = (P.nops == 2) ? (po >> 1) : po;
+  const size_t base = ((size_t)poly << (K1 + lr)) + tile * 32 + lane;
   const uint32_t *src = P.src[op] + base;
   uint32_t *dst = P.dst[op] + base;
   const ModQ m = P.m;
@@ -168,12 +170,12 @@ large_cols_inv_kernel(const __grid_constant__ LargeParams P) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
-  const uint32_t lr = P.logn - K1;
-  const uint32_t tiles = 1u << (lr - 5);
+  constexpr int lr = LARGE_LR;
+  constexpr uint32_t tiles = 1u << (lr - 5);
   const unsigned long long unit = blockIdx.x;
   const uint32_t tile = (uint32_t)(unit & (tiles - 1));
   const unsigned long long poly = unit >> (lr - 5);
-  const size_t base = ((size_t)poly << P.logn) + tile * 32 + lane;
+  const size_t base = ((size_t)poly << (K1 + lr)) + tile * 32 + lane;
   const uint32_t *src = P.src[0] + base;
   uint32_t *dst = P.dst[0] + base;
   const ModQ m = P.m;
@@ -278,8 +280,11 @@ __device__ __forceinline__ void load_row_lane_tw(LaneTw<LR> &t, const uint2 *tab
  * handles row j of WARPS*PPW consecutive polynomials, so the 8 warps of a CTA fetch the
  * same 4 KiB of row twiddles (one L2 read, then L1 hits).
  * ===================================================================================== */
+#ifndef LARGE_ROW_MINB
+#define LARGE_ROW_MINB 3
+#endif
 template <int LR, int ARITH, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 2)
+__global__ void __launch_bounds__(WARPS * 32, LARGE_ROW_MINB)
 large_rows_polymul_kernel(const __grid_constant__ LargeParams P) {
   using Gm = SmallGeom<LR>;
   extern __shared__ __align__(16) uint32_t smem[];
