@@ -149,8 +149,8 @@ def _cpu_worker_loop(args):
 
 
 def _cpu_worker_step(args):
-    """One slice of one step (--impl reference leg)."""
-    seed, rows = args
+    """One slice of one step (--impl reference leg): the slice is multiplied `reps` times."""
+    seed, rows, reps = args
     key = ("data", seed, rows)
     from oracle import loader
     if key not in _W:
@@ -158,10 +158,11 @@ def _cpu_worker_step(args):
         _W[key] = (O.random((rows, _W["n"]), _W["q"], seed), O.random((rows, _W["n"]), _W["q"], seed + 1))
     a, b = _W[key]
     t0 = time.perf_counter()
-    if "ref" in _W:
-        c = _W["ref"].product(a, b, _W["variant"])
-    else:
-        c = _W["orc"].product(_W["n"], _W["q"], a, b, _W["variant"], _W["psi"])
+    for _ in range(reps):
+        if "ref" in _W:
+            c = _W["ref"].product(a, b, _W["variant"])
+        else:
+            c = _W["orc"].product(_W["n"], _W["q"], a, b, _W["variant"], _W["psi"])
     return time.perf_counter() - t0, int(c[0, 0])
 
 
@@ -207,12 +208,14 @@ def run_reference_arm(args, n, q, psi, logb, desc):
     cores = host_cores()
     pool, kind, what = cpu_pool(n, q, psi, cores)
     full = 1 << logb
-    # bounded sample per step: ~0.25 s of all-core work at ~1e5 polymul/s/core (n=256)
-    est_rate = cores * 1.0e5 * (256 * 8) / (n * max(1, n.bit_length() - 1))
-    sample = int(min(full, max(cores, est_rate * 0.25)))
-    per = max(1, sample // cores)
-    sample = per * cores
-    jobs = [(SEED + 31 * i, per) for i in range(cores)]
+    # bounded sample per step: ~0.3 s of all-core work at ~3e5 polymul/s/core (n=256), as `reps`
+    # passes over a per-core slice of at most 4096 rows (the process-pool hand-off is then noise)
+    est_rate = cores * 3.0e5 * (256 * 8) / (n * max(1, n.bit_length() - 1))
+    per = max(1, min(4096, (1 << 20) // n, full // cores if full >= cores else 1))
+    step_s = min(0.3, max(0.03, 90.0 / max(1, args.steps + args.warmup)))   # whole run <= ~1.5 min
+    reps = max(1, int(est_rate * step_s / (per * cores)))
+    sample = per * cores * reps
+    jobs = [(SEED + 31 * i, per, reps) for i in range(cores)]
     try:
         for _ in range(max(1, args.warmup)):
             pool.map(_cpu_worker_step, jobs)
@@ -232,8 +235,9 @@ def run_reference_arm(args, n, q, psi, logb, desc):
         "config": {"workload": desc, "n": n, "q": q, "batch_per_step": sample,
                    "note": "CPU arm: host cores only, no GPU, no host<->device copies"},
         "cpu_baseline": {"value": value, "unit": "polymul/s", "cores": cores, "kind": kind,
-                         "sample": f"{what}; each step = {sample} of the workload's {full} polymuls "
-                                   f"split over {cores} processes (one per core)"},
+                         "sample": f"{what}; each step = {sample} polymuls ({reps} passes over {per} rows "
+                                   f"per process, {cores} processes = one per core; the workload has {full}), "
+                                   f"wall clock including the operand restore the reference needs"},
         "e2e": {"value": value, "unit": "polymul/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
