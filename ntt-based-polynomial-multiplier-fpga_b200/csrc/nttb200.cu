@@ -465,7 +465,7 @@ static int nslot() { static int v = env_int("NTTB200_NSLOT", 3, 1, 8); return v;
 
 static int ensure_slots(nttb200_plan *P, bool need_b) {
   if (!P->slots.empty()) return 0;
-  const size_t target_bytes = (size_t)env_int("NTTB200_SLOT_MB", 8, 1, 256) << 20;   /* per operand per slot */
+  const size_t target_bytes = (size_t)env_int("NTTB200_SLOT_MB", 16, 1, 256) << 20;   /* per operand per slot */
   P->slot_polys = std::max<size_t>(1, target_bytes / (P->n * sizeof(uint32_t)));
   P->slots.resize(NSLOT);
   for (auto &s : P->slots) {
@@ -489,9 +489,13 @@ extern "C" int nttb200_polymul_batch(nttb200_plan *P, int32_t *c, const int32_t 
   if (rc) return rc;
   const size_t n = P->n;
   size_t k = 0;
-  for (size_t done = 0; done < batch; done += P->slot_polys, k++) {
+  for (size_t done = 0, nb = 0; done < batch; done += nb, k++) {
     HostSlot &s = P->slots[k % NSLOT];
-    const size_t nb = std::min(P->slot_polys, batch - done);
+    /* The call is H2D-bound and ends with one kernel + one D2H that nothing overlaps: taper the
+     * last chunks (1/2, 1/4, 1/8 ... of a slot) so that this drain is short. */
+    const size_t left = batch - done;
+    nb = std::min(P->slot_polys, left);
+    if (left <= P->slot_polys && left > 64) nb = std::max<size_t>(left / 2, 64);
     const size_t bytes = nb * n * sizeof(uint32_t);
     /* the slot's previous D2H is ordered before these copies by stream order */
     NTT_CUDA(cudaMemcpyAsync(s.d_a, a + done * n, bytes, cudaMemcpyHostToDevice, s.stream));
