@@ -422,6 +422,34 @@ def test_cyclic_plan_q3329(gpu, oracle):
     p.close()
 
 
+@pytest.mark.parametrize("n,q", [(256, 12289), (1024, 12289), (256, 2013265921), (8192, 65537), (65536, 2013265921)])
+def test_repeatability_under_load(gpu, oracle, n, q):
+    """compute-sanitizer is closed on this pool, so races in the shared-memory exchanges / the
+    cp.async prefetch are hunted the blunt way: the same device-resident batch, multiplied 12
+    times while the SMs are fully loaded, must give bit-identical results every time, and the
+    first/last rows must equal the oracle."""
+    import torch
+    batch = max(64, (1 << 22) // n)
+    p = gpu.Plan(n, q)
+    g = torch.Generator(device="cuda").manual_seed(7 + n)
+    a = torch.randint(0, q, (batch, n), dtype=torch.int32, device="cuda", generator=g)
+    b = torch.randint(0, q, (batch, n), dtype=torch.int32, device="cuda", generator=g)
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for _ in range(12):
+        c = torch.empty_like(a)
+        p.polymul_dev(c.data_ptr(), a.data_ptr(), b.data_ptr(), batch, st)
+        outs.append(c)
+    torch.cuda.synchronize()
+    for c in outs[1:]:
+        assert bool((c == outs[0]).all())
+    idx = [0, 1, batch // 2, batch - 2, batch - 1]
+    ti = torch.tensor(idx, device="cuda")
+    want = oracle.product(n, q, a[ti].cpu().numpy(), b[ti].cpu().numpy(), 10)
+    assert (outs[0][ti].cpu().numpy() == want).all()
+    p.close()
+
+
 def _dev_buffers(torch, *arrays):
     return [torch.from_numpy(x).cuda() for x in arrays]
 
