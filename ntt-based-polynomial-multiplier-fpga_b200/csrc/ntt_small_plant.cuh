@@ -326,13 +326,18 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
   const unsigned long long ntiles = (P.batch + Gm::PPW - 1) / Gm::PPW;
   const unsigned long long wstride = (unsigned long long)gridDim.x * WARPS;
   unsigned long long tile = (unsigned long long)blockIdx.x * WARPS + warp;
-  if (tile < ntiles) plant_prefetch<L>(pf_a, pf_b, P.a, P.b, tile, P.batch, lane);
 
+  /* programmatic dependent launch: let the next launch on the stream start its CTAs (and
+   * their twiddle loads, which depend on nothing) while this grid drains; operands may be the
+   * previous kernel's output, so they are only touched after griddepcontrol.wait */
+  asm volatile("griddepcontrol.launch_dependents;");
   LaneTw1<L> twf, twi;
   if (TWREG) {
     twf.load(P.tw_fwd, l);
     twi.load(P.tw_inv, l);
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (tile < ntiles) plant_prefetch<L>(pf_a, pf_b, P.a, P.b, tile, P.batch, lane);
 
   for (; tile < ntiles; tile += wstride) {
     const unsigned long long poly = tile * Gm::PPW + sub;

@@ -29,6 +29,16 @@ int plant_minb(int L) {
   return 2;
 }
 
+/* NTTB200_PDL=0 turns programmatic dependent launch off (tuning / debugging knob) */
+int plant_pdl() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("NTTB200_PDL");
+    v = e ? atoi(e) != 0 : 1;
+  }
+  return v;
+}
+
 template <int L, int MINB>
 int run_plant(const nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b, size_t batch,
               cudaStream_t st) {
@@ -62,7 +72,17 @@ int run_plant(const nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint3
   const unsigned long long want = (tiles + Cfg::WARPS - 1) / Cfg::WARPS;
   const unsigned long long cap = (unsigned long long)P->sm_count * per_sm;
   const int grid = (int)(want < cap ? (want ? want : 1) : cap);
-  kernel<<<grid, Cfg::WARPS * 32, smem, st>>>(p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(Cfg::WARPS * 32);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = plant_pdl() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NTT_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
   nttb200_count_launch(1);
   NTT_CUDA(cudaGetLastError());
   return 0;
