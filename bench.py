@@ -138,14 +138,19 @@ def _cpu_worker_init(n, q, psi, use_ref, variant):
 
 def _cpu_worker_loop(args):
     """Timed loop (cpu_baseline leg): seconds of work on a private slice, returns (rate, calls)."""
-    seed, rows, seconds = args
+    seed, rows, seconds = args[:3]
+    variant = args[3] if len(args) > 3 and args[3] is not None else _W["variant"]
+    flavour = args[4] if len(args) > 4 else None
     from oracle import loader
     O = loader.Oracle()
     n, q = _W["n"], _W["q"]
     a, b = O.random((rows, n), q, seed), O.random((rows, n), q, seed + 1)
     if "ref" in _W:
-        return _W["ref"].bench_loop(a, b, _W["variant"], seconds)
-    return _W["orc"].bench_loop(n, q, a, b, _W["variant"], seconds, _W["psi"])
+        ref = _W["ref"]
+        if flavour:
+            ref = _W.setdefault("ref_" + flavour, loader.Reference(flavour))
+        return ref.bench_loop(a, b, variant, seconds)
+    return _W["orc"].bench_loop(n, q, a, b, variant, seconds, _W["psi"])
 
 
 def _cpu_worker_step(args):
@@ -189,14 +194,27 @@ def cpu_baseline(n, q, psi, seconds=4.0):
     cores = host_cores()
     pool, kind, what = cpu_pool(n, q, psi, cores)
     rows = max(1, min(4096, (1 << 20) // n))
+    variants = {}
     try:
         res = pool.map(_cpu_worker_loop, [(SEED + 17 * i, rows, seconds) for i in range(cores)])
+        if kind == "reference":   # secondary rows of BASELINE.md section 3, 1 s each, all cores
+            from oracle import loader
+            for name, var, flav in (("ntt_red256_product4 (optimized GS)", loader.REF_RED_GS, None),
+                                    ("ntt256_product1 (CT)", loader.REF_CT, None),
+                                    ("ntt256_product4 (GS)", loader.REF_GS, None),
+                                    ("merged CT-fwd/GS-inv pipeline", loader.REF_MERGED, None),
+                                    ("ntt_red256_product1, as-documented flag-less build (-O0)", loader.REF_RED_CT, "O0")):
+                try:
+                    r2 = pool.map(_cpu_worker_loop, [(SEED + 17 * i, rows, 1.0, var, flav) for i in range(cores)])
+                    variants[name] = sum(r for r, _ in r2)
+                except Exception as ex:
+                    variants[name] = repr(ex)
     finally:
         pool.close()
         pool.join()
     total = sum(r for r, _ in res)
     return {"value": total, "unit": "polymul/s", "cores": cores, "kind": kind,
-            "per_core": total / cores,
+            "per_core": total / cores, "other_variants_polymul_per_s": variants,
             "sample": f"{what}; one process per core, each looping over a private slice of {rows} random "
                       f"polymuls for {seconds:.0f} s (operand restore excluded, as time_testing256.c:175-185)"}
 
