@@ -93,6 +93,20 @@ int nttb200_polymul_batch(nttb200_plan *plan, int32_t *c, const int32_t *a, cons
 int nttb200_polymul_batch_dev(nttb200_plan *plan, int32_t *c_dev, const int32_t *a_dev,
                               const int32_t *b_dev, size_t batch, void *stream);
 
+/* ---- several GPUs of one box: contiguous batch slices, one plan and one host thread per GPU,
+ * no collective (independent products share no data).  One process per GPU with
+ * nttb200_set_device() + nttb200_shard_bounds() is the other way (what bench.py does). ------- */
+typedef struct nttb200_multi nttb200_multi;
+int nttb200_multi_create(nttb200_multi **multi, uint32_t n, uint32_t q, uint32_t psi, uint32_t flags,
+                         int ngpus /* 0 = every visible GPU */);
+void nttb200_multi_destroy(nttb200_multi *multi);
+int nttb200_multi_gpus(const nttb200_multi *multi);
+nttb200_plan *nttb200_multi_plan(nttb200_multi *multi, int gpu);
+/* host buffers; rows [g B/G, (g+1) B/G) are multiplied on GPU g; returns when c is complete */
+int nttb200_multi_polymul_batch(nttb200_multi *multi, int32_t *c, const int32_t *a, const int32_t *b,
+                                size_t batch);
+void nttb200_shard_bounds(size_t batch, int world, int rank, size_t *lo, size_t *hi);
+
 /* ---- standalone transforms ("the NTT call surface") ---------------------------
  * In place on [batch][n].  Outputs are canonical [0, q) and bit-identical to the
  * reference function of the same dataflow run with the same table.             */

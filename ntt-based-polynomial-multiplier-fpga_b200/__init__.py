@@ -9,5 +9,5 @@ suite and ``bench.py``.  The package directory name contains hyphens, so import 
 from .capi import (  # noqa: F401
     NttError, Plan, lib, lib_path, build_library, device_count, set_device, make_table,
     find_psi, find_omega, is_prime, host_alloc, measure_int_peak, last_launch_count,
-    TRANSFORMS, DATAFLOWS, TABLES, ntt_table_batch, legacy,
+    TRANSFORMS, DATAFLOWS, TABLES, ntt_table_batch, legacy, MultiPlan, shard_bounds,
 )

@@ -122,6 +122,13 @@ def lib() -> C.CDLL:
     L.nttb200_red_elementwise_batch.argtypes = [C.c_int, i32p, i32p, i32p, C.c_int32, sz]
     L.nttb200_bitrev_shuffle_batch.argtypes = [i32p, C.c_uint32, sz]
     L.nttb200_shuffle_with_table.argtypes = [i32p, sz, vp, C.c_uint32]
+    L.nttb200_multi_create.argtypes = [C.POINTER(vp), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+    L.nttb200_multi_destroy.argtypes = [vp]
+    L.nttb200_multi_destroy.restype = None
+    L.nttb200_multi_gpus.argtypes = [vp]
+    L.nttb200_multi_polymul_batch.argtypes = [vp, i32p, i32p, i32p, sz]
+    L.nttb200_shard_bounds.argtypes = [sz, C.c_int, C.c_int, C.POINTER(sz), C.POINTER(sz)]
+    L.nttb200_shard_bounds.restype = None
     L.nttb200_legacy_set_clobber.argtypes = [C.c_int]
     L.nttb200_legacy_set_clobber.restype = None
     _lib = L
@@ -195,6 +202,37 @@ class _Pinned:
 
 def host_alloc(shape) -> _Pinned:
     return _Pinned(shape)
+
+
+def shard_bounds(batch: int, world: int, rank: int) -> tuple[int, int]:
+    lo, hi = C.c_size_t(0), C.c_size_t(0)
+    lib().nttb200_shard_bounds(batch, world, rank, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+class MultiPlan:
+    """One plan per GPU of the box; host batches are split into contiguous slices (no collective)."""
+
+    def __init__(self, n: int, q: int, psi: int = 0, ngpus: int = 0) -> None:
+        h = C.c_void_p()
+        _check(lib().nttb200_multi_create(C.byref(h), n, q, psi, 0, ngpus))
+        self._h, self.n, self.q = h, n, q
+        self.gpus = int(lib().nttb200_multi_gpus(h))
+
+    def polymul_host_ptr(self, c_ptr: int, a_ptr: int, b_ptr: int, batch: int) -> None:
+        _check(lib().nttb200_multi_polymul_batch(self._h, c_ptr, a_ptr, b_ptr, batch))
+
+    def polymul(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.int32).reshape(-1, self.n)
+        b = np.ascontiguousarray(b, dtype=np.int32).reshape(-1, self.n)
+        c = np.empty_like(a)
+        self.polymul_host_ptr(_ptr(c), _ptr(a), _ptr(b), a.shape[0])
+        return c
+
+    def close(self) -> None:
+        if self._h:
+            lib().nttb200_multi_destroy(self._h)
+            self._h = None
 
 
 class Plan:

@@ -16,6 +16,8 @@
 #include <algorithm>
 #include <mutex>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "host_tables.h"
@@ -610,6 +612,86 @@ extern "C" int nttb200_ntt_table_batch(uint32_t n, uint32_t q, int dataflow, con
   cudaFree(d_a);
   if (e != cudaSuccess) return nttb200_fail(NTTB200_ECUDA, "table transform: %s", cudaGetErrorString(e));
   return rc;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* multi-GPU: contiguous batch slices, one plan + one host thread per GPU, no collective   */
+/* (independent products share nothing but the read-only tables -- SURVEY 8e)              */
+/* ------------------------------------------------------------------------------------ */
+struct nttb200_multi {
+  std::vector<nttb200_plan *> plans;
+  uint32_t n = 0;
+};
+
+extern "C" int nttb200_multi_create(nttb200_multi **out, uint32_t n, uint32_t q, uint32_t psi, uint32_t flags,
+                                    int ngpus) {
+  if (!out) return nttb200_fail(NTTB200_EPARAM, "multi pointer is NULL");
+  *out = nullptr;
+  const int have = nttb200_device_count();
+  if (have <= 0) return nttb200_fail(NTTB200_ECUDA, "no CUDA device (there is no CPU fallback)");
+  if (ngpus <= 0) ngpus = have;
+  if (ngpus > have) return nttb200_fail(NTTB200_EPARAM, "%d GPUs requested, %d visible", ngpus, have);
+  nttb200_multi *M = new (std::nothrow) nttb200_multi;
+  if (!M) return nttb200_fail(NTTB200_ENOMEM, "out of host memory");
+  M->n = n;
+  const int saved = g_device;
+  int rc = 0;
+  for (int g = 0; g < ngpus && rc == 0; g++) {
+    nttb200_plan *P = nullptr;
+    rc = nttb200_set_device(g);
+    if (rc == 0) rc = nttb200_plan_create(&P, n, q, psi, flags);
+    if (rc == 0) M->plans.push_back(P);
+  }
+  g_device = saved;
+  if (saved >= 0) cudaSetDevice(saved);
+  if (rc) {
+    for (auto *P : M->plans) nttb200_plan_destroy(P);
+    delete M;
+    return rc;
+  }
+  *out = M;
+  return 0;
+}
+extern "C" void nttb200_multi_destroy(nttb200_multi *M) {
+  if (!M) return;
+  for (auto *P : M->plans) nttb200_plan_destroy(P);
+  delete M;
+}
+extern "C" int nttb200_multi_gpus(const nttb200_multi *M) { return M ? (int)M->plans.size() : 0; }
+extern "C" nttb200_plan *nttb200_multi_plan(nttb200_multi *M, int gpu) {
+  return (M && gpu >= 0 && gpu < (int)M->plans.size()) ? M->plans[gpu] : nullptr;
+}
+/* rows [g B/G, (g+1) B/G) go to GPU g (the partition of SURVEY 8e) */
+extern "C" void nttb200_shard_bounds(size_t batch, int world, int rank, size_t *lo, size_t *hi) {
+  if (world < 1) world = 1;
+  if (lo) *lo = (size_t)(((unsigned __int128)batch * (unsigned)rank) / (unsigned)world);
+  if (hi) *hi = (size_t)(((unsigned __int128)batch * (unsigned)(rank + 1)) / (unsigned)world);
+}
+extern "C" int nttb200_multi_polymul_batch(nttb200_multi *M, int32_t *c, const int32_t *a, const int32_t *b,
+                                           size_t batch) {
+  if (!M || !c || !a || !b) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
+  const int G = (int)M->plans.size();
+  std::vector<int> rcs(G, 0);
+  std::vector<std::string> errs(G);
+  std::vector<int> launches(G, 0);
+  std::vector<std::thread> th;
+  for (int g = 0; g < G; g++) {
+    th.emplace_back([&, g]() {
+      size_t lo, hi;
+      nttb200_shard_bounds(batch, G, g, &lo, &hi);
+      const size_t o = lo * M->n;
+      rcs[g] = nttb200_polymul_batch(M->plans[g], c + o, a + o, b + o, hi - lo);
+      if (rcs[g]) errs[g] = nttb200_last_error();
+      launches[g] = nttb200_last_launch_count();
+    });
+  }
+  for (auto &t : th) t.join();
+  g_launches = 0;
+  for (int g = 0; g < G; g++) {
+    g_launches += launches[g];
+    if (rcs[g]) return nttb200_fail(rcs[g], "GPU %d: %s", g, errs[g].c_str());
+  }
+  return 0;
 }
 
 /* ------------------------------------------------------------------------------------ */

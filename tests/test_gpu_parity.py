@@ -450,6 +450,29 @@ def test_repeatability_under_load(gpu, oracle, n, q):
     p.close()
 
 
+@pytest.mark.parametrize("n,q", [(256, 12289), (1024, 12289), (256, 2013265921), (4096, 40961), (65536, 2013265921)])
+def test_in_place_result_over_an_operand(gpu, oracle, n, q):
+    """c == a or c == b (exactly the same buffer) is allowed on the device path: every kernel has
+    consumed a polynomial's operand rows before it stores that polynomial's result."""
+    import torch
+    batch = max(37, (1 << 20) // n + 5)
+    p = gpu.Plan(n, q)
+    g = torch.Generator(device="cuda").manual_seed(11 + n)
+    a = torch.randint(0, q, (batch, n), dtype=torch.int32, device="cuda", generator=g)
+    b = torch.randint(0, q, (batch, n), dtype=torch.int32, device="cuda", generator=g)
+    st = torch.cuda.current_stream().cuda_stream
+    c = torch.empty_like(a)
+    p.polymul_dev(c.data_ptr(), a.data_ptr(), b.data_ptr(), batch, st)
+    a2, b2 = a.clone(), b.clone()
+    p.polymul_dev(a2.data_ptr(), a2.data_ptr(), b.data_ptr(), batch, st)      # c over a
+    p.polymul_dev(b2.data_ptr(), a.data_ptr(), b2.data_ptr(), batch, st)      # c over b
+    torch.cuda.synchronize()
+    assert bool((a2 == c).all()) and bool((b2 == c).all())
+    want = oracle.product(n, q, a[:3].cpu().numpy(), b[:3].cpu().numpy(), 10)
+    assert (c[:3].cpu().numpy() == want).all()
+    p.close()
+
+
 def _dev_buffers(torch, *arrays):
     return [torch.from_numpy(x).cuda() for x in arrays]
 
@@ -503,3 +526,15 @@ def test_kernels_cross_check_fused_vs_literal_dataflow(gpu, oracle):
     literal = gpu.ntt_table_batch(n, q, "ct_std2rev", gpu.make_table("mixed_powers_rev", n, q, p.psi), a)
     assert (fused == literal).all()
     p.close()
+
+
+def test_multi_gpu_sharder_in_one_process(gpu, oracle):
+    """nttb200_multi_*: every visible GPU gets a contiguous slice (1 GPU on the default box; the
+    same test is run with --gpus 2)."""
+    n, q = 256, 12289
+    m = gpu.MultiPlan(n, q, 1002)
+    assert m.gpus == gpu.device_count() >= 1
+    for batch in (1, 7, 4099):
+        a, b = oracle.random((batch, n), q, 1 + batch), oracle.random((batch, n), q, 2 + batch)
+        assert (m.polymul(a, b) == oracle.product(n, q, a, b, 10)).all()
+    m.close()

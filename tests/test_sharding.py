@@ -67,3 +67,13 @@ def test_two_ranks_gloo():
     assert [r[1:3] for r in res] == [(0, 5), (5, 10)]
     assert all(r[4] == 2.0 for r in res)             # max over ranks
     assert all(r[5] == 10.0 for r in res)            # units processed by all ranks
+
+
+def test_c_shard_bounds_match_the_python_partition(nttb200):
+    sh = __import__("importlib").import_module("ntt-based-polynomial-multiplier-fpga_b200.sharding")
+    for batch in (0, 1, 7, 65536, (1 << 20) + 3):
+        for world in (1, 2, 3, 8):
+            got = [nttb200.shard_bounds(batch, world, r) for r in range(world)]
+            assert got == [sh.shard_bounds(batch, world, r) for r in range(world)]
+            assert got[0][0] == 0 and got[-1][1] == batch
+            assert all(got[i][1] == got[i + 1][0] for i in range(world - 1))
