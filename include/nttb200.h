@@ -93,6 +93,15 @@ int nttb200_polymul_batch(nttb200_plan *plan, int32_t *c, const int32_t *a, cons
 int nttb200_polymul_batch_dev(nttb200_plan *plan, int32_t *c_dev, const int32_t *a_dev,
                               const int32_t *b_dev, size_t batch, void *stream);
 
+/* ---- packed 16-bit I/O: an EXTENSION outside the reference API for plans with
+ * q <= 12385 and n <= 1024: coefficients travel as uint16_t, which halves the PCIe and HBM
+ * bytes per product (6 n instead of 12 n).  Never used for the roofline figures of bench.py.
+ * Operands must be 16-byte aligned. */
+int nttb200_polymul_batch_u16(nttb200_plan *plan, uint16_t *c, const uint16_t *a, const uint16_t *b,
+                              size_t batch);
+int nttb200_polymul_batch_u16_dev(nttb200_plan *plan, uint16_t *c_dev, const uint16_t *a_dev,
+                                  const uint16_t *b_dev, size_t batch, void *stream);
+
 /* ---- several GPUs of one box: contiguous batch slices, one plan and one host thread per GPU,
  * no collective (independent products share no data).  One process per GPU with
  * nttb200_set_device() + nttb200_shard_bounds() is the other way (what bench.py does). ------- */

@@ -122,6 +122,8 @@ def lib() -> C.CDLL:
     L.nttb200_red_elementwise_batch.argtypes = [C.c_int, i32p, i32p, i32p, C.c_int32, sz]
     L.nttb200_bitrev_shuffle_batch.argtypes = [i32p, C.c_uint32, sz]
     L.nttb200_shuffle_with_table.argtypes = [i32p, sz, vp, C.c_uint32]
+    L.nttb200_polymul_batch_u16.argtypes = [vp, vp, vp, vp, sz]
+    L.nttb200_polymul_batch_u16_dev.argtypes = [vp, vp, vp, vp, sz, vp]
     L.nttb200_multi_create.argtypes = [C.POINTER(vp), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
     L.nttb200_multi_destroy.argtypes = [vp]
     L.nttb200_multi_destroy.restype = None
@@ -269,6 +271,17 @@ class Plan:
         c = np.empty_like(a) if out is None else out
         _check(lib().nttb200_polymul_batch(self._h, _ptr(c), _ptr(a), _ptr(b), a.shape[0]))
         return c
+
+    def polymul_u16(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        """Packed 16-bit extension (q <= 12385): uint16 in, uint16 out."""
+        a = np.ascontiguousarray(a, dtype=np.uint16).reshape(-1, self.n)
+        b = np.ascontiguousarray(b, dtype=np.uint16).reshape(-1, self.n)
+        c = np.empty_like(a)
+        _check(lib().nttb200_polymul_batch_u16(self._h, _ptr(c), _ptr(a), _ptr(b), a.shape[0]))
+        return c
+
+    def polymul_u16_dev(self, c_ptr: int, a_ptr: int, b_ptr: int, batch: int, stream: int = 0) -> None:
+        _check(lib().nttb200_polymul_batch_u16_dev(self._h, c_ptr, a_ptr, b_ptr, batch, stream))
 
     def transform(self, kind: str, a: np.ndarray) -> np.ndarray:
         x = np.ascontiguousarray(a, dtype=np.int32).reshape(-1, self.n).copy()

@@ -46,9 +46,9 @@ constexpr uint32_t PLANT_QMAX = 12385;     /* 28 * q * q < 2^32 */
 
 template <int R>
 struct PlantParams {
-  const uint32_t *a;
-  const uint32_t *b;
-  uint32_t *c;
+  const void *a;             /* [batch][n] of IO (uint32_t for the reference API, uint16_t for the  */
+  const void *b;             /*  packed extension nttb200_polymul_batch_u16)                        */
+  void *c;
   const uint32_t *tw_fwd;    /* device level table of w~, n entries           */
   const uint32_t *tw_inv;
   unsigned long long batch;
@@ -273,23 +273,25 @@ __device__ __forceinline__ void cp_async16(uint32_t *smem_dst, const uint32_t *g
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int L>
+template <int L, typename IO = uint32_t>
 struct PlantGeom {
   using Gm = SmallGeom<L>;
-  /* words per polynomial in the prefetch buffer: 16-byte aligned rows, and consecutive
+  static constexpr int EPC = 16 / (int)sizeof(IO);              /* elements per 16-byte chunk */
+  /* elements per polynomial in the prefetch buffer: 16-byte aligned rows, and consecutive
    * polynomials of a warp land on different banks for the layout-1 reads */
-  static constexpr int PSTRIDE = Gm::N + ((Gm::T >= 32) ? 0 : ((Gm::T % 4 == 0) ? Gm::T : 4));
-  static constexpr int CHUNKS = Gm::N / 4;                    /* 16-byte chunks per polynomial */
-  static constexpr int ITERS = (Gm::PPW * CHUNKS + 31) / 32;   /* cp.async per lane per operand */
+  static constexpr int PSTRIDE = Gm::N + ((Gm::T >= 32) ? 0 : ((Gm::T % EPC == 0) ? Gm::T : EPC));
+  static constexpr int CHUNKS = Gm::N / EPC;                    /* 16-byte chunks per polynomial */
+  static constexpr int ITERS = (Gm::PPW * CHUNKS + 31) / 32;     /* cp.async per lane per operand */
+  static constexpr int PF_WORDS = (Gm::PPW * PSTRIDE * (int)sizeof(IO) + 15) / 16 * 4;   /* per operand */
   /* per warp: prefetch a, prefetch b, transposition a, transposition b */
-  static constexpr int WARP_WORDS = 2 * Gm::PPW * PSTRIDE + 2 * Gm::PPW * Gm::STRIDE;
+  static constexpr int WARP_WORDS = 2 * PF_WORDS + 2 * Gm::PPW * Gm::STRIDE;
 };
 
-template <int L>
-__device__ __forceinline__ void plant_prefetch(uint32_t *pa, uint32_t *pb, const uint32_t *ga, const uint32_t *gb,
+template <int L, typename IO>
+__device__ __forceinline__ void plant_prefetch(IO *pa, IO *pb, const IO *ga, const IO *gb,
                                                unsigned long long tile, unsigned long long batch, int lane) {
   using Gm = SmallGeom<L>;
-  using Pg = PlantGeom<L>;
+  using Pg = PlantGeom<L, IO>;
 #pragma unroll
   for (int i = 0; i < Pg::ITERS; i++) {
     const int c = i * 32 + lane;
@@ -297,9 +299,11 @@ __device__ __forceinline__ void plant_prefetch(uint32_t *pa, uint32_t *pb, const
     const int cc = c % Pg::CHUNKS;
     const unsigned long long poly = tile * Gm::PPW + sub;
     if (sub < Gm::PPW && poly < batch) {
-      const size_t go = ((size_t)poly << L) + cc * 4;
-      cp_async16(pa + sub * Pg::PSTRIDE + cc * 4, ga + go);
-      cp_async16(pb + sub * Pg::PSTRIDE + cc * 4, gb + go);
+      const size_t go = ((size_t)poly << L) + cc * Pg::EPC;
+      cp_async16(reinterpret_cast<uint32_t *>(pa + sub * Pg::PSTRIDE + cc * Pg::EPC),
+                 reinterpret_cast<const uint32_t *>(ga + go));
+      cp_async16(reinterpret_cast<uint32_t *>(pb + sub * Pg::PSTRIDE + cc * Pg::EPC),
+                 reinterpret_cast<const uint32_t *>(gb + go));
     }
   }
 }
@@ -307,20 +311,22 @@ __device__ __forceinline__ void plant_prefetch(uint32_t *pa, uint32_t *pb, const
 /* =====================================================================================
  * Fused product kernel, half-word moduli.
  * ===================================================================================== */
-template <int L, int WARPS, int MINB, bool TWREG>
+template <int L, int WARPS, int MINB, bool TWREG, typename IO = uint32_t>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
   using Gm = SmallGeom<L>;
-  using Pg = PlantGeom<L>;
+  using Pg = PlantGeom<L, IO>;
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int sub = lane / Gm::T;
   const int l = lane % Gm::T;
-  uint32_t *pf_a = smem + warp * Pg::WARP_WORDS;
-  uint32_t *pf_b = pf_a + Gm::PPW * Pg::PSTRIDE;
-  uint32_t *sm_a = pf_b + Gm::PPW * Pg::PSTRIDE + sub * Gm::STRIDE;
+  IO *pf_a = reinterpret_cast<IO *>(smem + warp * Pg::WARP_WORDS);
+  IO *pf_b = reinterpret_cast<IO *>(smem + warp * Pg::WARP_WORDS + Pg::PF_WORDS);
+  uint32_t *sm_a = smem + warp * Pg::WARP_WORDS + 2 * Pg::PF_WORDS + sub * Gm::STRIDE;
   uint32_t *sm_b = sm_a + Gm::PPW * Gm::STRIDE;
+  const IO *ga = static_cast<const IO *>(P.a), *gb = static_cast<const IO *>(P.b);
+  IO *gc = static_cast<IO *>(P.c);
   const uint32_t q = P.q;
 
   const unsigned long long ntiles = (P.batch + Gm::PPW - 1) / Gm::PPW;
@@ -337,7 +343,7 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
     twi.load(P.tw_inv, l);
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (tile < ntiles) plant_prefetch<L>(pf_a, pf_b, P.a, P.b, tile, P.batch, lane);
+  if (tile < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile, P.batch, lane);
 
   for (; tile < ntiles; tile += wstride) {
     const unsigned long long poly = tile * Gm::PPW + sub;
@@ -352,7 +358,7 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
       xb[k] = pf_b[sub * Pg::PSTRIDE + (k << Gm::H) + l];
     }
     __syncwarp();                                     /* prefetch buffers are free again */
-    if (tile + wstride < ntiles) plant_prefetch<L>(pf_a, pf_b, P.a, P.b, tile + wstride, P.batch, lane);
+    if (tile + wstride < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile + wstride, P.batch, lane);
 
     pl_fwd_cols<L>(xa, P);
     pl_fwd_cols<L>(xb, P);
@@ -396,7 +402,11 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
       load_cols<L>(xa, sm_a, l);
     }
     pl_inv_cols<L, pl_gs_phase_out(Gm::H, 1)>(xa, P);
-    if (live) gstore_cols<L>(xa, P.c + (poly << L), l);
+    if (live) {
+      IO *cp = gc + (poly << L);
+#pragma unroll
+      for (int k = 0; k < Gm::NV; k++) cp[(k << Gm::H) + l] = (IO)xa[k];
+    }
     __syncwarp();                                     /* smem reuse by the next tile */
   }
 }

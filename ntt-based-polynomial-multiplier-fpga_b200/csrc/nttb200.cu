@@ -509,6 +509,49 @@ extern "C" int nttb200_polymul_batch(nttb200_plan *P, int32_t *c, const int32_t 
   return 0;
 }
 
+/* ---- packed 16-bit extension (outside the reference API; half-word moduli only) ---------- */
+extern "C" int nttb200_polymul_batch_u16_dev(nttb200_plan *P, uint16_t *c, const uint16_t *a, const uint16_t *b,
+                                             size_t batch, void *stream) {
+  if (!P || !c || !a || !b) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
+  if (!P->plant)
+    return nttb200_fail(NTTB200_EPARAM, "16-bit I/O needs a half-word modulus plan (q <= 12385, n <= 1024)");
+  if ((((uintptr_t)a | (uintptr_t)b) & 15u) != 0)
+    return nttb200_fail(NTTB200_EPARAM, "16-bit operands must be 16-byte aligned");
+  g_launches = 0;
+  if (batch == 0) return 0;
+  DeviceGuard guard(P->device);
+  return launch_polymul_small_plant_u16(P, c, a, b, batch, (cudaStream_t)stream);
+}
+
+extern "C" int nttb200_polymul_batch_u16(nttb200_plan *P, uint16_t *c, const uint16_t *a, const uint16_t *b,
+                                         size_t batch) {
+  if (!P || !c || !a || !b) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
+  if (!P->plant)
+    return nttb200_fail(NTTB200_EPARAM, "16-bit I/O needs a half-word modulus plan (q <= 12385, n <= 1024)");
+  g_launches = 0;
+  std::lock_guard<std::mutex> lock(P->mu);
+  DeviceGuard guard(P->device);
+  int rc = ensure_slots(P, true);
+  if (rc) return rc;
+  const size_t n = P->n;
+  const size_t slot = P->slot_polys * 2;             /* the slots are sized for 32-bit rows */
+  size_t k = 0;
+  for (size_t done = 0, nb = 0; done < batch; done += nb, k++) {
+    HostSlot &s = P->slots[k % NSLOT];
+    const size_t left = batch - done;
+    nb = std::min(slot, left);
+    if (left <= slot && left > 64) nb = std::max<size_t>(left / 2, 64);
+    const size_t bytes = nb * n * sizeof(uint16_t);
+    NTT_CUDA(cudaMemcpyAsync(s.d_a, a + done * n, bytes, cudaMemcpyHostToDevice, s.stream));
+    NTT_CUDA(cudaMemcpyAsync(s.d_b, b + done * n, bytes, cudaMemcpyHostToDevice, s.stream));
+    if ((rc = launch_polymul_small_plant_u16(P, (uint16_t *)s.d_c, (const uint16_t *)s.d_a,
+                                             (const uint16_t *)s.d_b, nb, s.stream))) return rc;
+    NTT_CUDA(cudaMemcpyAsync(c + done * n, s.d_c, bytes, cudaMemcpyDeviceToHost, s.stream));
+  }
+  for (auto &s : P->slots) NTT_CUDA(cudaStreamSynchronize(s.stream));
+  return 0;
+}
+
 extern "C" int nttb200_ntt_batch(nttb200_plan *P, int transform, int32_t *a, size_t batch) {
   if (!P || !a) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
   g_launches = 0;

@@ -39,11 +39,11 @@ int plant_pdl() {
   return v;
 }
 
-template <int L, int MINB>
-int run_plant(const nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b, size_t batch,
+template <int L, int MINB, typename IO = uint32_t>
+int run_plant(const nttb200_plan *P, void *c, const void *a, const void *b, size_t batch,
               cudaStream_t st) {
   using Gm = SmallGeom<L>;
-  using Pg = PlantGeom<L>;
+  using Pg = PlantGeom<L, IO>;
   using Cfg = PlantCfg<L>;
   const bool cyclic = (P->flags & NTTB200_PLAN_CYCLIC) != 0;
   const DevTable &fwd = cyclic ? P->fwd_plain : P->fwd_mixed;
@@ -62,7 +62,7 @@ int run_plant(const nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint3
     p.ufwd[i] = (size_t)i < fwd.h1.size() ? fwd.h1[i] : 0;
     p.uinv[i] = (size_t)i < inv.h1.size() ? inv.h1[i] : 0;
   }
-  auto kernel = polymul_plant_kernel<L, Cfg::WARPS, MINB, Cfg::TWREG>;
+  auto kernel = polymul_plant_kernel<L, Cfg::WARPS, MINB, Cfg::TWREG, IO>;
   const int smem = Cfg::WARPS * Pg::WARP_WORDS * (int)sizeof(uint32_t);
   int per_sm = 0;
   NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -121,6 +121,11 @@ int launch_polymul_small_plant(const nttb200_plan *P, uint32_t *c, const uint32_
                                size_t batch, cudaStream_t st) {
   if (plant_minb(P->logn) == 2) { PLANT_SWITCH(return (run_plant<L, 2>(P, c, a, b, batch, st))) }
   PLANT_SWITCH(return (run_plant<L, 3>(P, c, a, b, batch, st)))
+}
+/* packed 16-bit operands and result (extension outside the reference API) */
+int launch_polymul_small_plant_u16(const nttb200_plan *P, uint16_t *c, const uint16_t *a, const uint16_t *b,
+                                   size_t batch, cudaStream_t st) {
+  PLANT_SWITCH(return (run_plant<L, 2, uint16_t>(P, c, a, b, batch, st)))
 }
 int small_kernel_info_plant(const nttb200_plan *P, int *regs, int *smem_bytes, int *blocks_per_sm) {
   if (plant_minb(P->logn) == 2) { PLANT_SWITCH(return (info_plant<L, 2>(regs, smem_bytes, blocks_per_sm))) }

@@ -538,3 +538,21 @@ def test_multi_gpu_sharder_in_one_process(gpu, oracle):
         a, b = oracle.random((batch, n), q, 1 + batch), oracle.random((batch, n), q, 2 + batch)
         assert (m.polymul(a, b) == oracle.product(n, q, a, b, 10)).all()
     m.close()
+
+
+@pytest.mark.parametrize("n,q", [(8, 17), (16, 97), (64, 257), (128, 3329), (256, 12289), (256, 7681), (512, 12289),
+                                 (1024, 12289)])
+def test_packed_u16_extension(gpu, oracle, n, q):
+    """nttb200_polymul_batch_u16 (outside the reference API): same products, 16-bit transport."""
+    p = gpu.Plan(n, q)
+    for batch in (1, 3, 33, 1027):
+        a, b = oracle.random((batch, n), q, SEED + 7 * n + batch), oracle.random((batch, n), q, SEED + 9 * q + batch)
+        a[0], b[0] = q - 1, q - 1
+        got = p.polymul_u16(a.astype(np.uint16), b.astype(np.uint16))
+        assert got.dtype == np.uint16
+        assert (got.astype(np.int32) == oracle.product(n, q, a, b, 10)).all(), (n, q, batch)
+    p.close()
+    big = gpu.Plan(256, 8380417)
+    with pytest.raises(gpu.NttError):
+        big.polymul_u16(np.zeros((1, 256), np.uint16), np.zeros((1, 256), np.uint16))
+    big.close()
