@@ -17,8 +17,10 @@
  *   K2  row pass fwd(a'), fwd(b'), pointwise, row pass inv   (read a',b'  write c')
  *   K3  column pass inv on c' with n^-1 folded into its last stage (read c' write c)
  *
- * a', b', c' live in a scratch area sized to stay L2-resident (the host loops over batch
- * chunks), so HBM sees ~12n bytes per product and the intermediate 24n bytes are L2 traffic.
+ * a', b', c' live in a per-chunk scratch area (the host pipelines batch chunks over a few
+ * internal streams so that the column pass of one chunk overlaps the row pass of the previous
+ * one); the scratch is small enough to stay in L2, but with a 31-bit modulus the passes are
+ * instruction-bound, not memory-bound.
  *
  * Column pass: one CTA owns 32 adjacent columns (lanes = columns: every global access is a
  * 128-byte row segment) and all n1 rows; the K1 stages run as one or two register phases
