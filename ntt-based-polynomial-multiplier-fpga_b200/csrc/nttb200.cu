@@ -202,6 +202,7 @@ extern "C" void nttb200_plan_destroy(nttb200_plan *P) {
     cudaFree(s.d_a); cudaFree(s.d_b); cudaFree(s.d_c);
   }
   if (P->scratch) cudaFree(P->scratch);
+  if (P->zc_host) cudaFreeHost(P->zc_host);
   for (auto &ln : P->lanes) {
     if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamDestroy(ln.stream); }
     if (ln.done) cudaEventDestroy(ln.done);
@@ -465,8 +466,21 @@ static int env_int(const char *name, int dflt, int lo, int hi) {
 static int nslot() { static int v = env_int("NTTB200_NSLOT", 3, 1, 8); return v; }
 #define NSLOT nslot()
 
+static const size_t ZC_BYTES = 64u << 10;    /* per operand, zero-copy path of small calls */
+
 static int ensure_slots(nttb200_plan *P, bool need_b) {
   if (!P->slots.empty()) return 0;
+  if (!P->zc_host && P->kernel == PK_SMALL) {
+    void *h = nullptr, *d = nullptr;
+    if (cudaHostAlloc(&h, 3 * ZC_BYTES, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess &&
+        cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) {
+      P->zc_host = (uint32_t *)h;
+      P->zc_dev = (uint32_t *)d;
+    } else {
+      if (h) cudaFreeHost(h);
+      cudaGetLastError();                          /* the DMA ring below serves small calls too */
+    }
+  }
   const size_t target_bytes = (size_t)env_int("NTTB200_SLOT_MB", 16, 1, 256) << 20;   /* per operand per slot */
   P->slot_polys = std::max<size_t>(1, target_bytes / (P->n * sizeof(uint32_t)));
   P->slots.resize(NSLOT);
@@ -490,6 +504,21 @@ extern "C" int nttb200_polymul_batch(nttb200_plan *P, int32_t *c, const int32_t 
   int rc = ensure_slots(P, true);
   if (rc) return rc;
   const size_t n = P->n;
+  /* Small calls (the reference's one-polynomial-per-call convention, nttb200_legacy.h): no DMA
+   * at all -- operands are copied into a mapped pinned buffer that the kernel reads over PCIe
+   * directly, and it writes c straight back into host memory: one launch + one sync. */
+  if (batch * n * sizeof(uint32_t) <= ZC_BYTES && P->zc_host) {
+    HostSlot &s = P->slots[0];
+    const size_t bytes = batch * n * sizeof(uint32_t);
+    uint32_t *ha = P->zc_host, *hb = ha + ZC_BYTES / 4, *hc = hb + ZC_BYTES / 4;
+    uint32_t *da = P->zc_dev, *db = da + ZC_BYTES / 4, *dc = db + ZC_BYTES / 4;
+    memcpy(ha, a, bytes);
+    memcpy(hb, b, bytes);
+    if ((rc = polymul_dev(P, dc, da, db, batch, s.stream))) return rc;
+    NTT_CUDA(cudaStreamSynchronize(s.stream));
+    memcpy(c, hc, bytes);
+    return 0;
+  }
   size_t k = 0;
   for (size_t done = 0, nb = 0; done < batch; done += nb, k++) {
     HostSlot &s = P->slots[k % NSLOT];

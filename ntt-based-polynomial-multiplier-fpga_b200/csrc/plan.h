@@ -55,6 +55,9 @@ struct nttb200_plan {
   DevTable fwd_invroot;                   /* inv_omega_powers_rev used as a FORWARD table */
   DevTable inv_fwdroot;                   /* omega_powers_rev used as an INVERSE table    */
 
+  /* host-buffer path: mapped pinned buffer (a | b | c) for small calls, read and written by
+   * the kernel over PCIe without any DMA */
+  uint32_t *zc_host = nullptr, *zc_dev = nullptr;
   /* host-buffer path: ring of device staging slots */
   std::mutex mu;
   std::vector<HostSlot> slots;
