@@ -72,6 +72,63 @@ scale_kernel(uint32_t *a, const uint2 *tab, uint2 sc, uint32_t n, unsigned long 
 }
 
 /* =====================================================================================
+ * Whole literal transform in ONE launch for n <= 4096: one CTA per polynomial, the polynomial
+ * in shared memory, one __syncthreads per stage.  Same per-stage arithmetic as
+ * generic_stage_kernel (canonical after every stage) / generic_red_stage_kernel (exact
+ * Longa-Naehrig values).  This is what the one-polynomial-per-call legacy functions run, on a
+ * mapped pinned buffer, so a call costs one launch and one synchronisation.
+ * ===================================================================================== */
+__device__ __forceinline__ int32_t ln_mul_red_fwd(int32_t x, int32_t y);
+
+template <int DF, bool RED>
+__global__ void __launch_bounds__(512)
+literal_cta_kernel(uint32_t *data, const uint2 *tab, const int32_t *rtab, uint32_t n, uint32_t logn,
+                   unsigned long long batch, ModQ m, int skip0) {
+  extern __shared__ __align__(16) uint32_t sx[];
+  const bool descending = (DF == DF_CT_STD2REV || DF == DF_GS_STD2REV);
+  for (unsigned long long poly = blockIdx.x; poly < batch; poly += gridDim.x) {
+    uint32_t *g = data + (poly << logn);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) sx[i] = g[i];
+    __syncthreads();
+    for (uint32_t s = 0; s < logn; s++) {
+      const uint32_t lh = descending ? (logn - 1 - s) : s;
+      const uint32_t half = 1u << lh;
+      for (uint32_t b = threadIdx.x; b < (n >> 1); b += blockDim.x) {
+        const uint32_t hi_part = b >> lh, lo_part = b & (half - 1);
+        const uint32_t p0 = (hi_part << (lh + 1)) | lo_part;
+        uint32_t tidx, j;
+        if (DF == DF_CT_STD2REV || DF == DF_GS_REV2STD) { j = hi_part; tidx = ((n >> 1) >> lh) + hi_part; }
+        else { j = lo_part; tidx = half + lo_part; }
+        if (!RED) {
+          const uint2 w = tab[tidx];
+          uint32_t X = sx[p0], Y = sx[p0 + half];
+          if (DF == DF_CT_STD2REV || DF == DF_CT_REV2STD) ct_bfly<ARITH_CANON>(X, Y, w.x, w.y, m);
+          else gs_bfly<ARITH_CANON>(X, Y, w.x, w.y, m, 0u);
+          sx[p0] = X;
+          sx[p0 + half] = Y;
+        } else {
+          const int32_t w = rtab[tidx];
+          const bool plain = skip0 && j == 0;
+          const int32_t X = (int32_t)sx[p0], Y = (int32_t)sx[p0 + half];
+          if (DF == DF_CT_STD2REV || DF == DF_CT_REV2STD) {
+            const int32_t x = plain ? Y : ln_mul_red_fwd(Y, w);
+            sx[p0 + half] = (uint32_t)X - (uint32_t)x;
+            sx[p0] = (uint32_t)X + (uint32_t)x;
+          } else {
+            const int32_t d = (int32_t)((uint32_t)X - (uint32_t)Y);
+            sx[p0 + half] = (uint32_t)(plain ? d : ln_mul_red_fwd(d, w));
+            sx[p0] = (uint32_t)X + (uint32_t)Y;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) g[i] = sx[i];
+    __syncthreads();
+  }
+}
+
+/* =====================================================================================
  * Exact emulation of the reference's Longa-Naehrig ("RED") functions, q = 12289 hard-wired
  * as in R/NTT-RED/ntt_red.c:24-46: signed 32-bit values that are NOT reduced mod q
  * (R/NTT-RED/ntt_red256.h:18), red(x) = 3 (x & 4095) - (x >> 12), tables pre-scaled by 1/3.
@@ -85,6 +142,7 @@ __device__ __forceinline__ int32_t ln_mul_red(int32_t x, int32_t y) {           
   const uint32_t hi = (uint32_t)(z >> 12);         /* the reference truncates z >> 12 to int32 */
   return (int32_t)(3u * lo - hi);
 }
+__device__ __forceinline__ int32_t ln_mul_red_fwd(int32_t x, int32_t y) { return ln_mul_red(x, y); }
 
 /* skip0: the un-merged entry points (ntt_red_ct_*, ntt_red_gs_*) do the j = 0 butterflies
  * without a multiplication (e.g. ntt_red.c:339-343); the psi-merged ones multiply every j. */

@@ -650,6 +650,57 @@ extern "C" int nttb200_scalar_mul_array_batch(nttb200_plan *P, int32_t *a, int32
   return 0;
 }
 
+/* Process-wide mapped pinned scratch for the one-polynomial-per-call compatibility functions:
+ * [ table (n x 8 B) | data ], read and written by the kernel over PCIe; one launch + one sync. */
+struct ZcCtx {
+  std::mutex mu;
+  unsigned char *h = nullptr, *d = nullptr;
+  size_t bytes = 0;
+  cudaStream_t st = nullptr;
+  int dev = -1;
+};
+static ZcCtx g_zc;
+static const size_t ZC_CTX_BYTES = 1u << 20;
+static const uint32_t LITERAL_CTA_MAX_N = 4096;
+
+/* returns 0 and the locked context, or non-zero when the fast path is not available */
+static int zc_acquire(std::unique_lock<std::mutex> &lk) {
+  lk = std::unique_lock<std::mutex>(g_zc.mu);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 1; }
+  if (g_zc.h && g_zc.dev == dev) return 0;
+  if (g_zc.h) return 1;                              /* created on another device: use the slow path */
+  void *h = nullptr, *d = nullptr;
+  if (cudaHostAlloc(&h, ZC_CTX_BYTES, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+      cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&g_zc.st, cudaStreamNonBlocking) != cudaSuccess) {
+    if (h) cudaFreeHost(h);
+    cudaGetLastError();
+    return 1;
+  }
+  g_zc.h = (unsigned char *)h; g_zc.d = (unsigned char *)d; g_zc.bytes = ZC_CTX_BYTES; g_zc.dev = dev;
+  return 0;
+}
+
+template <bool RED>
+static int literal_cta_launch(int dataflow, uint32_t *d_a, const uint2 *d_tab, const int32_t *d_rtab, uint32_t n,
+                              size_t batch, const ModQ &m, int skip0, cudaStream_t st) {
+  using namespace nttb200;
+  const uint32_t logn = ht_log2(n);
+  const int threads = (int)std::min<uint32_t>(512, std::max<uint32_t>(32, n / 2));
+  const int grid = (int)std::min<size_t>(batch, (size_t)current_sms() * 4);
+  const size_t smem = n * sizeof(uint32_t);
+  switch (dataflow) {
+    case DF_CT_STD2REV: literal_cta_kernel<DF_CT_STD2REV, RED><<<grid, threads, smem, st>>>(d_a, d_tab, d_rtab, n, logn, batch, m, skip0); break;
+    case DF_GS_REV2STD: literal_cta_kernel<DF_GS_REV2STD, RED><<<grid, threads, smem, st>>>(d_a, d_tab, d_rtab, n, logn, batch, m, skip0); break;
+    case DF_CT_REV2STD: literal_cta_kernel<DF_CT_REV2STD, RED><<<grid, threads, smem, st>>>(d_a, d_tab, d_rtab, n, logn, batch, m, skip0); break;
+    default: literal_cta_kernel<DF_GS_STD2REV, RED><<<grid, threads, smem, st>>>(d_a, d_tab, d_rtab, n, logn, batch, m, skip0); break;
+  }
+  nttb200_count_launch(1);
+  NTT_CUDA(cudaGetLastError());
+  return 0;
+}
+
 /* Table-driven transform: the literal reference dataflow with the caller's table. */
 extern "C" int nttb200_ntt_table_batch(uint32_t n, uint32_t q, int dataflow, const uint32_t *p, int32_t *a,
                                        size_t batch) {
@@ -670,9 +721,24 @@ extern "C" int nttb200_ntt_table_batch(uint32_t n, uint32_t q, int dataflow, con
   uint32_t inv = 1;
   for (int i = 0; i < 5; i++) inv *= 2u - q * inv;
   m.qinv = inv;
+  const size_t bytes = batch * n * sizeof(uint32_t);
+  if (n <= LITERAL_CTA_MAX_N && n * sizeof(uint2) + bytes <= ZC_CTX_BYTES) {   /* one launch, no DMA */
+    std::unique_lock<std::mutex> lk;
+    if (zc_acquire(lk) == 0) {
+      uint2 *h_tab = (uint2 *)g_zc.h;
+      uint32_t *h_a = (uint32_t *)(g_zc.h + n * sizeof(uint2));
+      memcpy(h_tab, h.data(), n * sizeof(uint2));
+      memcpy(h_a, a, bytes);
+      int rc0 = literal_cta_launch<false>(dataflow, (uint32_t *)(g_zc.d + n * sizeof(uint2)), (const uint2 *)g_zc.d,
+                                          nullptr, n, batch, m, 0, g_zc.st);
+      if (rc0) return rc0;
+      NTT_CUDA(cudaStreamSynchronize(g_zc.st));
+      memcpy(a, h_a, bytes);
+      return 0;
+    }
+  }
   uint2 *d_tab = nullptr;
   uint32_t *d_a = nullptr;
-  const size_t bytes = batch * n * sizeof(uint32_t);
   int rc = 0;
   cudaError_t e = cudaMalloc(&d_tab, n * sizeof(uint2));
   if (e == cudaSuccess) e = cudaMalloc(&d_a, bytes);
@@ -793,6 +859,24 @@ extern "C" int nttb200_red_ntt_table_batch(uint32_t n, int dataflow, int skip_j0
   g_launches = 0;
   if (batch == 0) return 0;
   const uint32_t logn = ht_log2(n);
+  if (n <= LITERAL_CTA_MAX_N && n * sizeof(int32_t) + batch * n * sizeof(int32_t) <= ZC_CTX_BYTES &&
+      nttb200_device_count() > 0) {                                               /* one launch, no DMA */
+    std::unique_lock<std::mutex> lk;
+    if (zc_acquire(lk) == 0) {
+      const size_t bytes = batch * n * sizeof(int32_t);
+      int32_t *h_tab = (int32_t *)g_zc.h;
+      int32_t *h_a = (int32_t *)(g_zc.h + n * sizeof(int32_t));
+      memcpy(h_tab, p, n * sizeof(int32_t));
+      memcpy(h_a, a, bytes);
+      ModQ m{};
+      int rc0 = literal_cta_launch<true>(dataflow, (uint32_t *)(g_zc.d + n * sizeof(int32_t)), nullptr,
+                                         (const int32_t *)g_zc.d, n, batch, m, skip_j0, g_zc.st);
+      if (rc0) return rc0;
+      NTT_CUDA(cudaStreamSynchronize(g_zc.st));
+      memcpy(a, h_a, bytes);
+      return 0;
+    }
+  }
   return with_device_copy(a, batch * n * sizeof(int32_t), [&](void *d_a) -> int {
     int32_t *d_tab = nullptr;
     NTT_CUDA(cudaMalloc(&d_tab, n * sizeof(int32_t)));
@@ -828,6 +912,21 @@ extern "C" int nttb200_red_elementwise_batch(int op, int32_t *c, const int32_t *
   g_launches = 0;
   if (count == 0) return 0;
   const size_t bytes = count * sizeof(int32_t);
+  if (2 * bytes <= ZC_CTX_BYTES) {                                                /* one launch, no DMA */
+    std::unique_lock<std::mutex> lk;
+    if (zc_acquire(lk) == 0) {
+      int32_t *h_a = (int32_t *)g_zc.h, *h_b = (int32_t *)(g_zc.h + bytes);
+      memcpy(h_a, a, bytes);
+      if (op == RED_OP_MUL_RED) memcpy(h_b, b, bytes);
+      red_elementwise_kernel<<<grid_1d(count, 256, current_sms()), 256, 0, g_zc.st>>>(
+          op, (int32_t *)g_zc.d, (const int32_t *)g_zc.d, (const int32_t *)(g_zc.d + bytes), scalar, count);
+      nttb200_count_launch(1);
+      NTT_CUDA(cudaGetLastError());
+      NTT_CUDA(cudaStreamSynchronize(g_zc.st));
+      memcpy(c, h_a, bytes);
+      return 0;
+    }
+  }
   int32_t *d_a = nullptr, *d_b = nullptr;
   cudaError_t e = cudaMalloc(&d_a, bytes);
   if (e == cudaSuccess) e = cudaMemcpy(d_a, a, bytes, cudaMemcpyHostToDevice);
