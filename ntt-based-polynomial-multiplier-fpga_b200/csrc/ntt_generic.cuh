@@ -86,6 +86,11 @@ literal_cta_kernel(uint32_t *data, const uint2 *tab, const int32_t *rtab, uint32
                    unsigned long long batch, ModQ m, int skip0) {
   extern __shared__ __align__(16) uint32_t sx[];
   const bool descending = (DF == DF_CT_STD2REV || DF == DF_GS_STD2REV);
+  /* the table may live in mapped host memory: read it once */
+  uint2 *stab = reinterpret_cast<uint2 *>(sx + n);
+  int32_t *srtab = reinterpret_cast<int32_t *>(sx + n);
+  if (!RED) { for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) stab[i] = tab[i]; }
+  else { for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) srtab[i] = rtab[i]; }
   for (unsigned long long poly = blockIdx.x; poly < batch; poly += gridDim.x) {
     uint32_t *g = data + (poly << logn);
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) sx[i] = g[i];
@@ -100,14 +105,14 @@ literal_cta_kernel(uint32_t *data, const uint2 *tab, const int32_t *rtab, uint32
         if (DF == DF_CT_STD2REV || DF == DF_GS_REV2STD) { j = hi_part; tidx = ((n >> 1) >> lh) + hi_part; }
         else { j = lo_part; tidx = half + lo_part; }
         if (!RED) {
-          const uint2 w = tab[tidx];
+          const uint2 w = stab[tidx];
           uint32_t X = sx[p0], Y = sx[p0 + half];
           if (DF == DF_CT_STD2REV || DF == DF_CT_REV2STD) ct_bfly<ARITH_CANON>(X, Y, w.x, w.y, m);
           else gs_bfly<ARITH_CANON>(X, Y, w.x, w.y, m, 0u);
           sx[p0] = X;
           sx[p0 + half] = Y;
         } else {
-          const int32_t w = rtab[tidx];
+          const int32_t w = srtab[tidx];
           const bool plain = skip0 && j == 0;
           const int32_t X = (int32_t)sx[p0], Y = (int32_t)sx[p0 + half];
           if (DF == DF_CT_STD2REV || DF == DF_CT_REV2STD) {

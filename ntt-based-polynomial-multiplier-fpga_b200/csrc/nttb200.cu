@@ -689,7 +689,7 @@ static int literal_cta_launch(int dataflow, uint32_t *d_a, const uint2 *d_tab, c
   const uint32_t logn = ht_log2(n);
   const int threads = (int)std::min<uint32_t>(512, std::max<uint32_t>(32, n / 2));
   const int grid = (int)std::min<size_t>(batch, (size_t)current_sms() * 4);
-  const size_t smem = n * sizeof(uint32_t);
+  const size_t smem = n * sizeof(uint32_t) + n * (RED ? sizeof(int32_t) : sizeof(uint2));   /* <= 48 KiB */
   switch (dataflow) {
     case DF_CT_STD2REV: literal_cta_kernel<DF_CT_STD2REV, RED><<<grid, threads, smem, st>>>(d_a, d_tab, d_rtab, n, logn, batch, m, skip0); break;
     case DF_GS_REV2STD: literal_cta_kernel<DF_GS_REV2STD, RED><<<grid, threads, smem, st>>>(d_a, d_tab, d_rtab, n, logn, batch, m, skip0); break;
