@@ -556,3 +556,24 @@ def test_packed_u16_extension(gpu, oracle, n, q):
     with pytest.raises(gpu.NttError):
         big.polymul_u16(np.zeros((1, 256), np.uint16), np.zeros((1, 256), np.uint16))
     big.close()
+
+
+def test_operands_not_16_byte_aligned_fall_back_to_the_shoup_kernel(gpu, oracle):
+    """The Plantard kernel prefetches with 16-byte cp.async; operands at a 4-byte offset must still
+    give the right products (served by the Shoup kernel of the same plan)."""
+    import torch
+    n, q, batch = 256, 12289, 301
+    p = gpu.Plan(n, q)
+    a = oracle.random((batch, n), q, 5)
+    b = oracle.random((batch, n), q, 6)
+    da = torch.zeros(batch * n + 1, dtype=torch.int32, device="cuda")
+    db = torch.zeros(batch * n + 3, dtype=torch.int32, device="cuda")
+    dc = torch.zeros(batch * n + 1, dtype=torch.int32, device="cuda")
+    da[1:] = torch.from_numpy(a.reshape(-1)).cuda()
+    db[3:] = torch.from_numpy(b.reshape(-1)).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    p.polymul_dev(dc.data_ptr() + 4, da.data_ptr() + 4, db.data_ptr() + 12, batch, st)
+    torch.cuda.synchronize()
+    assert (dc[1:].cpu().numpy().reshape(batch, n) == oracle.product(n, q, a, b, 10)).all()
+    assert int(dc[0]) == 0
+    p.close()
