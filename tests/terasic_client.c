@@ -70,6 +70,21 @@ int main(int argc, char **argv) {
   PCIE_HANDLE h = p_open(0, 0, 0);
   if (!h) { fprintf(stderr, "PCIE_Open failed\n"); return 6; }
 
+  /* board bring-up loopbacks of linux_app/app.c:95-132, 150-265: a register keeps what was
+   * written, 128 KiB written by DMA to local memory read back identical */
+  {
+    typedef BOOL (*dma_t)(PCIE_HANDLE, DWORD, void *, DWORD);
+    dma_t dma_write = (dma_t)fn[8], dma_read = (dma_t)fn[9];
+    DWORD v = 0;
+    if (!wr32(h, 0, 0x100, 0xDEADBEEFu) || !rd32(h, 0, 0x100, &v) || v != 0xDEADBEEFu) return 20;
+    const unsigned len = 128 * 1024;
+    unsigned char *w = malloc(len), *r = calloc(len, 1);
+    for (unsigned i = 0; i < len; i++) w[i] = (unsigned char)(i * 131u + 7u);
+    if (!dma_write(h, 0x0, w, len) || !dma_read(h, 0x0, r, len)) return 21;
+    for (unsigned i = 0; i < len; i++) if (w[i] != r[i]) return 22;
+    free(w); free(r);
+  }
+
   /* mode 0: W || W_INV || q || n_inv in one FIFO write (the twiddle words are whatever the
    * host generated; a GPU back end only needs q) */
   const unsigned wcount = 272;
