@@ -6,14 +6,14 @@
  *
  *   Plantard word-size multiplication by a constant w, stored as
  *        w~ = ((-w 2^32) mod q) * q^-1  mod 2^32 :
- *        T = umulhi(Y * w~, q)           (IMAD + IMAD.HI.U32 = 3 fmaheavy issue slots)
+ *        T = umulhi(Y * w~, q)           (IMAD + IMAD.WIDE = 3 fmaheavy issue slots)
  *   gives  T = Y w mod q  EXACTLY CANONICAL in [0, q)  whenever  Y * q < 2^32.
  *   [p = Y w~ mod 2^32 satisfies p q = Y W + k 2^32 with W = (-w 2^32) mod q, so
  *    k = floor(p q / 2^32) when 0 <= Y W < 2^32, k == Y w (mod q) and 0 <= k < q.]
  *
  * Against the Shoup multiplication of modarith.cuh (IMAD.HI + 2 IMAD = 4 slots, result in
  * [0,2q), two table words per twiddle) this is 3 slots, a canonical result and ONE table
- * word: the butterfly is IMAD, IMAD.HI, IADD3, IADD3 and -- measured with
+ * word: the butterfly is IMAD, IMAD.WIDE (or IMAD.HI), IADD3, IADD3 and -- measured with
  * nttb200_measure_int_peak(13) vs (3) -- runs 1.31x faster on the B200 integer pipe,
  * which is the unit that binds this kernel (profiles/).  The lane twiddles held in
  * registers halve, which is what leaves room for the next tile's operands to be
