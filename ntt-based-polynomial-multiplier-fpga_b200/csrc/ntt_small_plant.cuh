@@ -38,6 +38,9 @@ namespace nttb200 {
 #ifndef PLANT_MULHI
 #define PLANT_MULHI 3
 #endif
+#ifndef PLANT_BULK_STORE
+#define PLANT_BULK_STORE 0  /* 1: results leave through cp.async.bulk (TMA) -- measured slower, DESIGN.md */
+#endif
 #ifndef PLANT_ADD3
 #define PLANT_ADD3 0
 #endif
@@ -345,6 +348,9 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (tile < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile, P.batch, lane);
 
+  /* bulk (TMA) stores need 16-byte aligned rows in shared memory: every size but the tiniest */
+  constexpr bool BULK = PLANT_BULK_STORE && (Gm::T >= 4) && (Gm::N * sizeof(IO) >= 16);
+  bool bulk_pending = false;
   for (; tile < ntiles; tile += wstride) {
     const unsigned long long poly = tile * Gm::PPW + sub;
     const bool live = poly < P.batch;
@@ -362,6 +368,10 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
 
     pl_fwd_cols<L>(xa, P);
     pl_fwd_cols<L>(xb, P);
+    if (BULK && bulk_pending) {                       /* the previous tile's result row has left sm_a */
+      if (l == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+    }
     if (Gm::H > 0) {
       store_cols<L>(xa, sm_a, l);
       store_cols<L>(xb, sm_b, l);
@@ -402,13 +412,34 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
       load_cols<L>(xa, sm_a, l);
     }
     pl_inv_cols<L, pl_gs_phase_out(Gm::H, 1)>(xa, P);
-    if (live) {
-      IO *cp = gc + (poly << L);
+    if (BULK) {
+    /* result row -> shared memory in natural order -> ONE bulk (TMA) copy per polynomial:
+     * cp.async.bulk.global.shared::cta, issued by the polynomial's first lane */
+    {
+      IO *row = reinterpret_cast<IO *>(sm_a);
+      __syncwarp();                                   /* load_cols of this tile is done with sm_a */
 #pragma unroll
-      for (int k = 0; k < Gm::NV; k++) cp[(k << Gm::H) + l] = (IO)xa[k];
+      for (int k = 0; k < Gm::NV; k++) row[(k << Gm::H) + l] = (IO)xa[k];
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (l == 0 && live) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(row);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     :: "l"(gc + (poly << L)), "r"(sa), "n"(Gm::N * (int)sizeof(IO)) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      bulk_pending = true;
     }
-    __syncwarp();                                     /* smem reuse by the next tile */
+    } else {
+      if (live) {
+        IO *cp = gc + (poly << L);
+#pragma unroll
+        for (int k = 0; k < Gm::NV; k++) cp[(k << Gm::H) + l] = (IO)xa[k];
+      }
+      __syncwarp();                                   /* smem reuse by the next tile */
+    }
   }
+  if (BULK && bulk_pending && l == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 }  // namespace nttb200

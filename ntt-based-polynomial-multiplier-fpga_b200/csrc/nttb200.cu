@@ -228,7 +228,7 @@ extern "C" const char *nttb200_plan_describe(const nttb200_plan *P) { return P ?
 int launch_polymul_small(const nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b,
                          size_t batch, cudaStream_t st) {
   /* the Plantard kernel prefetches with 16-byte cp.async: operands must be 16-byte aligned */
-  if (P->plant && (((uintptr_t)a | (uintptr_t)b) & 15u) == 0)
+  if (P->plant && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15u) == 0)
     return launch_polymul_small_plant(P, c, a, b, batch, st);
   switch (P->arith) {
     case ARITH_LAZY: return launch_polymul_small_lazy(P, c, a, b, batch, st);
@@ -544,8 +544,8 @@ extern "C" int nttb200_polymul_batch_u16_dev(nttb200_plan *P, uint16_t *c, const
   if (!P || !c || !a || !b) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
   if (!P->plant)
     return nttb200_fail(NTTB200_EPARAM, "16-bit I/O needs a half-word modulus plan (q <= 12385, n <= 1024)");
-  if ((((uintptr_t)a | (uintptr_t)b) & 15u) != 0)
-    return nttb200_fail(NTTB200_EPARAM, "16-bit operands must be 16-byte aligned");
+  if ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15u) != 0)
+    return nttb200_fail(NTTB200_EPARAM, "16-bit operands and result must be 16-byte aligned");
   g_launches = 0;
   if (batch == 0) return 0;
   DeviceGuard guard(P->device);
