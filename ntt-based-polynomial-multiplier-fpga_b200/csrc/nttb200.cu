@@ -208,6 +208,7 @@ extern "C" void nttb200_plan_destroy(nttb200_plan *P) {
     if (ln.done) cudaEventDestroy(ln.done);
   }
   if (P->fork) cudaEventDestroy(P->fork);
+  if (P->scratch_done) cudaEventDestroy(P->scratch_done);
   free_table(P->fwd_mixed); free_table(P->inv_mixed);
   free_table(P->fwd_plain); free_table(P->inv_plain);
   free_table(P->fwd_invroot); free_table(P->inv_fwdroot);
@@ -388,7 +389,12 @@ static int ensure_scratch(nttb200_plan *P, size_t polys, int lanes) {
 
 int launch_polymul_large(nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b, size_t batch,
                          cudaStream_t st) {
-  /* the scratch is per plan: concurrent device-resident calls on one plan must use one stream */
+  /* The scratch and the lanes belong to the plan: calls from several host threads / on several
+   * streams are serialised on the device through `scratch_done` (recorded at the end of every
+   * call, awaited at the start of the next), and on the host by large_mu. */
+  std::lock_guard<std::mutex> lock(P->large_mu);
+  if (!P->scratch_done) NTT_CUDA(cudaEventCreateWithFlags(&P->scratch_done, cudaEventDisableTiming));
+  else NTT_CUDA(cudaStreamWaitEvent(st, P->scratch_done, 0));
   const size_t chunk = std::max<size_t>(1, std::min<size_t>(batch, large_scratch_budget() / (P->n * 8ull)));
   const size_t nchunks = (batch + chunk - 1) / chunk;
   const int lanes = (int)std::min<size_t>((size_t)large_lanes(), nchunks);
@@ -418,6 +424,7 @@ int launch_polymul_large(nttb200_plan *P, uint32_t *c, const uint32_t *a, const 
       NTT_CUDA(cudaStreamWaitEvent(st, P->lanes[l].done, 0));
     }
   }
+  NTT_CUDA(cudaEventRecord(P->scratch_done, st));
   return 0;
 }
 

@@ -68,6 +68,8 @@ struct nttb200_plan {
   size_t scratch_polys = 0;
   std::vector<LargeLane> lanes;
   cudaEvent_t fork = nullptr;
+  cudaEvent_t scratch_done = nullptr;   /* end of the last call that used the scratch */
+  std::mutex large_mu;
 };
 
 /* error plumbing (nttb200.cu) */
