@@ -577,3 +577,25 @@ def test_operands_not_16_byte_aligned_fall_back_to_the_shoup_kernel(gpu, oracle)
     assert (dc[1:].cpu().numpy().reshape(batch, n) == oracle.product(n, q, a, b, 10)).all()
     assert int(dc[0]) == 0
     p.close()
+
+
+def test_large_n_calls_on_two_streams_share_the_scratch_safely(gpu, oracle):
+    """Two device-resident calls on ONE large-n plan, issued back to back on two different
+    streams, use the same scratch: the second must wait for the first on the device."""
+    import torch
+    n, q, batch = 8192, 65537, 96
+    p = gpu.Plan(n, q)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    xs = [torch.randint(0, q, (batch, n), dtype=torch.int32, device="cuda", generator=g) for _ in range(4)]
+    outs = [torch.empty_like(xs[0]) for _ in range(2)]
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        p.polymul_dev(outs[0].data_ptr(), xs[0].data_ptr(), xs[1].data_ptr(), batch, s1.cuda_stream)
+        p.polymul_dev(outs[1].data_ptr(), xs[2].data_ptr(), xs[3].data_ptr(), batch, s2.cuda_stream)
+    torch.cuda.synchronize()
+    idx = [0, 47, 95]
+    for o, (u, v) in zip(outs, ((xs[0], xs[1]), (xs[2], xs[3]))):
+        want = oracle.product(n, q, u[idx].cpu().numpy(), v[idx].cpu().numpy(), 10)
+        assert (o[idx].cpu().numpy() == want).all()
+    p.close()
