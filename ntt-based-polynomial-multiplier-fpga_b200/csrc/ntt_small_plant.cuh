@@ -442,4 +442,72 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
   if (BULK && bulk_pending && l == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+/* bring a value < B q to [0, q) with ceil(log2 B) conditional subtractions */
+template <int B, typename PT>
+__device__ __forceinline__ uint32_t pl_canon(uint32_t x, const PT &P) {
+  if (B > 8) x = csub(x, P.qmul[8]);
+  if (B > 4) x = csub(x, P.qmul[4]);
+  if (B > 2) x = csub(x, P.qmul[2]);
+  if (B > 1) x = csub(x, P.qmul[1]);
+  return x;
+}
+
+/* =====================================================================================
+ * Standalone transforms for half-word moduli, in place on P.c (uint32 rows), canonical output.
+ *   DIR 0: forward CT std->rev with the table P.tw_fwd / P.ufwd
+ *   DIR 1: inverse GS rev->std with P.tw_inv / P.uinv; the last stage multiplies its sum branch
+ *          by last_x and its diff branch by last_y (1 and p[1] when no scaling is wanted)
+ * Same reference functions as ntt_small_kernel (the table decides which).
+ * ===================================================================================== */
+template <int L, int WARPS, int DIR>
+__global__ void __launch_bounds__(WARPS * 32)
+ntt_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
+  using Gm = SmallGeom<L>;
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int sub = lane / Gm::T;
+  const int l = lane % Gm::T;
+  uint32_t *sm_a = smem + (warp * Gm::PPW + sub) * Gm::STRIDE;
+  uint32_t *data = static_cast<uint32_t *>(P.c);
+
+  LaneTw1<L> tw;
+  tw.load(DIR == 0 ? P.tw_fwd : P.tw_inv, l);
+
+  const unsigned long long ntiles = (P.batch + Gm::PPW - 1) / Gm::PPW;
+  const unsigned long long wstride = (unsigned long long)gridDim.x * WARPS;
+  for (unsigned long long tile = (unsigned long long)blockIdx.x * WARPS + warp; tile < ntiles;
+       tile += wstride) {
+    const unsigned long long poly = tile * Gm::PPW + sub;
+    const bool live = poly < P.batch;
+    const unsigned long long off = (live ? poly : 0ull) << L;
+    uint32_t x[Gm::NV];
+    if (DIR == 0) {
+      gload_cols<L>(x, data + off, l);
+      pl_fwd_cols<L>(x, P);
+      if (Gm::H > 0) {
+        store_cols<L>(x, sm_a, l);
+        __syncwarp();
+        load_rows<L>(x, sm_a, l);
+        pl_fwd_rows<L>(x, tw, P);
+      }
+#pragma unroll
+      for (int k = 0; k < Gm::NV; k++) x[k] = pl_canon<L + 1>(x[k], P);
+      __syncwarp();
+      if (live) gstore_rows<L>(x, data + off, l);
+    } else {
+      gload_rows<L>(x, data + off, l);
+      if (Gm::H > 0) {
+        pl_inv_rows<L>(x, tw, P);
+        store_rows<L>(x, sm_a, l);
+        __syncwarp();
+        load_cols<L>(x, sm_a, l);
+      }
+      pl_inv_cols<L, pl_gs_phase_out(Gm::H, 1)>(x, P);
+      __syncwarp();
+      if (live) gstore_cols<L>(x, data + off, l);
+    }
+  }
+}
+
 }  // namespace nttb200

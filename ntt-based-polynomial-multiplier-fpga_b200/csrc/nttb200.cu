@@ -170,11 +170,11 @@ extern "C" int nttb200_plan_create(nttb200_plan **out, uint32_t n, uint32_t q, u
   const uint32_t iomega = ht_invmod(omega, q);
   int rc = 0;
   ht_level_table(w.data(), n, q, 1, omega, 1);
-  rc = rc ? rc : upload_table(P->fwd_plain, w, q, cyclic ? pq : 0);
-  rc = rc ? rc : upload_table(P->inv_fwdroot, w, q);
+  rc = rc ? rc : upload_table(P->fwd_plain, w, q, pq);
+  rc = rc ? rc : upload_table(P->inv_fwdroot, w, q, pq);
   ht_level_table(w.data(), n, q, 1, iomega, 1);
-  rc = rc ? rc : upload_table(P->inv_plain, w, q, cyclic ? pq : 0);
-  rc = rc ? rc : upload_table(P->fwd_invroot, w, q);
+  rc = rc ? rc : upload_table(P->inv_plain, w, q, pq);
+  rc = rc ? rc : upload_table(P->fwd_invroot, w, q, pq);
   if (!cyclic) {
     ht_level_table(w.data(), n, q, psi, omega, 1);
     rc = rc ? rc : upload_table(P->fwd_mixed, w, q, pq);
@@ -239,6 +239,7 @@ int launch_polymul_small(const nttb200_plan *P, uint32_t *c, const uint32_t *a, 
 }
 int launch_ntt_small(const nttb200_plan *P, const DevTable &tab, int dir, int scale, uint32_t *a,
                      size_t batch, cudaStream_t st) {
+  if (P->plant && tab.d1 && !getenv("NTTB200_NTT_SHOUP")) return launch_ntt_small_plant(P, tab, dir, scale, a, batch, st);
   switch (P->arith) {
     case ARITH_LAZY: return launch_ntt_small_lazy(P, tab, dir, scale, a, batch, st);
     case ARITH_HARVEY: return launch_ntt_small_harvey(P, tab, dir, scale, a, batch, st);

@@ -105,5 +105,7 @@ int small_kernel_info(const nttb200_plan *P, int *regs, int *smem_bytes, int *bl
 int launch_polymul_small_plant(const nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b,
                                size_t batch, cudaStream_t st);
 int small_kernel_info_plant(const nttb200_plan *P, int *regs, int *smem_bytes, int *blocks_per_sm);
+int launch_ntt_small_plant(const nttb200_plan *P, const DevTable &tab, int dir, int scale, uint32_t *a,
+                           size_t batch, cudaStream_t st);
 int launch_polymul_small_plant_u16(const nttb200_plan *P, uint16_t *c, const uint16_t *a, const uint16_t *b,
                                    size_t batch, cudaStream_t st);

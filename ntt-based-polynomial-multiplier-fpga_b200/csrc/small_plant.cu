@@ -127,6 +127,48 @@ int launch_polymul_small_plant_u16(const nttb200_plan *P, uint16_t *c, const uin
                                    size_t batch, cudaStream_t st) {
   PLANT_SWITCH(return (run_plant<L, 2, uint16_t>(P, c, a, b, batch, st)))
 }
+template <int L, int DIR>
+int run_ntt_plant(const nttb200_plan *P, const DevTable &tab, int scale, uint32_t *a, size_t batch,
+                  cudaStream_t st) {
+  using Gm = SmallGeom<L>;
+  constexpr int WARPS = PlantCfg<L>::WARPS;
+  PlantParams<Gm::R> p{};
+  p.a = nullptr; p.b = nullptr; p.c = a; p.batch = batch;
+  p.tw_fwd = tab.d1; p.tw_inv = tab.d1;
+  p.q = P->q; p.qinv = P->m.qinv;
+  const uint32_t q = P->q;
+  const uint64_t sc = scale ? P->n_inv : 1;
+  p.last_x = nttb200_plant_form((uint32_t)sc, q, p.qinv);
+  p.last_y = nttb200_plant_form((uint32_t)(sc * tab.h[1].x % q), q, p.qinv);
+  for (int i = 0; i < (int)(sizeof p.qmul / sizeof p.qmul[0]); i++) p.qmul[i] = (uint32_t)i * q;
+  for (int i = 0; i < (1 << Gm::R); i++) {
+    const uint32_t v = (size_t)i < tab.h1.size() ? tab.h1[i] : 0;
+    p.ufwd[i] = v;
+    p.uinv[i] = v;
+  }
+  auto kernel = ntt_plant_kernel<L, WARPS, DIR>;
+  const int smem = WARPS * Gm::PPW * Gm::STRIDE * (int)sizeof(uint32_t);
+  int per_sm = 0;
+  NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  NTT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS * 32, smem));
+  if (per_sm < 1) return nttb200_fail(NTTB200_ECUDA, "plant transform kernel does not fit on an SM");
+  const unsigned long long tiles = (batch + Gm::PPW - 1) / Gm::PPW;
+  const unsigned long long want = (tiles + WARPS - 1) / WARPS;
+  const unsigned long long cap = (unsigned long long)P->sm_count * per_sm;
+  const int grid = (int)(want < cap ? (want ? want : 1) : cap);
+  kernel<<<grid, WARPS * 32, smem, st>>>(p);
+  nttb200_count_launch(1);
+  NTT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+/* standalone transform of a half-word-modulus plan: dir 0 forward CT, dir 1 inverse GS */
+int launch_ntt_small_plant(const nttb200_plan *P, const DevTable &tab, int dir, int scale, uint32_t *a,
+                           size_t batch, cudaStream_t st) {
+  if (dir == 0) { PLANT_SWITCH(return (run_ntt_plant<L, 0>(P, tab, scale, a, batch, st))) }
+  PLANT_SWITCH(return (run_ntt_plant<L, 1>(P, tab, scale, a, batch, st)))
+}
+
 int small_kernel_info_plant(const nttb200_plan *P, int *regs, int *smem_bytes, int *blocks_per_sm) {
   if (plant_minb(P->logn) == 2) { PLANT_SWITCH(return (info_plant<L, 2>(regs, smem_bytes, blocks_per_sm))) }
   PLANT_SWITCH(return (info_plant<L, 3>(regs, smem_bytes, blocks_per_sm)))
