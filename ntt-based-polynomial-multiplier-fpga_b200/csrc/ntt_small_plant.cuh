@@ -463,12 +463,16 @@ template <int L, int WARPS, int DIR>
 __global__ void __launch_bounds__(WARPS * 32)
 ntt_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
   using Gm = SmallGeom<L>;
+  using Pg = PlantGeom<L, uint32_t>;
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int sub = lane / Gm::T;
   const int l = lane % Gm::T;
-  uint32_t *sm_a = smem + (warp * Gm::PPW + sub) * Gm::STRIDE;
+  /* per warp: [prefetch buffer (forward only)] [transposition buffer] */
+  constexpr int WARP_WORDS = (DIR == 0 ? Pg::PF_WORDS : 0) + Gm::PPW * Gm::STRIDE;
+  uint32_t *pf = smem + warp * WARP_WORDS;
+  uint32_t *sm_a = pf + (DIR == 0 ? Pg::PF_WORDS : 0) + sub * Gm::STRIDE;
   uint32_t *data = static_cast<uint32_t *>(P.c);
 
   LaneTw1<L> tw;
@@ -476,14 +480,33 @@ ntt_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
 
   const unsigned long long ntiles = (P.batch + Gm::PPW - 1) / Gm::PPW;
   const unsigned long long wstride = (unsigned long long)gridDim.x * WARPS;
-  for (unsigned long long tile = (unsigned long long)blockIdx.x * WARPS + warp; tile < ntiles;
-       tile += wstride) {
+  unsigned long long tile = (unsigned long long)blockIdx.x * WARPS + warp;
+  /* forward: rows arrive by 128-bit cp.async one tile ahead (the column layout needs 32-bit
+   * accesses, which are cheap in shared memory and half-efficient on HBM) */
+  auto prefetch = [&](unsigned long long t) {
+#pragma unroll
+    for (int i = 0; i < Pg::ITERS; i++) {
+      const int c = i * 32 + lane;
+      const int s2 = c / Pg::CHUNKS, cc = c % Pg::CHUNKS;
+      const unsigned long long poly = t * Gm::PPW + s2;
+      if (s2 < Gm::PPW && poly < P.batch)
+        cp_async16(pf + s2 * Pg::PSTRIDE + cc * 4, data + (poly << L) + cc * 4);
+    }
+  };
+  if (DIR == 0 && tile < ntiles) prefetch(tile);
+
+  for (; tile < ntiles; tile += wstride) {
     const unsigned long long poly = tile * Gm::PPW + sub;
     const bool live = poly < P.batch;
     const unsigned long long off = (live ? poly : 0ull) << L;
     uint32_t x[Gm::NV];
     if (DIR == 0) {
-      gload_cols<L>(x, data + off, l);
+      cp_async_wait_all();
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < Gm::NV; k++) x[k] = pf[sub * Pg::PSTRIDE + (k << Gm::H) + l];
+      __syncwarp();
+      if (tile + wstride < ntiles) prefetch(tile + wstride);
       pl_fwd_cols<L>(x, P);
       if (Gm::H > 0) {
         store_cols<L>(x, sm_a, l);

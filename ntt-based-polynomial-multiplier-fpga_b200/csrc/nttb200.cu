@@ -239,7 +239,9 @@ int launch_polymul_small(const nttb200_plan *P, uint32_t *c, const uint32_t *a, 
 }
 int launch_ntt_small(const nttb200_plan *P, const DevTable &tab, int dir, int scale, uint32_t *a,
                      size_t batch, cudaStream_t st) {
-  if (P->plant && tab.d1 && !getenv("NTTB200_NTT_SHOUP")) return launch_ntt_small_plant(P, tab, dir, scale, a, batch, st);
+  /* (the forward Plantard kernel prefetches with 16-byte cp.async: rows must be 16-byte aligned) */
+  if (P->plant && tab.d1 && ((uintptr_t)a & 15u) == 0 && !getenv("NTTB200_NTT_SHOUP"))
+    return launch_ntt_small_plant(P, tab, dir, scale, a, batch, st);
   switch (P->arith) {
     case ARITH_LAZY: return launch_ntt_small_lazy(P, tab, dir, scale, a, batch, st);
     case ARITH_HARVEY: return launch_ntt_small_harvey(P, tab, dir, scale, a, batch, st);

@@ -147,7 +147,8 @@ int run_ntt_plant(const nttb200_plan *P, const DevTable &tab, int scale, uint32_
     p.uinv[i] = v;
   }
   auto kernel = ntt_plant_kernel<L, WARPS, DIR>;
-  const int smem = WARPS * Gm::PPW * Gm::STRIDE * (int)sizeof(uint32_t);
+  const int smem = WARPS * ((DIR == 0 ? PlantGeom<L, uint32_t>::PF_WORDS : 0) + Gm::PPW * Gm::STRIDE) *
+                   (int)sizeof(uint32_t);
   int per_sm = 0;
   NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   NTT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS * 32, smem));
