@@ -369,6 +369,26 @@ def main() -> int:
     e2e_value = world * batch * e2e_steps / e2e_s
 
     peak_gbs, peak_src = measured_peaks()
+    # the standalone NTT call surface (in place, 8n bytes per transform): HBM-bound kernels.
+    # Run on the a-buffers of the rotating sets (after the product has been timed and checked).
+    ntt_lines = {}
+    try:
+        for kind in ("mulntt_std2rev", "inttmul_rev2std_scaled") if "omega=" not in plan.describe() else ("ntt_std2rev", "intt_rev2std_scaled"):
+            for i in range(3):
+                plan.transform_dev(kind, bufs[i % sets][0].data_ptr(), batch, stream)
+            torch.cuda.synchronize()
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 30
+            t0e.record()
+            for i in range(reps):
+                plan.transform_dev(kind, bufs[i % sets][0].data_ptr(), batch, stream)
+            t1e.record()
+            torch.cuda.synchronize()
+            tms = t0e.elapsed_time(t1e) / reps
+            gbs = 8 * n * batch / (tms * 1e-3) / 1e9
+            ntt_lines[kind] = {"transforms_per_s": batch / (tms * 1e-3), "achieved_GBs": gbs, "frac_of_hbm_peak": gbs / peak_gbs}
+    except Exception as ex:
+        ntt_lines = {"error": repr(ex)}
     alg_bytes = 12 * n * batch                      # read a, read b, write c (int32 API)
     # n <= 1024: one fused kernel per step.  n > 1024: the step is a pipeline of 3 kernels per
     # L2-resident batch chunk; the roofline is then stated for the whole pipeline (step time).
@@ -428,6 +448,7 @@ def main() -> int:
                                  "pair; Plantard kernel (q<=12385): butterfly 3, pointwise 4, scale 3",
                          "arith": "plantard" if plantard else "shoup"},
         "parity_ok": parity_ok,
+        "standalone_ntt": ntt_lines,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
