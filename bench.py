@@ -41,6 +41,7 @@ WORKLOADS = {
     # name: (n, q, psi, log2 batch, description)
     "c2": (256, 12289, 1002, 16, "BASELINE configs[1]: batch 2^16 polymuls at the reference default (n=256,q=12289)"),
     "c3": (256, 7681, 0, 20, "BASELINE configs[2] (Kyber-like): n=256 q=7681 (3329 has no 512-th root), batch 2^20"),
+    "c3c": (256, 3329, 0, 20, "BASELINE configs[2], literal q=3329: cyclic product mod x^256-1 (the psi-free surface), batch 2^20"),
     "c4": (1024, 12289, 0, 18, "BASELINE configs[3] (Falcon/NewHope-like): n=1024 q=12289 batch 2^18"),
     "c5": (65536, 2013265921, 0, 10, "BASELINE configs[4]: n=2^16 q=2013265921 batch 2^10, multi-pass"),
 }
@@ -181,7 +182,7 @@ def host_cores() -> int:
 def cpu_pool(n, q, psi, cores):
     from oracle import loader
     use_ref = (n, q) == (256, 12289) and loader.reference_available()
-    variant = loader.REF_RED_CT if use_ref else loader.PRODUCT_MERGED
+    variant = loader.REF_RED_CT if use_ref else (loader.PRODUCT_MERGED if (q - 1) % (2 * n) == 0 else loader.PRODUCT_CYCLIC)
     ctx = mp.get_context("fork")
     pool = ctx.Pool(cores, initializer=_cpu_worker_init, initargs=(n, q, psi, use_ref, variant))
     kind = "reference" if use_ref else "port"
@@ -295,7 +296,8 @@ def main() -> int:
         sh.init_distributed("nccl")
     warmup = max(3, args.warmup)
 
-    plan = mod.Plan(n, q, psi)
+    cyclic = (q - 1) % (2 * n) != 0                  # q=3329, n=256: no 512-th root of unity
+    plan = mod.Plan(n, q, psi, cyclic=cyclic)
     row_bytes = n * 4
     # distinct buffer sets so that successive steps never find their inputs in the 126 MB L2
     sets = max(2, -(-3 * L2_BYTES // (3 * batch * row_bytes)) + 1)
@@ -350,7 +352,8 @@ def main() -> int:
     O = loader.Oracle()
     a, b, c = bufs[(args.steps - 1) % sets]
     idx = torch.tensor([0, 1, batch // 2, batch - 1], device=dev)
-    want = O.product(n, q, a[idx].cpu().numpy(), b[idx].cpu().numpy(), loader.PRODUCT_MERGED)
+    variant = loader.PRODUCT_CYCLIC if cyclic else loader.PRODUCT_MERGED
+    want = O.product(n, q, a[idx].cpu().numpy(), b[idx].cpu().numpy(), variant)
     parity_ok = bool((c[idx].cpu().numpy() == want).all())
 
     # e2e: host buffers (pinned) through nttb200_polymul_batch: H2D + kernel + D2H per step
@@ -365,7 +368,7 @@ def main() -> int:
     for _ in range(e2e_steps):
         plan.polymul_host_ptr(hc.ptr, ha.ptr, hb.ptr, batch)
     e2e_s = sh.max_over_ranks(time.perf_counter() - t0, dev)
-    e2e_ok = bool((hc.array[:2] == O.product(n, q, ha.array[:2], hb.array[:2], loader.PRODUCT_MERGED)).all())
+    e2e_ok = bool((hc.array[:2] == O.product(n, q, ha.array[:2], hb.array[:2], variant)).all())
     e2e_value = world * batch * e2e_steps / e2e_s
 
     peak_gbs, peak_src = measured_peaks()

@@ -477,13 +477,16 @@ def _dev_buffers(torch, *arrays):
     return [torch.from_numpy(x).cuda() for x in arrays]
 
 
-@pytest.mark.parametrize("n,q,logb", [(256, 12289, 20), (256, 7681, 20), (1024, 12289, 18)])
+@pytest.mark.parametrize("n,q,logb", [(256, 12289, 20), (256, 7681, 20), (1024, 12289, 18), (256, 3329, 20)])
 def test_full_size_batches_properties(gpu, oracle, n, q, logb):
     """BASELINE configs 3/4 at full batch, device-resident: sampled rows against the oracle plus
-    size-independent properties (commutativity, linearity in a, delta rows)."""
+    size-independent properties (commutativity, linearity in a, delta rows).  q = 3329 has no
+    512-th root of unity: that case is the cyclic product."""
     import torch
     batch = 1 << logb
-    p = gpu.Plan(n, q)
+    cyclic = (q - 1) % (2 * n) != 0
+    variant = 30 if cyclic else 10
+    p = gpu.Plan(n, q, cyclic=cyclic)
     g = torch.Generator(device="cuda").manual_seed(1234 + n + q)
     a = torch.randint(0, q, (batch, n), dtype=torch.int32, device="cuda", generator=g)
     b = torch.randint(0, q, (batch, n), dtype=torch.int32, device="cuda", generator=g)
@@ -498,7 +501,7 @@ def test_full_size_batches_properties(gpu, oracle, n, q, logb):
     idx = np.unique(np.concatenate([np.arange(0, 8), np.random.default_rng(1).integers(0, batch, 2048),
                                     np.arange(batch - 8, batch)]))
     ti = torch.from_numpy(idx).cuda()
-    want = oracle.product(n, q, a[ti].cpu().numpy(), b[ti].cpu().numpy(), 10)
+    want = oracle.product(n, q, a[ti].cpu().numpy(), b[ti].cpu().numpy(), variant)
     assert (c[ti].cpu().numpy() == want).all()
     # commutativity on the whole batch
     c2 = torch.empty_like(a)
