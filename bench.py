@@ -43,6 +43,7 @@ WORKLOADS = {
     "c3": (256, 7681, 0, 20, "BASELINE configs[2] (Kyber-like): n=256 q=7681 (3329 has no 512-th root), batch 2^20"),
     "c3c": (256, 3329, 0, 20, "BASELINE configs[2], literal q=3329: cyclic product mod x^256-1 (the psi-free surface), batch 2^20"),
     "c4": (1024, 12289, 0, 18, "BASELINE configs[3] (Falcon/NewHope-like): n=1024 q=12289 batch 2^18"),
+    "c5h": (65536, 998244353, 0, 10, "variant of configs[4] with a 30-bit prime (119*2^23+1): HARVEY class, 6-instruction butterflies"),
     "c5": (65536, 2013265921, 0, 10, "BASELINE configs[4]: n=2^16 q=2013265921 batch 2^10, multi-pass"),
 }
 # DRAM bytes (read + write) per launch of the dominant kernel, from `ncu --set full` captures
