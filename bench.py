@@ -369,8 +369,17 @@ def main() -> int:
     for _ in range(e2e_steps):
         plan.polymul_host_ptr(hc.ptr, ha.ptr, hb.ptr, batch)
     e2e_s = sh.max_over_ranks(time.perf_counter() - t0, dev)
-    e2e_ok = bool((hc.array[:2] == O.product(n, q, ha.array[:2], hb.array[:2], variant)).all())
+    rows = np.unique(np.r_[0:2, batch // 2 - 1:batch // 2 + 1, batch - 2:batch,
+                           np.random.default_rng(7).integers(0, batch, 26)])
+    e2e_ok = bool((hc.array[rows] == O.product(n, q, ha.array[rows], hb.array[rows], variant)).all())
     e2e_value = world * batch * e2e_steps / e2e_s
+    # what crossed the PCIe link in the last timed call: 16-bit words for the rows the host pool
+    # narrowed (half-word moduli, csrc/hostwire.c), the caller's 32-bit words for the rest
+    ws = plan.wire_stats()
+    if ws["rows16"] + ws["rows32"] == 0:
+        ws["rows32"] = batch
+    h2d_bytes = 2 * (2 * ws["rows16"] + 4 * ws["rows32"]) * n
+    d2h_bytes = (2 * ws["result_rows16"] + 4 * (batch - ws["result_rows16"])) * n
 
     peak_gbs, peak_src = measured_peaks()
     # the standalone NTT call surface (in place, 8n bytes per transform): HBM-bound kernels.
@@ -427,9 +436,13 @@ def main() -> int:
                    "l2": f"inputs rotate over {sets} buffer sets ({sets * 3 * batch * row_bytes >> 20} MiB) "
                          f"> 126 MB L2, so no step finds its operands cached",
                    "parallelism": f"batch-sharded x{world}, no collective"},
-        "e2e": {"value": e2e_value, "unit": "polymul/s", "h2d_bytes_per_step": 2 * batch * row_bytes,
-                "d2h_bytes_per_step": batch * row_bytes, "steps": e2e_steps,
-                "api": "nttb200_polymul_batch (host buffers, pinned; 3-slot stream ring)", "parity_ok": e2e_ok},
+        "e2e": {"value": e2e_value, "unit": "polymul/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
+                "api": "nttb200_polymul_batch (int32 host buffers in and out, pinned; stream ring; rows cross "
+                       "PCIe as 16-bit words when the host thread pool narrows them, else as 32-bit words)",
+                "wire": {"rows_16bit": ws["rows16"], "rows_32bit": ws["rows32"],
+                         "result_rows_16bit": ws["result_rows16"], "host_threads": ws["host_threads"],
+                         "mode": os.environ.get("NTTB200_WIRE", "auto")},
+                "host_bytes_per_step": 3 * batch * row_bytes, "parity_ok": e2e_ok},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",

@@ -88,6 +88,22 @@ const char *nttb200_plan_describe(const nttb200_plan *plan);
  * returns when c is complete. */
 int nttb200_polymul_batch(nttb200_plan *plan, int32_t *c, const int32_t *a, const int32_t *b,
                           size_t batch);
+/* Wire format of the host-buffer call above, half-word moduli (q <= 12385, n <= 1024), calls of
+ * 2^19 words per operand or more: the call is bound by the PCIe link, so chunks of the batch
+ * cross it as 16-bit words -- narrowed from / widened into the caller's int32_t rows by a pool of
+ * host threads through pinned staging (csrc/hostwire.c) -- as long as the host keeps up, and as
+ * the caller's 32-bit words otherwise; a chunk holding a word that does not fit 16 bits always
+ * travels as 32-bit words, so results never depend on the wire.  This stands where the
+ * reference streams 32-bit FIFO words to the board (COMM/linux_app/NTT_PCIECommunicationv2.c:
+ * 166-224).  The result rows of a 16-bit chunk return as 16-bit words that the pool widens into c
+ * (NTTB200_WIRE_C32=1: as int32 words written by the kernel and copied straight into a pinned c).
+ * Environment: NTTB200_WIRE=auto|16|32, NTTB200_HOST_THREADS (default: the CPUs the process may
+ * run on, at most 32).  Statistics of the plan's last host-buffer call: polynomials whose
+ * operands crossed the link as 16-bit / as 32-bit words (both 0 for calls below the threshold),
+ * and those whose result came back as 16-bit words: */
+int nttb200_plan_wire_stats(const nttb200_plan *plan, unsigned long long *rows16,
+                            unsigned long long *rows32, unsigned long long *rows_c16,
+                            int *host_threads);
 /* Device-resident buffers (the timed path: no PCIe in the loop).  Asynchronous on
  * `stream` (a cudaStream_t passed as void*, NULL = the legacy default stream). */
 int nttb200_polymul_batch_dev(nttb200_plan *plan, int32_t *c_dev, const int32_t *a_dev,

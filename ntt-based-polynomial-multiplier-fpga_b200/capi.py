@@ -69,6 +69,8 @@ def lib() -> C.CDLL:
     L.nttb200_plan_describe.restype = C.c_char_p
     L.nttb200_polymul_batch.argtypes = [vp, i32p, i32p, i32p, sz]
     L.nttb200_polymul_batch_dev.argtypes = [vp, i32p, i32p, i32p, sz, vp]
+    L.nttb200_plan_wire_stats.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong),
+                                          C.POINTER(C.c_ulonglong), C.POINTER(C.c_int)]
     L.nttb200_ntt_batch.argtypes = [vp, C.c_int, i32p, sz]
     L.nttb200_ntt_batch_dev.argtypes = [vp, C.c_int, i32p, sz, vp]
     L.nttb200_ntt_table_batch.argtypes = [C.c_uint32, C.c_uint32, C.c_int, u32p, i32p, sz]
@@ -271,6 +273,12 @@ class Plan:
         c = np.empty_like(a) if out is None else out
         _check(lib().nttb200_polymul_batch(self._h, _ptr(c), _ptr(a), _ptr(b), a.shape[0]))
         return c
+
+    def wire_stats(self) -> dict:
+        """Polynomials of the last host-buffer call that crossed PCIe as 16-bit / 32-bit words."""
+        c16, c32, r16, th = C.c_ulonglong(0), C.c_ulonglong(0), C.c_ulonglong(0), C.c_int(0)
+        _check(lib().nttb200_plan_wire_stats(self._h, C.byref(c16), C.byref(c32), C.byref(r16), C.byref(th)))
+        return {"rows16": c16.value, "rows32": c32.value, "result_rows16": r16.value, "host_threads": th.value}
 
     def polymul_u16(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
         """Packed 16-bit extension (q <= 12385): uint16 in, uint16 out."""

@@ -314,7 +314,7 @@ __device__ __forceinline__ void plant_prefetch(IO *pa, IO *pb, const IO *ga, con
 /* =====================================================================================
  * Fused product kernel, half-word moduli.
  * ===================================================================================== */
-template <int L, int WARPS, int MINB, bool TWREG, typename IO = uint32_t>
+template <int L, int WARPS, int MINB, bool TWREG, typename IO = uint32_t, typename OIO = IO>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
   using Gm = SmallGeom<L>;
@@ -329,7 +329,7 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
   uint32_t *sm_a = smem + warp * Pg::WARP_WORDS + 2 * Pg::PF_WORDS + sub * Gm::STRIDE;
   uint32_t *sm_b = sm_a + Gm::PPW * Gm::STRIDE;
   const IO *ga = static_cast<const IO *>(P.a), *gb = static_cast<const IO *>(P.b);
-  IO *gc = static_cast<IO *>(P.c);
+  OIO *gc = static_cast<OIO *>(P.c);                  /* result rows may be wider than the operands */
   const uint32_t q = P.q;
 
   const unsigned long long ntiles = (P.batch + Gm::PPW - 1) / Gm::PPW;
@@ -349,7 +349,7 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
   if (tile < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile, P.batch, lane);
 
   /* bulk (TMA) stores need 16-byte aligned rows in shared memory: every size but the tiniest */
-  constexpr bool BULK = PLANT_BULK_STORE && (Gm::T >= 4) && (Gm::N * sizeof(IO) >= 16);
+  constexpr bool BULK = PLANT_BULK_STORE && (Gm::T >= 4) && (Gm::N * sizeof(IO) >= 16) && sizeof(IO) == sizeof(OIO);
   bool bulk_pending = false;
   for (; tile < ntiles; tile += wstride) {
     const unsigned long long poly = tile * Gm::PPW + sub;
@@ -416,25 +416,25 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
     /* result row -> shared memory in natural order -> ONE bulk (TMA) copy per polynomial:
      * cp.async.bulk.global.shared::cta, issued by the polynomial's first lane */
     {
-      IO *row = reinterpret_cast<IO *>(sm_a);
+      OIO *row = reinterpret_cast<OIO *>(sm_a);
       __syncwarp();                                   /* load_cols of this tile is done with sm_a */
 #pragma unroll
-      for (int k = 0; k < Gm::NV; k++) row[(k << Gm::H) + l] = (IO)xa[k];
+      for (int k = 0; k < Gm::NV; k++) row[(k << Gm::H) + l] = (OIO)xa[k];
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (l == 0 && live) {
         const unsigned sa = (unsigned)__cvta_generic_to_shared(row);
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                     :: "l"(gc + (poly << L)), "r"(sa), "n"(Gm::N * (int)sizeof(IO)) : "memory");
+                     :: "l"(gc + (poly << L)), "r"(sa), "n"(Gm::N * (int)sizeof(OIO)) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       bulk_pending = true;
     }
     } else {
       if (live) {
-        IO *cp = gc + (poly << L);
+        OIO *cp = gc + (poly << L);
 #pragma unroll
-        for (int k = 0; k < Gm::NV; k++) cp[(k << Gm::H) + l] = (IO)xa[k];
+        for (int k = 0; k < Gm::NV; k++) cp[(k << Gm::H) + l] = (OIO)xa[k];
       }
       __syncwarp();                                   /* smem reuse by the next tile */
     }

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "host_tables.h"
+#include "hostwire.h"
 #include "ntt_generic.cuh"
 #include "plan.h"
 
@@ -200,6 +201,12 @@ extern "C" void nttb200_plan_destroy(nttb200_plan *P) {
     if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
     if (s.done) cudaEventDestroy(s.done);
     cudaFree(s.d_a); cudaFree(s.d_b); cudaFree(s.d_c);
+  }
+  for (auto &s : P->wslots) {
+    if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+    if (s.done) cudaEventDestroy(s.done);
+    cudaFree(s.d_a); cudaFree(s.d_b); cudaFree(s.d_c);
+    if (s.h_a) cudaFreeHost(s.h_a);
   }
   if (P->scratch) cudaFree(P->scratch);
   if (P->zc_host) cudaFreeHost(P->zc_host);
@@ -477,6 +484,7 @@ static int nslot() { static int v = env_int("NTTB200_NSLOT", 3, 1, 8); return v;
 #define NSLOT nslot()
 
 static const size_t ZC_BYTES = 64u << 10;    /* per operand, zero-copy path of small calls */
+static const size_t WIRE_MIN_WORDS = 1u << 19;   /* per operand: smaller calls keep the plain DMA ring */
 
 static int ensure_slots(nttb200_plan *P, bool need_b) {
   if (!P->slots.empty()) return 0;
@@ -505,6 +513,206 @@ static int ensure_slots(nttb200_plan *P, bool need_b) {
   return 0;
 }
 
+/* ------------------------------------------------------------------------------------ */
+/* Host buffers, half-word moduli: the WIRE pipeline.                                      */
+/* The host-buffer path is bound by the PCIe link (2n words in, n out per product), so    */
+/* chunks travel as 16-bit words where the host can narrow them fast enough (hostwire.c:  */
+/* worker threads, pinned staging) and as the caller's 32-bit words otherwise:            */
+/*   wire16 chunk: narrow a,b (CPU pool) -> H2D 2x2 B/word -> u16 kernel -> D2H 2 B/word   */
+/*                 -> widen into c (CPU pool)                                             */
+/*   wire32 chunk: H2D straight from the caller's buffers -> kernel -> D2H straight into c */
+/* Measured on the GPU box (16 host cores, c2): 32-bit wire 22.2 M         */
+/* polymul/s, 16-bit wire 29.5 M -- the host's memory system (narrowing reads 2n words per     */
+/* product at ~90 GB/s) is then what binds, not the link.  Two variants are kept behind knobs  */
+/* because they measured slower on that box: NTTB200_WIRE_AHEAD=k sends a chunk as 32-bit      */
+/* words when the pool is already k chunks behind (27.4 M at k=2); NTTB200_WIRE_C32=1 lets the */
+/* kernel write int32 result rows that one D2H copies straight into a pinned c, sparing the    */
+/* pool the widening (26.8 M: the extra upstream traffic slows the H2D reads).  Pageable       */
+/* caller buffers always go wire16: the pool is a faster stager than the driver's pageable     */
+/* path.  A chunk in which some word does not fit 16 bits is re-sent wire32, so results never  */
+/* depend on the wire.  NTTB200_WIRE=32|16|auto, NTTB200_WIRE_KWORDS (chunk),                  */
+/* NTTB200_WIRE_SLOTS are tuning knobs.                                                        */
+/* ------------------------------------------------------------------------------------ */
+enum { WS_FREE = 0, WS_NARROWING = 1, WS_INFLIGHT = 2, WS_WIDENING = 3 };
+
+static int wire_mode() {                               /* read per call: tests switch it */
+  const char *e = getenv("NTTB200_WIRE");
+  return (e && !strcmp(e, "32")) ? 32 : (e && !strcmp(e, "16")) ? 16 : 0;
+}
+
+static int ensure_wire_slots(nttb200_plan *P) {
+  if (!P->wslots.empty()) return 0;
+  const size_t words = (size_t)env_int("NTTB200_WIRE_KWORDS", 1024, 16, 65536) << 10;   /* per operand */
+  P->wire_polys = std::max<size_t>(1, words / P->n);
+  const size_t w = P->wire_polys * P->n;
+  P->wslots.resize(env_int("NTTB200_WIRE_SLOTS", 6, 2, 16));
+  for (auto &s : P->wslots) {
+    NTT_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    NTT_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    NTT_CUDA(cudaMalloc(&s.d_a, w * sizeof(uint32_t)));
+    NTT_CUDA(cudaMalloc(&s.d_b, w * sizeof(uint32_t)));
+    NTT_CUDA(cudaMalloc(&s.d_c, w * sizeof(uint32_t)));
+    void *h = nullptr;
+    NTT_CUDA(cudaHostAlloc(&h, 3 * w * sizeof(uint16_t), cudaHostAllocPortable));
+    s.h_a = (uint16_t *)h;
+    s.h_b = s.h_a + w;
+    s.h_c = s.h_b + w;
+  }
+  return 0;
+}
+
+static bool is_pinned(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+static int wire_send32(nttb200_plan *P, WireSlot &s, int32_t *c, const int32_t *a, const int32_t *b) {
+  const size_t n = P->n, bytes = s.rows * n * sizeof(uint32_t);
+  NTT_CUDA(cudaMemcpyAsync(s.d_a, a + s.row0 * n, bytes, cudaMemcpyHostToDevice, s.stream));
+  NTT_CUDA(cudaMemcpyAsync(s.d_b, b + s.row0 * n, bytes, cudaMemcpyHostToDevice, s.stream));
+  int rc = launch_polymul_small(P, s.d_c, s.d_a, s.d_b, s.rows, s.stream);
+  if (rc) return rc;
+  NTT_CUDA(cudaMemcpyAsync(c + s.row0 * n, s.d_c, bytes, cudaMemcpyDeviceToHost, s.stream));
+  NTT_CUDA(cudaEventRecord(s.done, s.stream));
+  s.wide = 1;
+  s.state = WS_INFLIGHT;
+  P->wire32_chunks += s.rows;
+  return 0;
+}
+/* 16-bit operands; the result comes back either as the caller's int32 rows written by the
+ * kernel's own 32-bit stores and one D2H straight into c (c pinned: the D2H direction of the link
+ * is otherwise half idle, and the host pool is spared the widening), or as 16-bit rows into
+ * pinned staging that the pool widens (c pageable) */
+static int wire_send16(nttb200_plan *P, WireSlot &s, int32_t *c, bool c_direct) {
+  const size_t n = P->n, bytes = s.rows * n * sizeof(uint16_t);
+  NTT_CUDA(cudaMemcpyAsync(s.d_a, s.h_a, bytes, cudaMemcpyHostToDevice, s.stream));
+  NTT_CUDA(cudaMemcpyAsync(s.d_b, s.h_b, bytes, cudaMemcpyHostToDevice, s.stream));
+  int rc;
+  if (c_direct) {
+    rc = launch_polymul_small_plant_u16in(P, s.d_c, (const uint16_t *)s.d_a, (const uint16_t *)s.d_b, s.rows,
+                                          s.stream);
+    if (rc) return rc;
+    NTT_CUDA(cudaMemcpyAsync(c + s.row0 * n, s.d_c, 2 * bytes, cudaMemcpyDeviceToHost, s.stream));
+  } else {
+    rc = launch_polymul_small_plant_u16(P, (uint16_t *)s.d_c, (const uint16_t *)s.d_a, (const uint16_t *)s.d_b,
+                                        s.rows, s.stream);
+    if (rc) return rc;
+    NTT_CUDA(cudaMemcpyAsync(s.h_c, s.d_c, bytes, cudaMemcpyDeviceToHost, s.stream));
+  }
+  NTT_CUDA(cudaEventRecord(s.done, s.stream));
+  s.wide = c_direct ? 2 : 0;                          /* 2: narrow in, nothing to widen */
+  s.state = WS_INFLIGHT;
+  P->wire16_chunks += s.rows;
+  if (c_direct) P->wire_c32_rows += s.rows;
+  return 0;
+}
+
+static int polymul_batch_wire(nttb200_plan *P, int32_t *c, const int32_t *a, const int32_t *b, size_t batch) {
+  int rc = ensure_wire_slots(P);
+  if (rc) return rc;
+  const size_t n = P->n;
+  const bool c_pinned = is_pinned(c);
+  const bool pinned = is_pinned(a) && is_pinned(b) && c_pinned;
+  const int mode = wire_mode();
+  const bool c_direct = c_pinned && env_int("NTTB200_WIRE_C32", 0, 0, 1) == 1;
+  const int ahead = env_int("NTTB200_WIRE_AHEAD", 99, 1, 99);
+  P->wire16_chunks = P->wire32_chunks = P->wire_c32_rows = 0;
+  uint32_t mask[16] = {0};                             /* per slot: OR of the words with high bits */
+  const size_t nsl = P->wslots.size();
+  size_t next = 0, busy = 0, chunk_no = 0;
+  const bool ramp = env_int("NTTB200_WIRE_RAMP", 1, 0, 1) != 0;
+  rc = 0;
+  nttb200_wire_begin();
+  while (next < batch || busy > 0) {
+    bool progress = false;
+    int narrowing = 0;
+    for (size_t i = 0; i < nsl && !rc; i++) {
+      WireSlot &s = P->wslots[i];
+      if (s.state == WS_NARROWING) {
+        if (nttb200_wire_done(s.job_a) && nttb200_wire_done(s.job_b)) {
+          rc = (mask[i] & 0xffff0000u) ? wire_send32(P, s, c, a, b) : wire_send16(P, s, c, c_direct);
+          progress = true;
+        } else {
+          narrowing++;
+        }
+      } else if (s.state == WS_INFLIGHT) {
+        const cudaError_t e = cudaEventQuery(s.done);
+        if (e == cudaSuccess) {
+          if (s.wide) {
+            s.state = WS_FREE;
+            busy--;
+          } else {
+            s.job_c = nttb200_wire_post_widen(c + s.row0 * n, s.h_c, s.rows * n);
+            s.state = WS_WIDENING;
+          }
+          progress = true;
+        } else if (e != cudaErrorNotReady) {
+          rc = nttb200_fail(NTTB200_ECUDA, "wire pipeline: %s", cudaGetErrorString(e));
+        }
+      } else if (s.state == WS_WIDENING) {
+        if (nttb200_wire_done(s.job_c)) {
+          s.state = WS_FREE;
+          busy--;
+          progress = true;
+        }
+      }
+    }
+    if (rc) break;
+    if (next < batch) {
+      for (size_t i = 0; i < nsl; i++) {
+        WireSlot &s = P->wslots[i];
+        if (s.state != WS_FREE) continue;
+        /* taper the last chunks so that the drain (one kernel + D2H + widen) is short */
+        const size_t left = batch - next;
+        size_t nb = std::min(P->wire_polys, left);
+        /* ... and ramp the first ones up (1/8, 1/4, 1/2 of a slot) so that the link starts early */
+        if (ramp && chunk_no < 3) nb = std::min(nb, std::max<size_t>(P->wire_polys >> (3 - chunk_no), 64));
+        if (left <= P->wire_polys && left > 64) nb = std::min(nb, std::max<size_t>(left / 2, 64));
+        chunk_no++;
+        s.row0 = next;
+        s.rows = nb;
+        next += nb;
+        busy++;
+        const bool wide = mode == 32 || (mode == 0 && pinned && narrowing >= ahead);
+        if (wide) {
+          rc = wire_send32(P, s, c, a, b);
+        } else {
+          mask[i] = 0;
+          s.job_a = nttb200_wire_post_narrow(s.h_a, a + s.row0 * n, nb * n, &mask[i]);
+          s.job_b = nttb200_wire_post_narrow(s.h_b, b + s.row0 * n, nb * n, &mask[i]);
+          s.state = WS_NARROWING;
+        }
+        progress = true;
+        break;
+      }
+      if (rc) break;
+    }
+    if (!progress) nttb200_wire_help();
+  }
+  if (rc) {                                            /* leave no job or copy behind */
+    for (auto &s : P->wslots) {
+      if (s.state == WS_NARROWING) { nttb200_wire_wait(s.job_a); nttb200_wire_wait(s.job_b); }
+      if (s.state == WS_WIDENING) nttb200_wire_wait(s.job_c);
+      cudaStreamSynchronize(s.stream);
+      s.state = WS_FREE;
+    }
+  }
+  nttb200_wire_end();
+  return rc;
+}
+
+extern "C" int nttb200_plan_wire_stats(const nttb200_plan *P, unsigned long long *rows16,
+                                       unsigned long long *rows32, unsigned long long *rows_c16,
+                                       int *host_threads) {
+  if (!P) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
+  if (rows16) *rows16 = P->wire16_chunks;
+  if (rows32) *rows32 = P->wire32_chunks;
+  if (rows_c16) *rows_c16 = P->wire16_chunks - P->wire_c32_rows;
+  if (host_threads) *host_threads = P->wslots.empty() ? 0 : nttb200_wire_threads();
+  return 0;
+}
+
 extern "C" int nttb200_polymul_batch(nttb200_plan *P, int32_t *c, const int32_t *a, const int32_t *b,
                                      size_t batch) {
   if (!P || !c || !a || !b) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
@@ -514,6 +722,7 @@ extern "C" int nttb200_polymul_batch(nttb200_plan *P, int32_t *c, const int32_t 
   int rc = ensure_slots(P, true);
   if (rc) return rc;
   const size_t n = P->n;
+  P->wire16_chunks = P->wire32_chunks = P->wire_c32_rows = 0;
   /* Small calls (the reference's one-polynomial-per-call convention, nttb200_legacy.h): no DMA
    * at all -- operands are copied into a mapped pinned buffer that the kernel reads over PCIe
    * directly, and it writes c straight back into host memory: one launch + one sync. */
@@ -529,6 +738,7 @@ extern "C" int nttb200_polymul_batch(nttb200_plan *P, int32_t *c, const int32_t 
     memcpy(c, hc, bytes);
     return 0;
   }
+  if (P->plant && wire_mode() != 32 && batch * n >= WIRE_MIN_WORDS) return polymul_batch_wire(P, c, a, b, batch);
   size_t k = 0;
   for (size_t done = 0, nb = 0; done < batch; done += nb, k++) {
     HostSlot &s = P->slots[k % NSLOT];

@@ -32,6 +32,17 @@ struct HostSlot {
   uint32_t *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;
 };
 
+/* slot of the 16/32-bit wire pipeline of nttb200_polymul_batch (half-word moduli) */
+struct WireSlot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  uint32_t *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;      /* device: words of either width   */
+  uint16_t *h_a = nullptr, *h_b = nullptr, *h_c = nullptr;      /* pinned staging, 16-bit rows     */
+  int state = 0, wide = 0;
+  size_t row0 = 0, rows = 0;
+  unsigned long long job_a = 0, job_b = 0, job_c = 0;
+};
+
 struct LargeLane {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
@@ -62,6 +73,9 @@ struct nttb200_plan {
   std::mutex mu;
   std::vector<HostSlot> slots;
   size_t slot_polys = 0;
+  std::vector<WireSlot> wslots;
+  size_t wire_polys = 0;           /* rows per wire chunk */
+  unsigned long long wire16_chunks = 0, wire32_chunks = 0, wire_c32_rows = 0;      /* rows sent on each wire by the last call */
 
   /* large-n: internal stream lanes, each with scratch for scratch_polys polynomials */
   uint32_t *scratch = nullptr;
@@ -109,3 +123,5 @@ int launch_ntt_small_plant(const nttb200_plan *P, const DevTable &tab, int dir, 
                            size_t batch, cudaStream_t st);
 int launch_polymul_small_plant_u16(const nttb200_plan *P, uint16_t *c, const uint16_t *a, const uint16_t *b,
                                    size_t batch, cudaStream_t st);
+int launch_polymul_small_plant_u16in(const nttb200_plan *P, uint32_t *c, const uint16_t *a, const uint16_t *b,
+                                     size_t batch, cudaStream_t st);

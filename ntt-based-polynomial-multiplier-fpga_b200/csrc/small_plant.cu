@@ -39,7 +39,7 @@ int plant_pdl() {
   return v;
 }
 
-template <int L, int MINB, typename IO = uint32_t>
+template <int L, int MINB, typename IO = uint32_t, typename OIO = IO>
 int run_plant(const nttb200_plan *P, void *c, const void *a, const void *b, size_t batch,
               cudaStream_t st) {
   using Gm = SmallGeom<L>;
@@ -62,7 +62,7 @@ int run_plant(const nttb200_plan *P, void *c, const void *a, const void *b, size
     p.ufwd[i] = (size_t)i < fwd.h1.size() ? fwd.h1[i] : 0;
     p.uinv[i] = (size_t)i < inv.h1.size() ? inv.h1[i] : 0;
   }
-  auto kernel = polymul_plant_kernel<L, Cfg::WARPS, MINB, Cfg::TWREG, IO>;
+  auto kernel = polymul_plant_kernel<L, Cfg::WARPS, MINB, Cfg::TWREG, IO, OIO>;
   const int smem = Cfg::WARPS * Pg::WARP_WORDS * (int)sizeof(uint32_t);
   int per_sm = 0;
   NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -126,6 +126,12 @@ int launch_polymul_small_plant(const nttb200_plan *P, uint32_t *c, const uint32_
 int launch_polymul_small_plant_u16(const nttb200_plan *P, uint16_t *c, const uint16_t *a, const uint16_t *b,
                                    size_t batch, cudaStream_t st) {
   PLANT_SWITCH(return (run_plant<L, 2, uint16_t>(P, c, a, b, batch, st)))
+}
+/* 16-bit operands, 32-bit result: the wire pipeline of the host-buffer call narrows a and b on
+ * the host and lets the kernel write the caller's int32 rows (nttb200.cu, polymul_batch_wire) */
+int launch_polymul_small_plant_u16in(const nttb200_plan *P, uint32_t *c, const uint16_t *a, const uint16_t *b,
+                                     size_t batch, cudaStream_t st) {
+  PLANT_SWITCH(return (run_plant<L, 2, uint16_t, uint32_t>(P, c, a, b, batch, st)))
 }
 template <int L, int DIR>
 int run_ntt_plant(const nttb200_plan *P, const DevTable &tab, int scale, uint32_t *a, size_t batch,

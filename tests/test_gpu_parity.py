@@ -602,3 +602,72 @@ def test_large_n_calls_on_two_streams_share_the_scratch_safely(gpu, oracle):
         want = oracle.product(n, q, u[idx].cpu().numpy(), v[idx].cpu().numpy(), 10)
         assert (o[idx].cpu().numpy() == want).all()
     p.close()
+
+
+@pytest.mark.parametrize("n,q,batch", [(256, 12289, 2048), (256, 12289, 20011), (256, 7681, 9000),
+                                       (1024, 12289, 3001), (64, 257, 40000)])
+def test_host_buffer_wire_formats_give_the_same_products(gpu, oracle, n, q, batch, monkeypatch):
+    """nttb200_polymul_batch on half-word moduli: chunks cross PCIe as 16-bit or 32-bit words
+    (csrc/hostwire.c, polymul_batch_wire).  Every mode -- forced 16, forced 32, automatic mix,
+    pageable and pinned buffers -- must return the reference products, and the statistics must
+    show which wire was used."""
+    p = gpu.Plan(n, q)
+    a, b = oracle.random((batch, n), q, SEED + batch), oracle.random((batch, n), q, SEED + 3 * batch)
+    a[0], b[0], a[-1], b[-1] = q - 1, q - 1, q - 1, 1
+    idx = np.unique(np.r_[0:40, batch - 40:batch, np.random.default_rng(batch).integers(0, batch, 300)])
+    want = oracle.product(n, q, a[idx], b[idx], 10)
+    ref = None
+    for mode in ("32", "16", "auto"):
+        monkeypatch.setenv("NTTB200_WIRE", mode)
+        got = p.polymul(a, b)                               # pageable numpy buffers
+        st = p.wire_stats()
+        assert (got[idx] == want).all(), mode
+        if mode == "32":
+            assert st["rows16"] == 0
+            ref = got
+        else:
+            assert st["rows16"] == batch and st["rows32"] == 0, st      # pageable: always narrowed
+            assert st["result_rows16"] == batch, st                     # ... and widened by the pool
+            assert (got == ref).all(), mode
+    ha, hb, hc = (gpu.host_alloc((batch, n)) for _ in range(3))
+    ha.array[:], hb.array[:] = a, b
+    for mode in ("16", "auto"):
+        monkeypatch.setenv("NTTB200_WIRE", mode)
+        hc.array[:] = -1
+        p.polymul_host_ptr(hc.ptr, ha.ptr, hb.ptr, batch)
+        st = p.wire_stats()
+        assert (hc.array == ref).all(), mode
+        assert st["result_rows16"] == st["rows16"], st         # widened by the pool ...
+        monkeypatch.setenv("NTTB200_WIRE_C32", "1")            # ... or int32 rows written by the kernel
+        monkeypatch.setenv("NTTB200_WIRE_AHEAD", "1")          # and chunks as 32-bit words when the pool lags
+        hc.array[:] = -1
+        p.polymul_host_ptr(hc.ptr, ha.ptr, hb.ptr, batch)
+        st = p.wire_stats()
+        assert (hc.array == ref).all() and st["result_rows16"] == 0 and st["rows16"] + st["rows32"] == batch, (mode, st)
+        monkeypatch.delenv("NTTB200_WIRE_C32")
+        monkeypatch.delenv("NTTB200_WIRE_AHEAD")
+        assert st["rows16"] + st["rows32"] == batch and (mode == "auto" or st["rows32"] == 0), st
+    for h in (ha, hb, hc):
+        h.free()
+    p.close()
+
+
+def test_words_that_do_not_fit_16_bits_travel_as_32_bit_words(gpu, oracle, monkeypatch):
+    """Out-of-contract inputs (a word >= 2^16, a negative word) must give exactly what the 32-bit
+    wire gives: the chunk that holds them is re-sent as 32-bit words."""
+    n, q, batch = 256, 12289, 12000
+    p = gpu.Plan(n, q)
+    a, b = oracle.random((batch, n), q, 11), oracle.random((batch, n), q, 12)
+    a[5000, 17] += 8 * q                                    # 8q + x >= 2^16: a lazy representative
+    b[11999, 255] = -1
+    monkeypatch.setenv("NTTB200_WIRE", "32")
+    ref = p.polymul(a, b)
+    for mode in ("16", "auto"):
+        monkeypatch.setenv("NTTB200_WIRE", mode)
+        got = p.polymul(a, b)
+        st = p.wire_stats()
+        assert (got == ref).all()
+        assert st["rows32"] >= 2 and st["rows16"] >= 1 and st["rows16"] + st["rows32"] == batch, st
+    rows = np.r_[0:8, 4990:5000, 5001:5010]
+    assert (ref[rows] == oracle.product(n, q, a[rows], b[rows], 10)).all()
+    p.close()
