@@ -295,6 +295,9 @@ def main() -> int:
     dev = torch.device("cuda", local)
     if world > 1:
         sh.init_distributed("nccl")
+    # the ranks of one box share its host cores: split them between the per-process pools that
+    # narrow / widen the rows of the host-buffer call (csrc/hostwire.c)
+    os.environ.setdefault("NTTB200_HOST_THREADS", str(max(1, host_cores() // max(1, world))))
     warmup = max(3, args.warmup)
 
     cyclic = (q - 1) % (2 * n) != 0                  # q=3329, n=256: no 512-th root of unity
