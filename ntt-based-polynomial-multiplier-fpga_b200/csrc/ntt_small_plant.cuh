@@ -314,8 +314,11 @@ __device__ __forceinline__ void plant_prefetch(IO *pa, IO *pb, const IO *ga, con
 /* =====================================================================================
  * Fused product kernel, half-word moduli.
  * ===================================================================================== */
+#ifndef PLANT_MINB_SCALE
+#define PLANT_MINB_SCALE 1   /* with PLANT_WARPS=4: 2 keeps 16 warps per SM as 4 CTAs (tuning experiment) */
+#endif
 template <int L, int WARPS, int MINB, bool TWREG, typename IO = uint32_t, typename OIO = IO>
-__global__ void __launch_bounds__(WARPS * 32, MINB)
+__global__ void __launch_bounds__(WARPS * 32, (L <= 8) ? MINB * PLANT_MINB_SCALE : MINB)
 polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
   using Gm = SmallGeom<L>;
   using Pg = PlantGeom<L, IO>;
