@@ -465,7 +465,7 @@ def main() -> int:
                          "note": "peak = independent IMAD chains on every SM, measured live "
                                  "(nttb200_measure_int_peak); IMAD.HI measured at half that rate so it "
                                  "counts 2 slots. Shoup kernels: butterfly 4, pointwise 6, n^-1 scale 4 per "
-                                 "pair; Plantard kernel (q<=12385): butterfly 3, pointwise 4, scale 3",
+                                 "pair; Plantard kernel (q<=12385): butterfly 3, pointwise 4, scale 3 (at n<=256 every other butterfly runs a 2-slot + 2-ALU form, but ptxas moves as many additions onto the multiplier pipe, so the executed slots are the same)",
                          "arith": "plantard" if plantard else "shoup"},
         "parity_ok": parity_ok,
         "standalone_ntt": ntt_lines,

@@ -86,6 +86,43 @@ __device__ __forceinline__ uint32_t plant_mul(uint32_t y, uint32_t wt, uint32_t 
 #endif
   return t;
 }
+/* Variant B of the same multiplication: only the UPPER HALF of p = Y w~ mod 2^32 meets q,
+ *        T = ((p >> 16) + 1) q >> 16          (IMAD, SHF, IMAD, SHF)
+ * [(p>>16 + 1) q 2^16 = p q + (2^16 - p_lo) q, so the quotient by 2^32 is the same k as above
+ *  whenever Y W + 2^16 q < 2^32: every Y < 22 q for q <= 12385; tests/test_plantard_arith.py.]
+ * Two multiplier slots and two ALU instructions instead of three multiplier slots: PLANT_B_NUM
+ * of every PLANT_B_DEN butterflies use B, to move work from the multiplier (fmaheavy) pipe to
+ * the ALU pipe, which has room.  What that buys is small -- ptxas answers the extra ALU
+ * instructions by turning more of the butterfly additions into IMAD.IADD, so the multiplier
+ * slots per tile barely move (SASS counts in DESIGN.md section 4): measured +0.9 % (c2) and
+ * +1.3 % (c3) at 1/2, -6 % at n = 1024 where the longer code misses the instruction cache
+ * more, hence n <= 256 only. */
+#ifndef PLANT_B_NUM
+#define PLANT_B_NUM 1
+#endif
+#ifndef PLANT_B_DEN
+#define PLANT_B_DEN 2
+#endif
+#ifndef PLANT_B_MAXL
+#define PLANT_B_MAXL 8
+#endif
+constexpr int PLANT_B_LIMB = 22;
+__host__ __device__ constexpr bool pl_use_b(int L, int i) {
+  return PLANT_B_NUM > 0 && L <= PLANT_B_MAXL && (i % PLANT_B_DEN) < PLANT_B_NUM;
+}
+/* ordinal of the butterfly whose lower leg is register r at register bit `bit` */
+__host__ __device__ constexpr int pl_ord(int r, int bit) { return ((r >> (bit + 1)) << bit) | (r & ((1 << bit) - 1)); }
+__device__ __forceinline__ uint32_t plant_mul_b(uint32_t y, uint32_t wt, uint32_t q) {
+  const uint32_t p = y * wt;
+  uint32_t t = ((p >> 16) * q + q) >> 16;
+#if PLANT_OPAQUE
+  asm("" : "+r"(t));
+#endif
+  return t;
+}
+__device__ __forceinline__ uint32_t plant_mul_v(bool vb, uint32_t y, uint32_t wt, uint32_t q) {
+  return vb ? plant_mul_b(y, wt, q) : plant_mul(y, wt, q);
+}
 /* a + b as a THREE-input add (z is a kernel parameter that is always 0): ptxas turns plain
  * two-input adds into IMAD.IADD to "balance" the pipes, but the fmaheavy pipe is the one
  * that binds this kernel; a three-input add can only be an ALU-pipe IADD3 */
@@ -172,27 +209,30 @@ struct LaneTw1 {
 };
 
 /* CT butterfly: T = Y w mod q in [0,q); X' = X + T, Y' = X - T + q  (bounds grow by 1) */
-__device__ __forceinline__ void pl_ct(uint32_t &X, uint32_t &Y, uint32_t wt, uint32_t q, uint32_t z) {
-  const uint32_t T = plant_mul(Y, wt, q);
+__device__ __forceinline__ void pl_ct(uint32_t &X, uint32_t &Y, uint32_t wt, uint32_t q, uint32_t z,
+                                      bool vb = false) {
+  const uint32_t T = plant_mul_v(vb, Y, wt, q);
   Y = X - T + q;
   X = add_alu(X, T, z);
 }
 /* GS butterfly on two legs < b q: X' = X + Y (capped), Y' = (X - Y) w mod q in [0,q) */
 template <int B, typename PT>
-__device__ __forceinline__ void pl_gs(uint32_t &X, uint32_t &Y, uint32_t wt, const PT &P) {
+__device__ __forceinline__ void pl_gs(uint32_t &X, uint32_t &Y, uint32_t wt, const PT &P, bool vb) {
+  static_assert(2 * B <= PLANT_B_LIMB, "d = X - Y + B q < 2 B q must stay inside variant B's range");
   const uint32_t d = X - Y + P.qmul[B];
   uint32_t s = add_alu(X, Y, P.zero);
   if (2 * B > PLANT_CAP) s = csub(s, P.qmul[PLANT_CAP]);
   X = s;
-  Y = plant_mul(d, wt, P.q);
+  Y = plant_mul_v(vb, d, wt, P.q);
 }
 template <typename PT>
-__device__ __forceinline__ void pl_gs_b(int b, uint32_t &X, uint32_t &Y, uint32_t wt, const PT &P) {
+__device__ __forceinline__ void pl_gs_b(int b, uint32_t &X, uint32_t &Y, uint32_t wt, const PT &P,
+                                        bool vb = false) {
   switch (b) {                                     /* b is a compile-time constant after unrolling */
-    case 1: pl_gs<1>(X, Y, wt, P); break;
-    case 2: pl_gs<2>(X, Y, wt, P); break;
-    case 4: pl_gs<4>(X, Y, wt, P); break;
-    default: pl_gs<8>(X, Y, wt, P); break;
+    case 1: pl_gs<1>(X, Y, wt, P, vb); break;
+    case 2: pl_gs<2>(X, Y, wt, P, vb); break;
+    case 4: pl_gs<4>(X, Y, wt, P, vb); break;
+    default: pl_gs<8>(X, Y, wt, P, vb); break;
   }
 }
 
@@ -200,13 +240,14 @@ template <int L>
 __device__ __forceinline__ void pl_fwd_cols(uint32_t (&x)[SmallGeom<L>::NV],
                                             const PlantParams<SmallGeom<L>::R> &P) {
   using Gm = SmallGeom<L>;
+  static_assert(L + 1 <= PLANT_B_LIMB, "forward values < (L+1) q must stay inside variant B's range");
 #pragma unroll
   for (int s = 0; s < Gm::R; s++) {
     const int kb = Gm::R - 1 - s;
 #pragma unroll
     for (int k = 0; k < Gm::NV; k++) {
       if (k & (1 << kb)) continue;
-      pl_ct(x[k], x[k | (1 << kb)], P.ufwd[(1 << s) + (k >> (kb + 1))], P.q, P.zero);
+      pl_ct(x[k], x[k | (1 << kb)], P.ufwd[(1 << s) + (k >> (kb + 1))], P.q, P.zero, pl_use_b(L, pl_ord(k, kb) + s));
     }
   }
 }
@@ -222,7 +263,7 @@ __device__ __forceinline__ void pl_fwd_rows(uint32_t (&x)[SmallGeom<L>::NV], con
       if (r & (1 << bit)) continue;
       const int g = r >> Gm::H;
       const int u = (r & (Gm::T - 1)) >> (bit + 1);
-      pl_ct(x[r], x[r | (1 << bit)], tw.get(g, lv, u), P.q, P.zero);
+      pl_ct(x[r], x[r | (1 << bit)], tw.get(g, lv, u), P.q, P.zero, pl_use_b(L, pl_ord(r, bit) + lv + 1));
     }
   }
 }
@@ -239,7 +280,8 @@ __device__ __forceinline__ void pl_inv_rows(uint32_t (&x)[SmallGeom<L>::NV], con
       if (r & (1 << bit)) continue;
       const int g = r >> Gm::H;
       const int u = (r & (Gm::T - 1)) >> (bit + 1);
-      pl_gs_b(pl_gs_bound(r & (Gm::T - 1), bit, 1), x[r], x[r | (1 << bit)], tw.get(g, lv, u), P);
+      pl_gs_b(pl_gs_bound(r & (Gm::T - 1), bit, 1), x[r], x[r | (1 << bit)], tw.get(g, lv, u), P,
+              pl_use_b(L, pl_ord(r, bit) + bit + 2));
     }
   }
 }
@@ -258,12 +300,12 @@ __device__ __forceinline__ void pl_inv_cols(uint32_t (&x)[SmallGeom<L>::NV],
       const int k2 = k | (1 << kb);
       const int b = pl_gs_bound(k, kb, B_IN);
       if (kb < Gm::R - 1) {
-        pl_gs_b(b, x[k], x[k2], P.uinv[t + (k >> (kb + 1))], P);
+        pl_gs_b(b, x[k], x[k2], P.uinv[t + (k >> (kb + 1))], P, pl_use_b(L, pl_ord(k, kb) + kb));
       } else {
         const uint32_t d = x[k] - x[k2] + P.qmul[b];
         const uint32_t s = add_alu(x[k], x[k2], P.zero);
-        x[k2] = plant_mul(d, P.last_y, P.q);
-        x[k] = plant_mul(s, P.last_x, P.q);
+        x[k2] = plant_mul_v(pl_use_b(L, 2 * pl_ord(k, kb)), d, P.last_y, P.q);
+        x[k] = plant_mul_v(pl_use_b(L, 2 * pl_ord(k, kb) + 1), s, P.last_x, P.q);
       }
     }
   }

@@ -43,6 +43,29 @@ def test_plantard_constant_multiplication_is_canonical_up_to_28q(q):
     assert (T == (Y * Wc) % np.uint64(q)).all()
 
 
+@pytest.mark.parametrize("q", [17, 97, 257, 3329, 7681, 12289, 12373, 12385])
+def test_plantard_half_word_second_product_is_canonical_up_to_22q(q):
+    """Variant B of the constant multiplication: only the upper half of p = Y w~ mod 2^32 meets q,
+    T = ((p >> 16) + 1) q >> 16  (IMAD, SHF, IMAD, SHF: 2 multiplier slots instead of 3),
+    == Y w mod q, canonical, whenever Y q + 2^16 q <= 2^32 -- every Y < 22 q for q <= 12385."""
+    qinv = qinv32(q)
+    assert 22 * q * q + (q << 16) <= 1 << 32
+    rng = np.random.default_rng(q + 5)
+    ws = np.arange(q, dtype=np.uint64) if q <= 3329 else np.unique(
+        np.concatenate([rng.integers(0, q, 2000), [0, 1, 2, q - 1, q - 2, q // 2]])).astype(np.uint64)
+    wt = np.array([plant_form(int(w), q, qinv) for w in ws], dtype=np.uint64)
+    ys = np.unique(np.concatenate([rng.integers(0, 22 * q, 3000), np.arange(0, 40),
+                                   22 * q - 1 - np.arange(0, 40), q * np.arange(1, 22), q * np.arange(1, 23) - 1]))
+    ys = ys.astype(np.uint64)
+    Y, WT = np.meshgrid(ys, wt, indexing="ij")
+    _, Wc = np.meshgrid(ys, ws, indexing="ij")
+    p = (Y * WT) & np.uint64(M32)                                   # IMAD (low 32 bits)
+    t = ((p >> np.uint64(16)) * np.uint64(q) + np.uint64(q))        # IMAD on the upper half, + q
+    assert (t < (1 << 32)).all()
+    T = t >> np.uint64(16)
+    assert (T == (Y * Wc) % np.uint64(q)).all()
+
+
 @pytest.mark.parametrize("q", [3329, 7681, 12289])
 def test_plantard_pointwise_product(q):
     qinv = qinv32(q)
