@@ -44,6 +44,9 @@ namespace nttb200 {
 #ifndef PLANT_ADD3
 #define PLANT_ADD3 0
 #endif
+#ifndef PLANT_QREG
+#define PLANT_QREG 1   /* which constants live in ordinary registers, see PlRegs */
+#endif
 constexpr int PLANT_LIMB = 28;
 constexpr uint32_t PLANT_QMAX = 12385;     /* 28 * q * q < 2^32 */
 
@@ -63,6 +66,37 @@ struct PlantParams {
   uint32_t ufwd[1 << R];     /* entries [1, 2^R) of the forward level table (w~)          */
   uint32_t uinv[1 << R];
 };
+
+/* Constants that the butterflies read most often, held in ordinary registers.  ptxas keeps kernel
+ * parameters in UNIFORM registers (LDCU -> URx operands); measured on B200, the same kernel with q
+ * in an ordinary register instead runs 2.5 % faster (c2 1 159 -> 1 188 M polymul/s), so the hottest
+ * constants are copied once per thread through an addition with the always-zero parameter, which
+ * ptxas cannot fold back into a parameter read.  PLANT_QREG: 0 none, 1 q, 2 + q 2q 4q 8q,
+ * 3 + the twiddles of the first two forward stages, 4 + of the last inverse stages. */
+struct PlRegs {
+  uint32_t q, qinv;
+  uint32_t qm[4];            /* q, 2q, 4q, 8q                                   */
+  uint32_t tf[4], ti[4];     /* entries 1..3 of the forward / inverse level table */
+};
+template <typename PT>
+__device__ __forceinline__ PlRegs pl_regs(const PT &P) {
+  PlRegs r;
+  const uint32_t z = (PLANT_QREG >= 1) ? P.zero : 0u;
+  r.q = P.q + z;
+  r.qinv = P.qinv + ((PLANT_QREG >= 2) ? z : 0u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    r.qm[i] = P.qmul[1 << i] + z;
+    r.tf[i] = P.ufwd[i] + z;
+    r.ti[i] = P.uinv[i] + z;
+  }
+  return r;
+}
+template <typename PT>
+__device__ __forceinline__ uint32_t pl_qmul(int b, const PT &P, const PlRegs &G) {
+  if (PLANT_QREG >= 2 && (b == 1 || b == 2 || b == 4 || b == 8)) return G.qm[b == 1 ? 0 : b == 2 ? 1 : b == 4 ? 2 : 3];
+  return P.qmul[b];
+}
 
 /* floor(p q / 2^32).  Written as mul.wide + unpack rather than mul.hi: ptxas folds an add that
  * follows an IMAD.HI into its addend and, when the product has two such consumers (every
@@ -217,28 +251,28 @@ __device__ __forceinline__ void pl_ct(uint32_t &X, uint32_t &Y, uint32_t wt, uin
 }
 /* GS butterfly on two legs < b q: X' = X + Y (capped), Y' = (X - Y) w mod q in [0,q) */
 template <int B, typename PT>
-__device__ __forceinline__ void pl_gs(uint32_t &X, uint32_t &Y, uint32_t wt, const PT &P, bool vb) {
+__device__ __forceinline__ void pl_gs(uint32_t &X, uint32_t &Y, uint32_t wt, const PT &P, const PlRegs &G, bool vb) {
   static_assert(2 * B <= PLANT_B_LIMB, "d = X - Y + B q < 2 B q must stay inside variant B's range");
-  const uint32_t d = X - Y + P.qmul[B];
+  const uint32_t d = X - Y + pl_qmul(B, P, G);
   uint32_t s = add_alu(X, Y, P.zero);
-  if (2 * B > PLANT_CAP) s = csub(s, P.qmul[PLANT_CAP]);
+  if (2 * B > PLANT_CAP) s = csub(s, pl_qmul(PLANT_CAP, P, G));
   X = s;
-  Y = plant_mul_v(vb, d, wt, P.q);
+  Y = plant_mul_v(vb, d, wt, G.q);
 }
 template <typename PT>
 __device__ __forceinline__ void pl_gs_b(int b, uint32_t &X, uint32_t &Y, uint32_t wt, const PT &P,
-                                        bool vb = false) {
+                                        const PlRegs &G, bool vb = false) {
   switch (b) {                                     /* b is a compile-time constant after unrolling */
-    case 1: pl_gs<1>(X, Y, wt, P, vb); break;
-    case 2: pl_gs<2>(X, Y, wt, P, vb); break;
-    case 4: pl_gs<4>(X, Y, wt, P, vb); break;
-    default: pl_gs<8>(X, Y, wt, P, vb); break;
+    case 1: pl_gs<1>(X, Y, wt, P, G, vb); break;
+    case 2: pl_gs<2>(X, Y, wt, P, G, vb); break;
+    case 4: pl_gs<4>(X, Y, wt, P, G, vb); break;
+    default: pl_gs<8>(X, Y, wt, P, G, vb); break;
   }
 }
 
 template <int L>
 __device__ __forceinline__ void pl_fwd_cols(uint32_t (&x)[SmallGeom<L>::NV],
-                                            const PlantParams<SmallGeom<L>::R> &P) {
+                                            const PlantParams<SmallGeom<L>::R> &P, const PlRegs &G) {
   using Gm = SmallGeom<L>;
   static_assert(L + 1 <= PLANT_B_LIMB, "forward values < (L+1) q must stay inside variant B's range");
 #pragma unroll
@@ -247,13 +281,15 @@ __device__ __forceinline__ void pl_fwd_cols(uint32_t (&x)[SmallGeom<L>::NV],
 #pragma unroll
     for (int k = 0; k < Gm::NV; k++) {
       if (k & (1 << kb)) continue;
-      pl_ct(x[k], x[k | (1 << kb)], P.ufwd[(1 << s) + (k >> (kb + 1))], P.q, P.zero, pl_use_b(L, pl_ord(k, kb) + s));
+      const int ti = (1 << s) + (k >> (kb + 1));
+      pl_ct(x[k], x[k | (1 << kb)], (PLANT_QREG >= 3 && ti < 4) ? G.tf[ti] : P.ufwd[ti], G.q, P.zero,
+            pl_use_b(L, pl_ord(k, kb) + s));
     }
   }
 }
 template <int L>
 __device__ __forceinline__ void pl_fwd_rows(uint32_t (&x)[SmallGeom<L>::NV], const LaneTw1<L> &tw,
-                                            const PlantParams<SmallGeom<L>::R> &P) {
+                                            const PlantParams<SmallGeom<L>::R> &P, const PlRegs &G) {
   using Gm = SmallGeom<L>;
 #pragma unroll
   for (int lv = 0; lv < Gm::H; lv++) {
@@ -263,14 +299,14 @@ __device__ __forceinline__ void pl_fwd_rows(uint32_t (&x)[SmallGeom<L>::NV], con
       if (r & (1 << bit)) continue;
       const int g = r >> Gm::H;
       const int u = (r & (Gm::T - 1)) >> (bit + 1);
-      pl_ct(x[r], x[r | (1 << bit)], tw.get(g, lv, u), P.q, P.zero, pl_use_b(L, pl_ord(r, bit) + lv + 1));
+      pl_ct(x[r], x[r | (1 << bit)], tw.get(g, lv, u), G.q, P.zero, pl_use_b(L, pl_ord(r, bit) + lv + 1));
     }
   }
 }
 /* inverse, layout 2 (register bits 0..H-1 of r_lo; the g bit of r is not a history bit) */
 template <int L>
 __device__ __forceinline__ void pl_inv_rows(uint32_t (&x)[SmallGeom<L>::NV], const LaneTw1<L> &tw,
-                                            const PlantParams<SmallGeom<L>::R> &P) {
+                                            const PlantParams<SmallGeom<L>::R> &P, const PlRegs &G) {
   using Gm = SmallGeom<L>;
 #pragma unroll
   for (int bit = 0; bit < Gm::H; bit++) {
@@ -280,7 +316,7 @@ __device__ __forceinline__ void pl_inv_rows(uint32_t (&x)[SmallGeom<L>::NV], con
       if (r & (1 << bit)) continue;
       const int g = r >> Gm::H;
       const int u = (r & (Gm::T - 1)) >> (bit + 1);
-      pl_gs_b(pl_gs_bound(r & (Gm::T - 1), bit, 1), x[r], x[r | (1 << bit)], tw.get(g, lv, u), P,
+      pl_gs_b(pl_gs_bound(r & (Gm::T - 1), bit, 1), x[r], x[r | (1 << bit)], tw.get(g, lv, u), P, G,
               pl_use_b(L, pl_ord(r, bit) + bit + 2));
     }
   }
@@ -289,7 +325,7 @@ __device__ __forceinline__ void pl_inv_rows(uint32_t (&x)[SmallGeom<L>::NV], con
  * in), so the outputs are canonical */
 template <int L, int B_IN>
 __device__ __forceinline__ void pl_inv_cols(uint32_t (&x)[SmallGeom<L>::NV],
-                                            const PlantParams<SmallGeom<L>::R> &P) {
+                                            const PlantParams<SmallGeom<L>::R> &P, const PlRegs &G) {
   using Gm = SmallGeom<L>;
 #pragma unroll
   for (int kb = 0; kb < Gm::R; kb++) {
@@ -300,12 +336,14 @@ __device__ __forceinline__ void pl_inv_cols(uint32_t (&x)[SmallGeom<L>::NV],
       const int k2 = k | (1 << kb);
       const int b = pl_gs_bound(k, kb, B_IN);
       if (kb < Gm::R - 1) {
-        pl_gs_b(b, x[k], x[k2], P.uinv[t + (k >> (kb + 1))], P, pl_use_b(L, pl_ord(k, kb) + kb));
+        const int ti = t + (k >> (kb + 1));
+        pl_gs_b(b, x[k], x[k2], (PLANT_QREG >= 4 && ti < 4) ? G.ti[ti] : P.uinv[ti], P, G,
+                pl_use_b(L, pl_ord(k, kb) + kb));
       } else {
-        const uint32_t d = x[k] - x[k2] + P.qmul[b];
+        const uint32_t d = x[k] - x[k2] + pl_qmul(b, P, G);
         const uint32_t s = add_alu(x[k], x[k2], P.zero);
-        x[k2] = plant_mul_v(pl_use_b(L, 2 * pl_ord(k, kb)), d, P.last_y, P.q);
-        x[k] = plant_mul_v(pl_use_b(L, 2 * pl_ord(k, kb) + 1), s, P.last_x, P.q);
+        x[k2] = plant_mul_v(pl_use_b(L, 2 * pl_ord(k, kb)), d, P.last_y, G.q);
+        x[k] = plant_mul_v(pl_use_b(L, 2 * pl_ord(k, kb) + 1), s, P.last_x, G.q);
       }
     }
   }
@@ -375,7 +413,8 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
   uint32_t *sm_b = sm_a + Gm::PPW * Gm::STRIDE;
   const IO *ga = static_cast<const IO *>(P.a), *gb = static_cast<const IO *>(P.b);
   OIO *gc = static_cast<OIO *>(P.c);                  /* result rows may be wider than the operands */
-  const uint32_t q = P.q;
+  const PlRegs G = pl_regs(P);
+  const uint32_t q = G.q;
 
   const unsigned long long ntiles = (P.batch + Gm::PPW - 1) / Gm::PPW;
   const unsigned long long wstride = (unsigned long long)gridDim.x * WARPS;
@@ -411,8 +450,8 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
     __syncwarp();                                     /* prefetch buffers are free again */
     if (tile + wstride < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile + wstride, P.batch, lane);
 
-    pl_fwd_cols<L>(xa, P);
-    pl_fwd_cols<L>(xb, P);
+    pl_fwd_cols<L>(xa, P, G);
+    pl_fwd_cols<L>(xb, P, G);
     if (BULK && bulk_pending) {                       /* the previous tile's result row has left sm_a */
       if (l == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncwarp();
@@ -424,8 +463,8 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
       load_rows<L>(xa, sm_a, l);
       load_rows<L>(xb, sm_b, l);
       if (!TWREG) twf.load(P.tw_fwd, l);
-      pl_fwd_rows<L>(xa, twf, P);
-      pl_fwd_rows<L>(xb, twf, P);
+      pl_fwd_rows<L>(xa, twf, P, G);
+      pl_fwd_rows<L>(xb, twf, P, G);
     }
 
     /* pointwise product (mul_array, R/NTT/ntt.C:131-137) as a Plantard product of two
@@ -441,7 +480,7 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
       if (pw.nb > 0) bv = csub(bv, P.qmul[pw.hb[0]]);
       if (pw.nb > 1) bv = csub(bv, P.qmul[pw.hb[1]]);
       if (pw.nb > 2) bv = csub(bv, P.qmul[pw.hb[2]]);
-      uint32_t v = mulhi_nofold(av * bv * P.qinv, q);
+      uint32_t v = mulhi_nofold(av * bv * G.qinv, q);
 #if PLANT_OPAQUE
       asm("" : "+r"(v));
 #endif
@@ -450,13 +489,13 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
 
     if (Gm::H > 0) {
       if (!TWREG) twi.load(P.tw_inv, l);
-      pl_inv_rows<L>(xa, twi, P);
+      pl_inv_rows<L>(xa, twi, P, G);
       __syncwarp();                                   /* all lanes done reading sm_a */
       store_rows<L>(xa, sm_a, l);
       __syncwarp();
       load_cols<L>(xa, sm_a, l);
     }
-    pl_inv_cols<L, pl_gs_phase_out(Gm::H, 1)>(xa, P);
+    pl_inv_cols<L, pl_gs_phase_out(Gm::H, 1)>(xa, P, G);
     if (BULK) {
     /* result row -> shared memory in natural order -> ONE bulk (TMA) copy per polynomial:
      * cp.async.bulk.global.shared::cta, issued by the polynomial's first lane */
@@ -522,6 +561,7 @@ ntt_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
 
   LaneTw1<L> tw;
   tw.load(DIR == 0 ? P.tw_fwd : P.tw_inv, l);
+  const PlRegs G = pl_regs(P);
 
   const unsigned long long ntiles = (P.batch + Gm::PPW - 1) / Gm::PPW;
   const unsigned long long wstride = (unsigned long long)gridDim.x * WARPS;
@@ -552,12 +592,12 @@ ntt_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
       for (int k = 0; k < Gm::NV; k++) x[k] = pf[sub * Pg::PSTRIDE + (k << Gm::H) + l];
       __syncwarp();
       if (tile + wstride < ntiles) prefetch(tile + wstride);
-      pl_fwd_cols<L>(x, P);
+      pl_fwd_cols<L>(x, P, G);
       if (Gm::H > 0) {
         store_cols<L>(x, sm_a, l);
         __syncwarp();
         load_rows<L>(x, sm_a, l);
-        pl_fwd_rows<L>(x, tw, P);
+        pl_fwd_rows<L>(x, tw, P, G);
       }
 #pragma unroll
       for (int k = 0; k < Gm::NV; k++) x[k] = pl_canon<L + 1>(x[k], P);
@@ -566,12 +606,12 @@ ntt_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
     } else {
       gload_rows<L>(x, data + off, l);
       if (Gm::H > 0) {
-        pl_inv_rows<L>(x, tw, P);
+        pl_inv_rows<L>(x, tw, P, G);
         store_rows<L>(x, sm_a, l);
         __syncwarp();
         load_cols<L>(x, sm_a, l);
       }
-      pl_inv_cols<L, pl_gs_phase_out(Gm::H, 1)>(x, P);
+      pl_inv_cols<L, pl_gs_phase_out(Gm::H, 1)>(x, P, G);
       __syncwarp();
       if (live) gstore_cols<L>(x, data + off, l);
     }
