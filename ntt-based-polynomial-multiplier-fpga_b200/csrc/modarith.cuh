@@ -27,6 +27,28 @@ struct ModQ {
   uint32_t qinv;   /* q^-1 mod 2^32 (Montgomery)               */
 };
 
+/* The modulus constants arrive as kernel parameters, which ptxas keeps in UNIFORM registers
+ * (LDCU -> URx operands).  Measured on B200 with the Plantard kernel, the
+ * butterflies run faster when the constants they read on every instruction sit in ordinary
+ * registers: adding a parameter that is always 0 makes the copy one that ptxas cannot fold
+ * back into a parameter read.  NTT_MODQ_REGS=0 turns it off (tuning knob). */
+#ifndef NTT_MODQ_REGS
+#define NTT_MODQ_REGS 1
+#endif
+__device__ __forceinline__ ModQ modq_regs(const ModQ &m, uint32_t zero) {
+#if NTT_MODQ_REGS
+  ModQ r;
+  r.q = m.q + zero;
+  r.nq = m.nq + zero;
+  r.q2 = m.q2 + zero;
+  r.qinv = m.qinv + zero;
+  return r;
+#else
+  (void)zero;
+  return m;
+#endif
+}
+
 /* x * w mod q for a twiddle w with companion wp = floor(w 2^32 / q): any 32-bit x,
  * result in [0, 2q).  IMAD.HI + 2 IMAD. */
 __device__ __forceinline__ uint32_t shoup_mul(uint32_t x, uint32_t w, uint32_t wp, const ModQ &m) {

@@ -47,6 +47,7 @@ struct LargeParams {
   uint2 last_x;               /* K3: multiplier of the sum branch of the very last stage     */
   uint2 last_y;               /* K3: multiplier of its diff branch (twiddle p[1] * scale)    */
   uint2 one;                  /* (1, floor(2^32/q)): Shoup pair that only reduces            */
+  uint32_t zero;              /* always 0 (modq_regs)                                        */
 };
 
 constexpr int LARGE_LR = 8;       /* rows of 2^8 coefficients: fixed, so row strides are immediates */
@@ -93,7 +94,7 @@ large_cols_fwd_kernel(const __grid_constant__ LargeParams P) {
   const size_t base = ((size_t)poly << (K1 + lr)) + tile * 32 + lane;
   const uint32_t *src = P.src[op] + base;
   uint32_t *dst = P.dst[op] + base;
-  const ModQ m = P.m;
+  const ModQ m = modq_regs(P.m, P.zero);
 
   uint32_t x[G::NV];
   /* phase A: row bits K1-1 .. K1-RA are register bits; this warp's fixed low row bits = w */
@@ -180,7 +181,7 @@ large_cols_inv_kernel(const __grid_constant__ LargeParams P) {
   const size_t base = ((size_t)poly << (K1 + lr)) + tile * 32 + lane;
   const uint32_t *src = P.src[0] + base;
   uint32_t *dst = P.dst[0] + base;
-  const ModQ m = P.m;
+  const ModQ m = modq_regs(P.m, P.zero);
 
   uint32_t x[G::NV];
   if (G::RB > 0) {
@@ -296,7 +297,7 @@ large_rows_polymul_kernel(const __grid_constant__ LargeParams P) {
   const int l = lane % Gm::T;
   uint32_t *sm_a = smem + (warp * 2 * Gm::PPW + sub) * Gm::STRIDE;
   uint32_t *sm_b = sm_a + Gm::PPW * Gm::STRIDE;
-  const ModQ m = P.m;
+  const ModQ m = modq_regs(P.m, P.zero);
   const uint32_t k1 = P.logn - LR;
   const uint32_t j = blockIdx.x & ((1u << k1) - 1);
   const unsigned long long bg = blockIdx.x >> k1;
@@ -364,7 +365,7 @@ large_rows_ntt_kernel(const __grid_constant__ LargeParams P) {
   const int sub = lane / Gm::T;
   const int l = lane % Gm::T;
   uint32_t *sm_a = smem + (warp * Gm::PPW + sub) * Gm::STRIDE;
-  const ModQ m = P.m;
+  const ModQ m = modq_regs(P.m, P.zero);
   const uint32_t k1 = P.logn - LR;
   const uint32_t j = blockIdx.x & ((1u << k1) - 1);
   const unsigned long long bg = blockIdx.x >> k1;

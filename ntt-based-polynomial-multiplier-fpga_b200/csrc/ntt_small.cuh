@@ -52,6 +52,7 @@ struct SmallParams {
                               n^-1 * 2^32 (fused) / n^-1 (scaled intt) / unused          */
   uint2 last_y;            /* multiplier of the DIFF branch of the last inverse stage    */
   uint32_t flags;
+  uint32_t zero;           /* always 0 (modq_regs) */
   UniformTw<R> u;
 };
 
@@ -364,7 +365,7 @@ polymul_small_kernel(const __grid_constant__ SmallParams<SmallGeom<L>::R> P) {
   const int l = lane % Gm::T;              /* lane within the polynomial      */
   uint32_t *sm_a = smem + (warp * 2 * Gm::PPW + sub) * Gm::STRIDE;
   uint32_t *sm_b = sm_a + Gm::PPW * Gm::STRIDE;
-  const ModQ m = P.m;
+  const ModQ m = modq_regs(P.m, P.zero);
 
   LaneTw<L> twf, twi;
   if (TWREG) {
@@ -440,7 +441,7 @@ ntt_small_kernel(const __grid_constant__ SmallParams<SmallGeom<L>::R> P) {
   const int sub = lane / Gm::T;
   const int l = lane % Gm::T;
   uint32_t *sm_a = smem + (warp * Gm::PPW + sub) * Gm::STRIDE;
-  const ModQ m = P.m;
+  const ModQ m = modq_regs(P.m, P.zero);
   const uint32_t one_p = 0xFFFFFFFFu / m.q;          /* floor(2^32/q) for q not a power of 2 */
 
   LaneTw<L> tw;
