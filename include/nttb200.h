@@ -158,6 +158,7 @@ enum nttb200_transform {
   NTTB200_NTT_REV2STD = 7
 };
 int nttb200_ntt_batch(nttb200_plan *plan, int transform, int32_t *a, size_t batch);
+/* a_dev must be 16-byte aligned (NTTB200_EPARAM otherwise): rows move with 128-bit accesses */
 int nttb200_ntt_batch_dev(nttb200_plan *plan, int transform, int32_t *a_dev, size_t batch,
                           void *stream);
 

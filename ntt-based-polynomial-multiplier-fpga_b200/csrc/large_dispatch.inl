@@ -34,32 +34,50 @@ void fill_common(LargeParams &p, const nttb200_plan *P, const DevTable *fwd, con
   p.last_y = inv ? inv->h[1] : p.one;
 }
 
-template <int K1>
-int cols_fwd(const nttb200_plan *P, LargeParams &p, cudaStream_t st) {
-  using G = ColGeom<K1>;
-  auto kernel = large_cols_fwd_kernel<K1, LARGE_ARITH>;
+/* two columns per lane for the classes with cheap butterflies, when the rows are 8-byte aligned */
+constexpr int LARGE_CPL = (LARGE_ARITH == ARITH_CANON) ? 1 : 2;
+inline bool cols_aligned8(const LargeParams &p) {
+  uintptr_t v = 0;
+  for (int i = 0; i < 2; i++) v |= (uintptr_t)p.src[i] | (uintptr_t)p.dst[i];
+  return (v & 7u) == 0;
+}
+
+template <int K1, int CPL>
+int cols_fwd_cpl(const nttb200_plan *P, LargeParams &p, cudaStream_t st) {
+  using G = ColGeom<K1, CPL>;
+  auto kernel = large_cols_fwd_kernel<K1, LARGE_ARITH, CPL>;
   if (G::SMEM_BYTES > 48 * 1024)
     NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
-  const unsigned long long grid = p.batch * p.nops * (1ull << (P->logn - K1 - 5));
+  const unsigned long long grid = p.batch * p.nops * (1ull << (P->logn - K1 - G::LOG_TILE));
   if (grid > 0x7fffffffull) return nttb200_fail(NTTB200_EPARAM, "batch too large for one launch");
   kernel<<<(unsigned)grid, G::WARPS * 32, G::SMEM_BYTES, st>>>(p);
   nttb200_count_launch(1);
   NTT_CUDA(cudaGetLastError());
   return 0;
 }
-
 template <int K1>
-int cols_inv(const nttb200_plan *P, LargeParams &p, cudaStream_t st) {
-  using G = ColGeom<K1>;
-  auto kernel = large_cols_inv_kernel<K1, LARGE_ARITH>;
+int cols_fwd(const nttb200_plan *P, LargeParams &p, cudaStream_t st) {
+  if (LARGE_CPL == 2 && cols_aligned8(p)) return cols_fwd_cpl<K1, LARGE_CPL>(P, p, st);
+  return cols_fwd_cpl<K1, 1>(P, p, st);
+}
+
+template <int K1, int CPL>
+int cols_inv_cpl(const nttb200_plan *P, LargeParams &p, cudaStream_t st) {
+  using G = ColGeom<K1, CPL>;
+  auto kernel = large_cols_inv_kernel<K1, LARGE_ARITH, CPL>;
   if (G::SMEM_BYTES > 48 * 1024)
     NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
-  const unsigned long long grid = p.batch * (1ull << (P->logn - K1 - 5));
+  const unsigned long long grid = p.batch * (1ull << (P->logn - K1 - G::LOG_TILE));
   if (grid > 0x7fffffffull) return nttb200_fail(NTTB200_EPARAM, "batch too large for one launch");
   kernel<<<(unsigned)grid, G::WARPS * 32, G::SMEM_BYTES, st>>>(p);
   nttb200_count_launch(1);
   NTT_CUDA(cudaGetLastError());
   return 0;
+}
+template <int K1>
+int cols_inv(const nttb200_plan *P, LargeParams &p, cudaStream_t st) {
+  if (LARGE_CPL == 2 && cols_aligned8(p)) return cols_inv_cpl<K1, LARGE_CPL>(P, p, st);
+  return cols_inv_cpl<K1, 1>(P, p, st);
 }
 
 #define LARGE_K1_SWITCH(fn, ...)                                                   \

@@ -22,8 +22,8 @@
  * one); the scratch is small enough to stay in L2, but with a 31-bit modulus the passes are
  * instruction-bound, not memory-bound.
  *
- * Column pass: one CTA owns 32 adjacent columns (lanes = columns: every global access is a
- * 128-byte row segment) and all n1 rows; the K1 stages run as one or two register phases
+ * Column pass: one CTA owns 32 or 64 adjacent columns (one or two per lane: every global access
+ * is a 128- or 256-byte row segment) and all n1 rows; the K1 stages run as one or two register phases
  * (RA then RB stages) with one exchange through shared memory.  Twiddle reads are
  * warp-uniform (they depend on the row bits only).
  * Row pass: the register/shared-memory machinery of ntt_small.cuh, one row of one
@@ -52,16 +52,63 @@ struct LargeParams {
 
 constexpr int LARGE_LR = 8;       /* rows of 2^8 coefficients: fixed, so row strides are immediates */
 
-template <int K1>
+template <int K1, int CPL = 1>
 struct ColGeom {
   static constexpr int RA = (K1 <= 4) ? K1 : (K1 + 1) / 2;   /* stages of the phase on the high row bits */
   static constexpr int RB = K1 - RA;                          /* stages of the phase on the low row bits  */
-  static constexpr int NV = 1 << RA;                          /* coefficients per thread                   */
+  static constexpr int NV = 1 << RA;                          /* column vectors per thread                 */
   static constexpr int WARPS = 1 << RB;
   static constexpr int GB = 1 << (RA - RB);                   /* RB-groups per thread (RB > 0)             */
   static constexpr int ROWS = 1 << K1;
-  static constexpr int SMEM_BYTES = (RB > 0) ? ROWS * 32 * 4 : 0;
+  static constexpr int TILE_COLS = 32 * CPL;                  /* adjacent columns per CTA                  */
+  static constexpr int LOG_TILE = (CPL == 2) ? 6 : 5;
+  static constexpr int SMEM_BYTES = (RB > 0) ? ROWS * TILE_COLS * 4 : 0;
 };
+/* columns per lane: 1 (32-bit accesses, 128-byte row segments per warp) or 2 (64-bit accesses,
+ * 256-byte segments, half the load/store instructions; operands must be 8-byte aligned).
+ * Measured at n = 2^16: two columns per lane help the classes with cheap butterflies (HARVEY
+ * 1.55 -> 1.75 M polymul/s) and not CANON (1.51 -> 1.48 M), whose 8-instruction butterflies
+ * dominate; large_dispatch.inl picks per class. */
+template <int CPL> struct CVec { uint32_t v[CPL]; };
+template <int CPL>
+__device__ __forceinline__ CVec<CPL> cv_ldg(const uint32_t *p) {
+  CVec<CPL> r;
+  if (CPL == 1) {
+    r.v[0] = __ldg(p);
+  } else {
+    const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+    r.v[0] = t.x;
+    r.v[CPL - 1] = t.y;
+  }
+  return r;
+}
+template <int CPL>
+__device__ __forceinline__ CVec<CPL> cv_ld(const uint32_t *p) {
+  CVec<CPL> r;
+  if (CPL == 1) {
+    r.v[0] = *p;
+  } else {
+    const uint2 t = *reinterpret_cast<const uint2 *>(p);
+    r.v[0] = t.x;
+    r.v[CPL - 1] = t.y;
+  }
+  return r;
+}
+template <int CPL>
+__device__ __forceinline__ void cv_st(uint32_t *p, const CVec<CPL> &x) {
+  if (CPL == 1) *p = x.v[0];
+  else *reinterpret_cast<uint2 *>(p) = make_uint2(x.v[0], x.v[CPL - 1]);
+}
+template <int ARITH, int CPL>
+__device__ __forceinline__ void cv_ct(CVec<CPL> &X, CVec<CPL> &Y, uint2 tw, const ModQ &m) {
+#pragma unroll
+  for (int c = 0; c < CPL; c++) ct_bfly<ARITH>(X.v[c], Y.v[c], tw.x, tw.y, m);
+}
+template <int ARITH, int CPL>
+__device__ __forceinline__ void cv_gs(CVec<CPL> &X, CVec<CPL> &Y, uint2 tw, const ModQ &m, uint32_t yb) {
+#pragma unroll
+  for (int c = 0; c < CPL; c++) gs_bfly<ARITH>(X.v[c], Y.v[c], tw.x, tw.y, m, yb);
+}
 
 /* final reduction of a value produced by the forward column+row passes to [0, q) */
 template <int ARITH>
@@ -77,29 +124,31 @@ __device__ __forceinline__ uint32_t canon_fwd(uint32_t x, uint2 one, const ModQ 
  * Output range: LAZY < (2 K1 + 1) q, HARVEY [0,4q), CANON [0,q) -- the row pass continues
  * in the same class, so nothing is reduced here.
  * ===================================================================================== */
-template <int K1, int ARITH>
+template <int K1, int ARITH, int CPL>
 __global__ void __launch_bounds__(ColGeom<K1>::WARPS * 32)
 large_cols_fwd_kernel(const __grid_constant__ LargeParams P) {
-  using G = ColGeom<K1>;
+  using G = ColGeom<K1, CPL>;
+  using V = CVec<CPL>;
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
   constexpr int lr = LARGE_LR;                            /* log2 of the row length */
-  constexpr uint32_t tiles = 1u << (lr - 5);
+  constexpr int lt = lr - G::LOG_TILE;                    /* log2 of the tiles per row */
   const unsigned long long unit = blockIdx.x;
-  const uint32_t tile = (uint32_t)(unit & (tiles - 1));
-  const unsigned long long po = unit >> (lr - 5);
+  const uint32_t tile = (uint32_t)(unit & ((1u << lt) - 1));
+  const unsigned long long po = unit >> lt;
   const uint32_t op = (P.nops == 2) ? (uint32_t)(po & 1) : 0u;
   const unsigned long long poly = (P.nops == 2) ? (po >> 1) : po;
-  const size_t base = ((size_t)poly << (K1 + lr)) + tile * 32 + lane;
+  const size_t base = ((size_t)poly << (K1 + lr)) + tile * G::TILE_COLS + lane * CPL;
   const uint32_t *src = P.src[op] + base;
   uint32_t *dst = P.dst[op] + base;
+  uint32_t *sm = smem + lane * CPL;                       /* [row][32 lanes][CPL] */
   const ModQ m = modq_regs(P.m, P.zero);
 
-  uint32_t x[G::NV];
+  V x[G::NV];
   /* phase A: row bits K1-1 .. K1-RA are register bits; this warp's fixed low row bits = w */
 #pragma unroll
-  for (int k = 0; k < G::NV; k++) x[k] = __ldg(src + ((size_t)((k << G::RB) | w) << lr));
+  for (int k = 0; k < G::NV; k++) x[k] = cv_ldg<CPL>(src + ((size_t)((k << G::RB) | w) << lr));
 #pragma unroll
   for (int s = 0; s < G::RA; s++) {
     const int bit = G::RA - 1 - s;
@@ -107,16 +156,16 @@ large_cols_fwd_kernel(const __grid_constant__ LargeParams P) {
     for (int k = 0; k < G::NV; k++) {
       if (k & (1 << bit)) continue;
       const uint2 tw = __ldg(P.tab + (1 << s) + (k >> (bit + 1)));
-      ct_bfly<ARITH>(x[k], x[k | (1 << bit)], tw.x, tw.y, m);
+      cv_ct<ARITH, CPL>(x[k], x[k | (1 << bit)], tw, m);
     }
   }
   if (G::RB == 0) {
 #pragma unroll
-    for (int k = 0; k < G::NV; k++) dst[(size_t)k << lr] = x[k];
+    for (int k = 0; k < G::NV; k++) cv_st<CPL>(dst + ((size_t)k << lr), x[k]);
     return;
   }
 #pragma unroll
-  for (int k = 0; k < G::NV; k++) smem[(((k << G::RB) | w) << 5) + lane] = x[k];
+  for (int k = 0; k < G::NV; k++) cv_st<CPL>(sm + ((k << G::RB) | w) * G::TILE_COLS, x[k]);
   __syncthreads();
   /* phase B: row bits RB-1 .. 0 are register bits; fixed high row bits hfix = w*GB + g */
 #pragma unroll
@@ -124,7 +173,7 @@ large_cols_fwd_kernel(const __grid_constant__ LargeParams P) {
     const int hfix = w * G::GB + g;
 #pragma unroll
     for (int kk = 0; kk < (1 << G::RB); kk++)
-      x[(g << G::RB) + kk] = smem[(((hfix << G::RB) | kk) << 5) + lane];
+      x[(g << G::RB) + kk] = cv_ld<CPL>(sm + ((hfix << G::RB) | kk) * G::TILE_COLS);
   }
 #pragma unroll
   for (int s = 0; s < G::RB; s++) {
@@ -136,7 +185,7 @@ large_cols_fwd_kernel(const __grid_constant__ LargeParams P) {
       for (int kk = 0; kk < (1 << G::RB); kk++) {
         if (kk & (1 << bit)) continue;
         const uint2 tw = __ldg(P.tab + (1 << (G::RA + s)) + (hfix << s) + (kk >> (bit + 1)));
-        ct_bfly<ARITH>(x[(g << G::RB) + kk], x[(g << G::RB) + (kk | (1 << bit))], tw.x, tw.y, m);
+        cv_ct<ARITH, CPL>(x[(g << G::RB) + kk], x[(g << G::RB) + (kk | (1 << bit))], tw, m);
       }
     }
   }
@@ -145,7 +194,7 @@ large_cols_fwd_kernel(const __grid_constant__ LargeParams P) {
     const int hfix = w * G::GB + g;
 #pragma unroll
     for (int kk = 0; kk < (1 << G::RB); kk++)
-      dst[(size_t)((hfix << G::RB) | kk) << lr] = x[(g << G::RB) + kk];
+      cv_st<CPL>(dst + ((size_t)((hfix << G::RB) | kk) << lr), x[(g << G::RB) + kk]);
   }
 }
 
@@ -166,31 +215,33 @@ __device__ __forceinline__ void gs_last(uint32_t &X, uint32_t &Y, uint32_t yb, u
   X = csub(shoup_mul(s, lx.x, lx.y, m), m.q);
 }
 
-template <int K1, int ARITH>
+template <int K1, int ARITH, int CPL>
 __global__ void __launch_bounds__(ColGeom<K1>::WARPS * 32)
 large_cols_inv_kernel(const __grid_constant__ LargeParams P) {
-  using G = ColGeom<K1>;
+  using G = ColGeom<K1, CPL>;
+  using V = CVec<CPL>;
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
   constexpr int lr = LARGE_LR;
-  constexpr uint32_t tiles = 1u << (lr - 5);
+  constexpr int lt = lr - G::LOG_TILE;
   const unsigned long long unit = blockIdx.x;
-  const uint32_t tile = (uint32_t)(unit & (tiles - 1));
-  const unsigned long long poly = unit >> (lr - 5);
-  const size_t base = ((size_t)poly << (K1 + lr)) + tile * 32 + lane;
+  const uint32_t tile = (uint32_t)(unit & ((1u << lt) - 1));
+  const unsigned long long poly = unit >> lt;
+  const size_t base = ((size_t)poly << (K1 + lr)) + tile * G::TILE_COLS + lane * CPL;
   const uint32_t *src = P.src[0] + base;
   uint32_t *dst = P.dst[0] + base;
+  uint32_t *sm = smem + lane * CPL;
   const ModQ m = modq_regs(P.m, P.zero);
 
-  uint32_t x[G::NV];
+  V x[G::NV];
   if (G::RB > 0) {
 #pragma unroll
     for (int g = 0; g < G::GB; g++) {
       const int hfix = w * G::GB + g;
 #pragma unroll
       for (int kk = 0; kk < (1 << G::RB); kk++)
-        x[(g << G::RB) + kk] = __ldg(src + ((size_t)((hfix << G::RB) | kk) << lr));
+        x[(g << G::RB) + kk] = cv_ldg<CPL>(src + ((size_t)((hfix << G::RB) | kk) << lr));
     }
 #pragma unroll
     for (int bit = 0; bit < G::RB; bit++) {
@@ -203,7 +254,7 @@ large_cols_inv_kernel(const __grid_constant__ LargeParams P) {
           if (kk & (1 << bit)) continue;
           const int j = (hfix << (G::RB - 1 - bit)) | (kk >> (bit + 1));
           const uint2 tw = __ldg(P.tab_inv + (1 << (K1 - 1 - bit)) + j);
-          gs_bfly<ARITH>(x[(g << G::RB) + kk], x[(g << G::RB) + (kk | (1 << bit))], tw.x, tw.y, m, yb);
+          cv_gs<ARITH, CPL>(x[(g << G::RB) + kk], x[(g << G::RB) + (kk | (1 << bit))], tw, m, yb);
         }
       }
     }
@@ -212,14 +263,14 @@ large_cols_inv_kernel(const __grid_constant__ LargeParams P) {
       const int hfix = w * G::GB + g;
 #pragma unroll
       for (int kk = 0; kk < (1 << G::RB); kk++)
-        smem[(((hfix << G::RB) | kk) << 5) + lane] = x[(g << G::RB) + kk];
+        cv_st<CPL>(sm + ((hfix << G::RB) | kk) * G::TILE_COLS, x[(g << G::RB) + kk]);
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < G::NV; k++) x[k] = smem[(((k << G::RB) | w) << 5) + lane];
+    for (int k = 0; k < G::NV; k++) x[k] = cv_ld<CPL>(sm + ((k << G::RB) | w) * G::TILE_COLS);
   } else {
 #pragma unroll
-    for (int k = 0; k < G::NV; k++) x[k] = __ldg(src + ((size_t)k << lr));
+    for (int k = 0; k < G::NV; k++) x[k] = cv_ldg<CPL>(src + ((size_t)k << lr));
   }
 #pragma unroll
   for (int bit = 0; bit < G::RA; bit++) {
@@ -229,14 +280,16 @@ large_cols_inv_kernel(const __grid_constant__ LargeParams P) {
       if (k & (1 << bit)) continue;
       if (bit < G::RA - 1) {
         const uint2 tw = __ldg(P.tab_inv + (1 << (G::RA - 1 - bit)) + (k >> (bit + 1)));
-        gs_bfly<ARITH>(x[k], x[k | (1 << bit)], tw.x, tw.y, m, yb);
+        cv_gs<ARITH, CPL>(x[k], x[k | (1 << bit)], tw, m, yb);
       } else {
-        gs_last<ARITH>(x[k], x[k | (1 << bit)], yb, P.last_x, P.last_y, m);
+#pragma unroll
+        for (int c = 0; c < CPL; c++)
+          gs_last<ARITH>(x[k].v[c], x[k | (1 << bit)].v[c], yb, P.last_x, P.last_y, m);
       }
     }
   }
 #pragma unroll
-  for (int k = 0; k < G::NV; k++) dst[(size_t)((k << G::RB) | w) << lr] = x[k];
+  for (int k = 0; k < G::NV; k++) cv_st<CPL>(dst + ((size_t)((k << G::RB) | w) << lr), x[k]);
 }
 
 /* =====================================================================================

@@ -462,6 +462,8 @@ extern "C" int nttb200_polymul_batch_dev(nttb200_plan *P, int32_t *c, const int3
 extern "C" int nttb200_ntt_batch_dev(nttb200_plan *P, int transform, int32_t *a, size_t batch,
                                      void *stream) {
   if (!P || !a) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
+  /* the transform kernels move rows with 128-bit accesses */
+  if (((uintptr_t)a & 15u) != 0) return nttb200_fail(NTTB200_EPARAM, "a_dev must be 16-byte aligned");
   g_launches = 0;
   DeviceGuard guard(P->device);
   return transform_dev(P, transform, (uint32_t *)a, batch, (cudaStream_t)stream);

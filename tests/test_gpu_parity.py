@@ -671,3 +671,34 @@ def test_words_that_do_not_fit_16_bits_travel_as_32_bit_words(gpu, oracle, monke
     rows = np.r_[0:8, 4990:5000, 5001:5010]
     assert (ref[rows] == oracle.product(n, q, a[rows], b[rows], 10)).all()
     p.close()
+
+
+@pytest.mark.parametrize("n,q", [(2048, 12289), (8192, 998244353), (2048, 2013265921)])
+def test_large_n_operands_at_a_4_byte_offset(gpu, oracle, n, q):
+    """The column passes of the cheap-butterfly classes read two adjacent columns per lane with
+    64-bit accesses; rows that are only 4-byte aligned must take the one-column kernels and
+    give the same products."""
+    import torch
+    batch = 7
+    p = gpu.Plan(n, q)
+    a, b = oracle.random((batch, n), q, 21), oracle.random((batch, n), q, 22)
+    da = torch.zeros(batch * n + 1, dtype=torch.int32, device="cuda")
+    db = torch.zeros(batch * n + 1, dtype=torch.int32, device="cuda")
+    dc = torch.zeros(batch * n + 1, dtype=torch.int32, device="cuda")
+    da[1:] = torch.from_numpy(a.reshape(-1)).cuda()
+    db[1:] = torch.from_numpy(b.reshape(-1)).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    p.polymul_dev(dc.data_ptr() + 4, da.data_ptr() + 4, db.data_ptr() + 4, batch, st)
+    torch.cuda.synchronize()
+    want = oracle.product(n, q, a, b, 10)
+    assert (dc[1:].cpu().numpy().reshape(batch, n) == want).all()
+    assert int(dc[0]) == 0
+    with pytest.raises(gpu.NttError):                       # transforms: 16-byte aligned rows only
+        p.transform_dev("mulntt_std2rev", da.data_ptr() + 4, batch, st)
+    x = da[1:].clone()
+    assert x.data_ptr() % 16 == 0
+    p.transform_dev("mulntt_std2rev", x.data_ptr(), batch, st)
+    p.transform_dev("inttmul_rev2std_scaled", x.data_ptr(), batch, st)
+    torch.cuda.synchronize()
+    assert (x.cpu().numpy().reshape(batch, n) == a).all()
+    p.close()
