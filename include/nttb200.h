@@ -97,6 +97,8 @@ int nttb200_polymul_batch(nttb200_plan *plan, int32_t *c, const int32_t *a, cons
  * reference streams 32-bit FIFO words to the board (COMM/linux_app/NTT_PCIECommunicationv2.c:
  * 166-224).  The result rows of a 16-bit chunk return as 16-bit words that the pool widens into c
  * (NTTB200_WIRE_C32=1: as int32 words written by the kernel and copied straight into a pinned c).
+ * Pageable (malloc) buffers of the other plans with n <= 1024 go through the same pipeline with
+ * the pool as a parallel 32-bit stager (NTTB200_STAGE_PAGEABLE=0: the driver's pageable path).
  * Environment: NTTB200_WIRE=auto|16|32, NTTB200_HOST_THREADS (default: the CPUs the process may
  * run on, at most 32).  Statistics of the plan's last host-buffer call: polynomials whose
  * operands crossed the link as 16-bit / as 32-bit words (both 0 for calls below the threshold),

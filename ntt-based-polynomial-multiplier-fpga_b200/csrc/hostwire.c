@@ -11,8 +11,13 @@
  * caller's int32_t buffer.  This replaces what the reference's transfer program does with its
  * 32-bit FIFO words (COMM/linux_app/NTT_PCIECommunicationv2.c:166-224).
  *
- * This file holds only byte shuffling: narrowing, widening and the thread pool that runs
- * them.  No modular arithmetic happens on the CPU.  Narrowing also ORs all the input words
+ * Callers that hold their polynomials in pageable (malloc) memory -- the reference's own
+ * convention -- and cannot use the 16-bit wire (moduli above 12385) get the same pool as a
+ * parallel stager: 32-bit words are copied into / out of the pinned staging by the workers,
+ * 5x faster than the driver's pageable cudaMemcpyAsync path on the GPU box.
+ *
+ * This file holds only byte shuffling: narrowing, widening, copying and the thread pool that
+ * runs them.  No modular arithmetic happens on the CPU.  Narrowing also ORs all the input words
  * together: if any word does not fit 16 bits the caller falls back to the 32-bit wire for that
  * part of the batch, so results never depend on the wire format.
  *
@@ -96,6 +101,27 @@ __attribute__((target("avx2"))) static void widen_avx2(int32_t *dst, const uint1
 }
 #endif
 
+#if defined(__x86_64__)
+/* 32-bit words into a buffer that this library does not read again (the caller's c): non-temporal */
+__attribute__((target("avx2"))) static void copy_stream_avx2(int32_t *dst, const int32_t *src, size_t n) {
+  size_t i = 0;
+  if (((uintptr_t)dst & 31u) == 0) {
+    for (; i + 32 <= n; i += 32) {
+      const __m256i a0 = _mm256_loadu_si256((const __m256i *)(src + i));
+      const __m256i a1 = _mm256_loadu_si256((const __m256i *)(src + i + 8));
+      const __m256i a2 = _mm256_loadu_si256((const __m256i *)(src + i + 16));
+      const __m256i a3 = _mm256_loadu_si256((const __m256i *)(src + i + 24));
+      _mm256_stream_si256((__m256i *)(dst + i), a0);
+      _mm256_stream_si256((__m256i *)(dst + i + 8), a1);
+      _mm256_stream_si256((__m256i *)(dst + i + 16), a2);
+      _mm256_stream_si256((__m256i *)(dst + i + 24), a3);
+    }
+    _mm_sfence();
+  }
+  memcpy(dst + i, src + i, (n - i) * sizeof(int32_t));
+}
+#endif
+
 static int g_have_avx2 = -1;
 static int have_avx2(void) {
   if (g_have_avx2 < 0) {
@@ -122,9 +148,17 @@ void nttb200_wire_widen(int32_t *dst, const uint16_t *src, size_t n) {
   widen_scalar(dst, src, n);
 }
 
+void nttb200_wire_copy(int32_t *dst, const int32_t *src, size_t n, int streaming) {
+#if defined(__x86_64__)
+  if (streaming && have_avx2()) { copy_stream_avx2(dst, src, n); return; }
+#endif
+  (void)streaming;
+  memcpy(dst, src, n * sizeof(int32_t));
+}
+
 /* ---- the pool ---------------------------------------------------------------------- */
 
-enum { JOB_NARROW = 1, JOB_WIDEN = 2 };
+enum { JOB_NARROW = 1, JOB_WIDEN = 2, JOB_COPY = 3, JOB_COPY_STREAM = 4 };
 #define RING 256                      /* jobs in flight (a batch call keeps < 4 per slot)      */
 #define BLOCK_WORDS ((size_t)16384)   /* words per grabbed block: 64 KiB of int32              */
 
@@ -159,8 +193,10 @@ static void run_block(job_t *J, int kind, void *dst, const void *src, size_t wor
   if (kind == JOB_NARROW) {
     const uint32_t m = nttb200_wire_narrow((uint16_t *)dst + lo, (const int32_t *)src + lo, cnt);
     if ((m & 0xffff0000u) && mask_out) atomic_fetch_or_explicit(mask_out, m, memory_order_relaxed);
-  } else {
+  } else if (kind == JOB_WIDEN) {
     nttb200_wire_widen((int32_t *)dst + lo, (const uint16_t *)src + lo, cnt);
+  } else {
+    nttb200_wire_copy((int32_t *)dst + lo, (const int32_t *)src + lo, cnt, kind == JOB_COPY_STREAM);
   }
   atomic_fetch_add_explicit(&J->finished, 1, memory_order_release);
 }
@@ -281,6 +317,9 @@ static uint64_t post(int kind, void *dst, const void *src, size_t words, _Atomic
 
 uint64_t nttb200_wire_post_narrow(uint16_t *dst, const int32_t *src, size_t words, uint32_t *mask_out) {
   return post(JOB_NARROW, dst, src, words, (_Atomic uint32_t *)mask_out);
+}
+uint64_t nttb200_wire_post_copy(int32_t *dst, const int32_t *src, size_t words, int streaming) {
+  return post(streaming ? JOB_COPY_STREAM : JOB_COPY, dst, src, words, NULL);
 }
 uint64_t nttb200_wire_post_widen(int32_t *dst, const uint16_t *src, size_t words) {
   return post(JOB_WIDEN, dst, src, words, NULL);

@@ -535,7 +535,7 @@ static int ensure_slots(nttb200_plan *P, bool need_b) {
 /* depend on the wire.  NTTB200_WIRE=32|16|auto, NTTB200_WIRE_KWORDS (chunk),                  */
 /* NTTB200_WIRE_SLOTS are tuning knobs.                                                        */
 /* ------------------------------------------------------------------------------------ */
-enum { WS_FREE = 0, WS_NARROWING = 1, WS_INFLIGHT = 2, WS_WIDENING = 3 };
+enum { WS_FREE = 0, WS_STAGING = 1, WS_INFLIGHT = 2, WS_WIDENING = 3 };
 
 static int wire_mode() {                               /* read per call: tests switch it */
   const char *e = getenv("NTTB200_WIRE");
@@ -554,9 +554,9 @@ static int ensure_wire_slots(nttb200_plan *P) {
     NTT_CUDA(cudaMalloc(&s.d_a, w * sizeof(uint32_t)));
     NTT_CUDA(cudaMalloc(&s.d_b, w * sizeof(uint32_t)));
     NTT_CUDA(cudaMalloc(&s.d_c, w * sizeof(uint32_t)));
-    void *h = nullptr;
-    NTT_CUDA(cudaHostAlloc(&h, 3 * w * sizeof(uint16_t), cudaHostAllocPortable));
-    s.h_a = (uint16_t *)h;
+    void *h = nullptr;                                 /* staging holds words of either width */
+    NTT_CUDA(cudaHostAlloc(&h, 3 * w * sizeof(uint32_t), cudaHostAllocPortable));
+    s.h_a = (uint32_t *)h;
     s.h_b = s.h_a + w;
     s.h_c = s.h_b + w;
   }
@@ -569,23 +569,32 @@ static bool is_pinned(const void *p) {
   return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
 }
 
-static int wire_send32(nttb200_plan *P, WireSlot &s, int32_t *c, const int32_t *a, const int32_t *b) {
+/* how a chunk crosses the link */
+enum { WK_16 = 0,        /* narrowed by the pool, 16-bit words both ways (or int32 result rows: c_direct) */
+       WK_32_DIRECT = 1, /* DMA straight from / into the caller's pinned buffers                        */
+       WK_32_STAGED = 2  /* 32-bit words copied by the pool through pinned staging (pageable callers)   */ };
+
+/* 32-bit words: from the caller's pinned buffers, or from staging the pool has filled */
+static int wire_send32(nttb200_plan *P, WireSlot &s, int32_t *c, const int32_t *a, const int32_t *b, bool staged) {
   const size_t n = P->n, bytes = s.rows * n * sizeof(uint32_t);
-  NTT_CUDA(cudaMemcpyAsync(s.d_a, a + s.row0 * n, bytes, cudaMemcpyHostToDevice, s.stream));
-  NTT_CUDA(cudaMemcpyAsync(s.d_b, b + s.row0 * n, bytes, cudaMemcpyHostToDevice, s.stream));
+  const void *sa = staged ? (const void *)s.h_a : (const void *)(a + s.row0 * n);
+  const void *sb = staged ? (const void *)s.h_b : (const void *)(b + s.row0 * n);
+  void *dc = staged ? (void *)s.h_c : (void *)(c + s.row0 * n);
+  NTT_CUDA(cudaMemcpyAsync(s.d_a, sa, bytes, cudaMemcpyHostToDevice, s.stream));
+  NTT_CUDA(cudaMemcpyAsync(s.d_b, sb, bytes, cudaMemcpyHostToDevice, s.stream));
   int rc = launch_polymul_small(P, s.d_c, s.d_a, s.d_b, s.rows, s.stream);
   if (rc) return rc;
-  NTT_CUDA(cudaMemcpyAsync(c + s.row0 * n, s.d_c, bytes, cudaMemcpyDeviceToHost, s.stream));
+  NTT_CUDA(cudaMemcpyAsync(dc, s.d_c, bytes, cudaMemcpyDeviceToHost, s.stream));
   NTT_CUDA(cudaEventRecord(s.done, s.stream));
-  s.wide = 1;
+  s.kind = staged ? WK_32_STAGED : WK_32_DIRECT;
+  s.host_out = staged;
   s.state = WS_INFLIGHT;
   P->wire32_chunks += s.rows;
   return 0;
 }
-/* 16-bit operands; the result comes back either as the caller's int32 rows written by the
- * kernel's own 32-bit stores and one D2H straight into c (c pinned: the D2H direction of the link
- * is otherwise half idle, and the host pool is spared the widening), or as 16-bit rows into
- * pinned staging that the pool widens (c pageable) */
+/* 16-bit operands; the result comes back as 16-bit rows into pinned staging that the pool widens,
+ * or (c_direct) as the caller's int32 rows written by the kernel's own 32-bit stores and copied
+ * straight into a pinned c */
 static int wire_send16(nttb200_plan *P, WireSlot &s, int32_t *c, bool c_direct) {
   const size_t n = P->n, bytes = s.rows * n * sizeof(uint16_t);
   NTT_CUDA(cudaMemcpyAsync(s.d_a, s.h_a, bytes, cudaMemcpyHostToDevice, s.stream));
@@ -603,11 +612,26 @@ static int wire_send16(nttb200_plan *P, WireSlot &s, int32_t *c, bool c_direct) 
     NTT_CUDA(cudaMemcpyAsync(s.h_c, s.d_c, bytes, cudaMemcpyDeviceToHost, s.stream));
   }
   NTT_CUDA(cudaEventRecord(s.done, s.stream));
-  s.wide = c_direct ? 2 : 0;                          /* 2: narrow in, nothing to widen */
+  s.kind = WK_16;
+  s.host_out = !c_direct;
   s.state = WS_INFLIGHT;
   P->wire16_chunks += s.rows;
   if (c_direct) P->wire_c32_rows += s.rows;
   return 0;
+}
+/* queue the pool jobs that fill the slot's staging with the chunk's operands */
+static void wire_stage_in(nttb200_plan *P, WireSlot &s, const int32_t *a, const int32_t *b, int kind, uint32_t *mask) {
+  const size_t n = P->n, words = s.rows * n;
+  if (kind == WK_16) {
+    *mask = 0;
+    s.job_a = nttb200_wire_post_narrow((uint16_t *)s.h_a, a + s.row0 * n, words, mask);
+    s.job_b = nttb200_wire_post_narrow((uint16_t *)s.h_b, b + s.row0 * n, words, mask);
+  } else {
+    s.job_a = nttb200_wire_post_copy((int32_t *)s.h_a, a + s.row0 * n, words, 0);
+    s.job_b = nttb200_wire_post_copy((int32_t *)s.h_b, b + s.row0 * n, words, 0);
+  }
+  s.kind = kind;
+  s.state = WS_STAGING;
 }
 
 static int polymul_batch_wire(nttb200_plan *P, int32_t *c, const int32_t *a, const int32_t *b, size_t batch) {
@@ -617,6 +641,7 @@ static int polymul_batch_wire(nttb200_plan *P, int32_t *c, const int32_t *a, con
   const bool c_pinned = is_pinned(c);
   const bool pinned = is_pinned(a) && is_pinned(b) && c_pinned;
   const int mode = wire_mode();
+  const bool narrow_ok = P->plant && mode != 32;
   const bool c_direct = c_pinned && env_int("NTTB200_WIRE_C32", 0, 0, 1) == 1;
   const int ahead = env_int("NTTB200_WIRE_AHEAD", 99, 1, 99);
   P->wire16_chunks = P->wire32_chunks = P->wire_c32_rows = 0;
@@ -628,24 +653,29 @@ static int polymul_batch_wire(nttb200_plan *P, int32_t *c, const int32_t *a, con
   nttb200_wire_begin();
   while (next < batch || busy > 0) {
     bool progress = false;
-    int narrowing = 0;
+    int staging = 0;
     for (size_t i = 0; i < nsl && !rc; i++) {
       WireSlot &s = P->wslots[i];
-      if (s.state == WS_NARROWING) {
+      if (s.state == WS_STAGING) {
         if (nttb200_wire_done(s.job_a) && nttb200_wire_done(s.job_b)) {
-          rc = (mask[i] & 0xffff0000u) ? wire_send32(P, s, c, a, b) : wire_send16(P, s, c, c_direct);
+          if (s.kind == WK_32_STAGED) rc = wire_send32(P, s, c, a, b, true);
+          else if (!(mask[i] & 0xffff0000u)) rc = wire_send16(P, s, c, c_direct);
+          else if (pinned) rc = wire_send32(P, s, c, a, b, false);       /* a word does not fit 16 bits */
+          else wire_stage_in(P, s, a, b, WK_32_STAGED, &mask[i]);
           progress = true;
         } else {
-          narrowing++;
+          staging++;
         }
       } else if (s.state == WS_INFLIGHT) {
         const cudaError_t e = cudaEventQuery(s.done);
         if (e == cudaSuccess) {
-          if (s.wide) {
+          if (!s.host_out) {
             s.state = WS_FREE;
             busy--;
           } else {
-            s.job_c = nttb200_wire_post_widen(c + s.row0 * n, s.h_c, s.rows * n);
+            s.job_c = (s.kind == WK_16)
+                          ? nttb200_wire_post_widen(c + s.row0 * n, (const uint16_t *)s.h_c, s.rows * n)
+                          : nttb200_wire_post_copy(c + s.row0 * n, (const int32_t *)s.h_c, s.rows * n, 1);
             s.state = WS_WIDENING;
           }
           progress = true;
@@ -676,15 +706,8 @@ static int polymul_batch_wire(nttb200_plan *P, int32_t *c, const int32_t *a, con
         s.rows = nb;
         next += nb;
         busy++;
-        const bool wide = mode == 32 || (mode == 0 && pinned && narrowing >= ahead);
-        if (wide) {
-          rc = wire_send32(P, s, c, a, b);
-        } else {
-          mask[i] = 0;
-          s.job_a = nttb200_wire_post_narrow(s.h_a, a + s.row0 * n, nb * n, &mask[i]);
-          s.job_b = nttb200_wire_post_narrow(s.h_b, b + s.row0 * n, nb * n, &mask[i]);
-          s.state = WS_NARROWING;
-        }
+        if (pinned && (!narrow_ok || (mode == 0 && staging >= ahead))) rc = wire_send32(P, s, c, a, b, false);
+        else wire_stage_in(P, s, a, b, narrow_ok ? WK_16 : WK_32_STAGED, &mask[i]);
         progress = true;
         break;
       }
@@ -694,7 +717,7 @@ static int polymul_batch_wire(nttb200_plan *P, int32_t *c, const int32_t *a, con
   }
   if (rc) {                                            /* leave no job or copy behind */
     for (auto &s : P->wslots) {
-      if (s.state == WS_NARROWING) { nttb200_wire_wait(s.job_a); nttb200_wire_wait(s.job_b); }
+      if (s.state == WS_STAGING) { nttb200_wire_wait(s.job_a); nttb200_wire_wait(s.job_b); }
       if (s.state == WS_WIDENING) nttb200_wire_wait(s.job_c);
       cudaStreamSynchronize(s.stream);
       s.state = WS_FREE;
@@ -740,7 +763,12 @@ extern "C" int nttb200_polymul_batch(nttb200_plan *P, int32_t *c, const int32_t 
     memcpy(c, hc, bytes);
     return 0;
   }
-  if (P->plant && wire_mode() != 32 && batch * n >= WIRE_MIN_WORDS) return polymul_batch_wire(P, c, a, b, batch);
+  /* large batches: half-word moduli cross the link as 16-bit words; pageable buffers of any small-n
+   * plan are staged by the host pool instead of the driver (polymul_batch_wire) */
+  if (P->kernel == PK_SMALL && batch * n >= WIRE_MIN_WORDS &&
+      ((P->plant && wire_mode() != 32) ||
+       (env_int("NTTB200_STAGE_PAGEABLE", 1, 0, 1) && !(is_pinned(a) && is_pinned(b) && is_pinned(c)))))
+    return polymul_batch_wire(P, c, a, b, batch);
   size_t k = 0;
   for (size_t done = 0, nb = 0; done < batch; done += nb, k++) {
     HostSlot &s = P->slots[k % NSLOT];

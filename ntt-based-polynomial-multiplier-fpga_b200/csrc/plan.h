@@ -37,8 +37,9 @@ struct WireSlot {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
   uint32_t *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;      /* device: words of either width   */
-  uint16_t *h_a = nullptr, *h_b = nullptr, *h_c = nullptr;      /* pinned staging, 16-bit rows     */
-  int state = 0, wide = 0;
+  uint32_t *h_a = nullptr, *h_b = nullptr, *h_c = nullptr;      /* pinned staging, words of either width */
+  int state = 0, kind = 0;
+  bool host_out = false;                                        /* the result passes through h_c   */
   size_t row0 = 0, rows = 0;
   unsigned long long job_a = 0, job_b = 0, job_c = 0;
 };

@@ -702,3 +702,34 @@ def test_large_n_operands_at_a_4_byte_offset(gpu, oracle, n, q):
     torch.cuda.synchronize()
     assert (x.cpu().numpy().reshape(batch, n) == a).all()
     p.close()
+
+
+@pytest.mark.parametrize("n,q,batch", [(256, 8380417, 9001), (1024, 2013265921, 1500), (256, 12289, 5000)])
+def test_pageable_buffers_are_staged_by_the_host_pool(gpu, oracle, n, q, batch, monkeypatch):
+    """malloc'd (pageable) caller buffers -- the reference's convention -- of plans that cannot use
+    the 16-bit wire: the host pool copies 32-bit words through pinned staging instead of the
+    driver's pageable path.  Same products as the plain DMA ring."""
+    p = gpu.Plan(n, q)
+    a, b = oracle.random((batch, n), q, 31 + batch), oracle.random((batch, n), q, 32 + batch)
+    idx = np.unique(np.r_[0:16, batch - 16:batch, np.random.default_rng(n).integers(0, batch, 64)])
+    want = oracle.product(n, q, a[idx], b[idx], 10)
+    monkeypatch.setenv("NTTB200_WIRE", "32")
+    monkeypatch.setenv("NTTB200_STAGE_PAGEABLE", "0")
+    ref = p.polymul(a, b)                                   # driver-staged ring
+    assert p.wire_stats()["rows32"] == 0 and (ref[idx] == want).all()
+    monkeypatch.setenv("NTTB200_STAGE_PAGEABLE", "1")
+    got = p.polymul(a, b)
+    st = p.wire_stats()
+    assert st["rows32"] == batch and st["rows16"] == 0 and st["host_threads"] >= 1, st
+    assert (got == ref).all()
+    monkeypatch.delenv("NTTB200_WIRE")
+    got = p.polymul(a, b)                                   # default mode
+    assert (got == ref).all()
+    ha, hb, hc = (gpu.host_alloc((batch, n)) for _ in range(3))     # mixed: pinned operands, pageable result
+    ha.array[:], hb.array[:] = a, b
+    out = np.full((batch, n), -1, np.int32)
+    p.polymul_host_ptr(out.ctypes.data, ha.ptr, hb.ptr, batch)
+    assert (out == ref).all()
+    for h in (ha, hb, hc):
+        h.free()
+    p.close()

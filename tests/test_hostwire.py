@@ -19,6 +19,8 @@ def L(nttb200):
     lib.nttb200_wire_post_narrow.restype = C.c_uint64
     lib.nttb200_wire_post_widen.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.nttb200_wire_post_widen.restype = C.c_uint64
+    lib.nttb200_wire_post_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    lib.nttb200_wire_post_copy.restype = C.c_uint64
     lib.nttb200_wire_wait.argtypes = [C.c_uint64]
     lib.nttb200_wire_wait.restype = None
     lib.nttb200_wire_done.argtypes = [C.c_uint64]
@@ -105,3 +107,18 @@ def test_pool_serves_several_posting_threads_and_recycles_its_ring(L):
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert not errors
+
+
+@pytest.mark.parametrize("streaming", [0, 1])
+@pytest.mark.parametrize("words,offset", [(1, 0), (31, 1), (32, 0), (40000, 0), (100003, 3)])
+def test_pool_copies_32_bit_words(L, words, offset, streaming):
+    rng = np.random.default_rng(words)
+    src = rng.integers(-2**31, 2**31 - 1, words + offset, dtype=np.int64).astype(np.int32)[offset:]
+    dst = np.full(words + offset + 8, 7, np.int32)
+    L.nttb200_wire_begin()
+    try:
+        L.nttb200_wire_wait(L.nttb200_wire_post_copy(dst[offset:].ctypes.data, src.ctypes.data, words, streaming))
+    finally:
+        L.nttb200_wire_end()
+    assert (dst[offset:offset + words] == src).all()
+    assert (dst[:offset] == 7).all() and (dst[offset + words:] == 7).all()
