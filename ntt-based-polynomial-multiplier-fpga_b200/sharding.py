@@ -27,9 +27,10 @@ def init_distributed(backend: str):
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29511")
     # bench.py prints exactly one JSON line on stdout: keep NCCL's "NCCL version ..." banner
-    # (NCCL_DEBUG=VERSION/INFO in some environments) out of it
+    # (printed at NCCL_DEBUG=VERSION and at WARN) out of it; whatever NCCL has to say goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if not os.environ.get("NTTB200_KEEP_NCCL_DEBUG"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.pop("NCCL_DEBUG", None)
     if world > 1 and not dist.is_initialized():
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return dist
