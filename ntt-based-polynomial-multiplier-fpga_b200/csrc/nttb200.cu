@@ -643,7 +643,14 @@ static int polymul_batch_wire(nttb200_plan *P, int32_t *c, const int32_t *a, con
   const int mode = wire_mode();
   const bool narrow_ok = P->plant && mode != 32;
   const bool c_direct = c_pinned && env_int("NTTB200_WIRE_C32", 0, 0, 1) == 1;
-  const int ahead = env_int("NTTB200_WIRE_AHEAD", 99, 1, 99);
+  /* How much the pool can take.  A dozen threads or more keep up with the link (1 GPU, 16 host
+   * cores: 29.5 M polymul/s all-narrowed against 27.4 M mixed and 22.3 M all-32-bit).  Eight ranks
+   * sharing the 32 cores of one box get 4 threads each, and the box's memory system is what binds
+   * all of them together: 30.5 M all-narrowed, 47.5 M mixed (a chunk goes out as 32-bit words when
+   * the pool is already two chunks behind), 50.8 M all-32-bit.  Hence: >= 12 threads narrow
+   * everything, 6..11 mix, fewer leave pinned buffers to the DMA engines. */
+  const int pool = nttb200_wire_threads();
+  const int ahead = env_int("NTTB200_WIRE_AHEAD", pool >= 12 ? 99 : (pool >= 6 ? 2 : 0), 0, 99);
   P->wire16_chunks = P->wire32_chunks = P->wire_c32_rows = 0;
   uint32_t mask[16] = {0};                             /* per slot: OR of the words with high bits */
   const size_t nsl = P->wslots.size();
