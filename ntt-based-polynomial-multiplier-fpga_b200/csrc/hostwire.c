@@ -249,8 +249,24 @@ static void *worker(void *arg) {
   }
 }
 
+/* a forked child has none of the workers: start over with an empty pool of its own */
+static void pool_after_fork_in_child(void) {
+  pthread_mutex_init(&G.mu, NULL);
+  pthread_cond_init(&G.cv, NULL);
+  G.started = 0;
+  G.nworkers = 0;
+  atomic_store(&G.active, 0);
+  atomic_store(&G.posted, 0);
+  atomic_store(&G.retired, 0);
+}
+
 static int pool_start(void) {
+  static int atfork_set = 0;
   pthread_mutex_lock(&G.mu);
+  if (!atfork_set) {
+    pthread_atfork(NULL, NULL, pool_after_fork_in_child);
+    atfork_set = 1;
+  }
   if (!G.started) {
     int want = -1;
     const char *e = getenv("NTTB200_HOST_THREADS");

@@ -122,3 +122,35 @@ def test_pool_copies_32_bit_words(L, words, offset, streaming):
         L.nttb200_wire_end()
     assert (dst[offset:offset + words] == src).all()
     assert (dst[:offset] == 7).all() and (dst[offset + words:] == 7).all()
+
+
+def test_pool_survives_fork(nttb200):
+    """A forked child (multiprocessing, the bench's CPU legs) starts with an empty pool of its own.
+    Run in a fresh interpreter: pytest's own threads and hooks stay out of the fork."""
+    import subprocess
+    import sys
+    code = f"""
+import ctypes as C, numpy as np, os, warnings
+warnings.simplefilter("ignore")
+L = C.CDLL({nttb200.lib_path()!r})
+L.nttb200_wire_post_narrow.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+L.nttb200_wire_post_narrow.restype = C.c_uint64
+L.nttb200_wire_wait.argtypes = [C.c_uint64]
+src = np.arange(50000, dtype=np.int32)
+def narrow():
+    dst = np.zeros(50000, np.uint16)
+    L.nttb200_wire_begin()
+    L.nttb200_wire_wait(L.nttb200_wire_post_narrow(dst.ctypes.data, src.ctypes.data, 50000, None))
+    L.nttb200_wire_end()
+    return bool((dst == src.astype(np.uint16)).all())
+assert narrow()
+pid = os.fork()
+if pid == 0:
+    os._exit(0 if narrow() and narrow() else 1)
+_, status = os.waitpid(pid, 0)
+assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0, status
+assert narrow()
+print("ok")
+"""
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr
