@@ -48,9 +48,9 @@ WORKLOADS = {
 }
 # DRAM bytes (read + write) per launch of the dominant kernel, from `ncu --set full` captures
 # committed under profiles/ (a profiler run is never a bench value; this is the traffic only)
-TRAFFIC_NCU = {"c2": 134257920 + 36911104}
-TRAFFIC_SRC = {"c2": "profiles/r1_c2_polymul_plant_n256_v4_ncu_full.txt: dram__bytes_read.sum 134.26 MB + "
-                     "dram__bytes_write.sum 36.91 MB per launch (algorithmic 201.3 MB; part of c stays dirty in L2)"}
+TRAFFIC_NCU = {"c2": 134264064 + 35679488}
+TRAFFIC_SRC = {"c2": "profiles/r1_c2_polymul_plant_n256_v5_ncu_full.txt: dram__bytes_read.sum 134.26 MB + "
+                     "dram__bytes_write.sum 35.68 MB per launch (algorithmic 201.3 MB; part of c stays dirty in L2)"}
 SEED = 0x4E545442323030
 L2_BYTES = 126 * 1000 * 1000
 
@@ -417,7 +417,9 @@ def main() -> int:
     # (2 slots: measured half rate) + 2 IMAD; pointwise Montgomery = 2 IMAD.HI + 2 IMAD; the
     # n^-1 scaling costs one extra Shoup multiplication on the sum branch of the last stage
     plantard = "plantard" in plan.describe()
-    if plantard:      # IMAD + IMAD.HI per butterfly (3), 2 IMAD + IMAD.HI pointwise (4), 3 per n^-1 scale
+    if plantard and n <= 256:   # half-word second product: 2 IMAD (+ 2 shifts on the ALU pipe) per butterfly
+        slots = 2 * bflies + 4 * n + 2 * (n // 2)
+    elif plantard:    # IMAD + IMAD.HI per butterfly (3), 2 IMAD + IMAD.HI pointwise (4), 3 per n^-1 scale
         slots = 3 * bflies + 4 * n + 3 * (n // 2)
     else:
         slots = 4 * bflies + 6 * n + 4 * (n // 2)
@@ -454,8 +456,9 @@ def main() -> int:
                                "large_cols_fwd + large_rows_polymul + large_cols_inv (whole step)",
                      "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": roof_ms,
                      "traffic_source": TRAFFIC_SRC.get(args.workload)},
-        "int_roofline": {"bound": "fmaheavy-issue (binding for this path: ncu sm__pipe_fmaheavy is the "
-                                  "top unit, see profiles/)",
+        "int_roofline": {"bound": "multiplier (fmaheavy) pipe; the n<=256 Plantard kernel trades multiplier slots for "
+                                  "ALU instructions, so issue slots and the two integer pipes are near level "
+                                  "(ncu, profiles/): read this fraction next to roofline.frac, not as the binding one",
                          "achieved": slot_achieved, "peak": imad_peak, "unit": "IMAD-slot lane-ops/s",
                          "frac": slot_achieved / imad_peak if imad_peak else None,
                          "slots_per_polymul": slots,
@@ -465,7 +468,7 @@ def main() -> int:
                          "note": "peak = independent IMAD chains on every SM, measured live "
                                  "(nttb200_measure_int_peak); IMAD.HI measured at half that rate so it "
                                  "counts 2 slots. Shoup kernels: butterfly 4, pointwise 6, n^-1 scale 4 per "
-                                 "pair; Plantard kernel (q<=12385): butterfly 3, pointwise 4, scale 3 (at n<=256 every other butterfly runs a 2-slot + 2-ALU form, but ptxas moves as many additions onto the multiplier pipe, so the executed slots are the same)",
+                                 "pair; Plantard kernel (q<=12385): butterfly 3, pointwise 4, scale 3 at n=512/1024; at n<=256 butterfly and scale 2 (IMAD, SHF, IMAD, SHF: the second product takes only the upper half of the first)",
                          "arith": "plantard" if plantard else "shoup"},
         "parity_ok": parity_ok,
         "standalone_ntt": ntt_lines,

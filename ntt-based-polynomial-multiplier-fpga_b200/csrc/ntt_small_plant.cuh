@@ -124,18 +124,17 @@ __device__ __forceinline__ uint32_t plant_mul(uint32_t y, uint32_t wt, uint32_t 
  *        T = ((p >> 16) + 1) q >> 16          (IMAD, SHF, IMAD, SHF)
  * [(p>>16 + 1) q 2^16 = p q + (2^16 - p_lo) q, so the quotient by 2^32 is the same k as above
  *  whenever Y W + 2^16 q < 2^32: every Y < 22 q for q <= 12385; tests/test_plantard_arith.py.]
- * Two multiplier slots and two ALU instructions instead of three multiplier slots: PLANT_B_NUM
- * of every PLANT_B_DEN butterflies use B, to move work from the multiplier (fmaheavy) pipe to
- * the ALU pipe, which has room.  What that buys is small -- ptxas answers the extra ALU
- * instructions by turning more of the butterfly additions into IMAD.IADD, so the multiplier
- * slots per tile barely move (SASS counts in DESIGN.md section 4): measured +0.9 % (c2) and
- * +1.3 % (c3) at 1/2, -6 % at n = 1024 where the longer code misses the instruction cache
- * more, hence n <= 256 only. */
+ * Two multiplier slots and two ALU instructions instead of three multiplier slots.  Measured on
+ * B200: with q in an ordinary register (PlRegs) every butterfly of the
+ * n <= 256 kernels in this form is worth +7 % (c3 1 252 -> 1 343 M polymul/s; PLANT_B_NUM of every
+ * PLANT_B_DEN butterflies: 1/4 1 243, 1/2 1 274, 3/4 1 316, all 1 343) although ptxas answers the
+ * extra ALU instructions by turning butterfly additions into IMAD.IADD; at n = 1024 the longer
+ * code misses the instruction cache (249 -> 213 M), hence PLANT_B_MAXL = 8. */
 #ifndef PLANT_B_NUM
 #define PLANT_B_NUM 1
 #endif
 #ifndef PLANT_B_DEN
-#define PLANT_B_DEN 2
+#define PLANT_B_DEN 1
 #endif
 #ifndef PLANT_B_MAXL
 #define PLANT_B_MAXL 8
