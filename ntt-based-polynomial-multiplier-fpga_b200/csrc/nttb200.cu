@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <new>
 #include <string>
@@ -536,6 +537,8 @@ static int ensure_slots(nttb200_plan *P, bool need_b) {
 /* NTTB200_WIRE_SLOTS are tuning knobs.                                                        */
 /* ------------------------------------------------------------------------------------ */
 enum { WS_FREE = 0, WS_STAGING = 1, WS_INFLIGHT = 2, WS_WIDENING = 3 };
+/* host-buffer calls running side by side in this process (nttb200_multi_polymul_batch: one per GPU) */
+static std::atomic<int> g_wire_share{1};
 
 static int wire_mode() {                               /* read per call: tests switch it */
   const char *e = getenv("NTTB200_WIRE");
@@ -649,7 +652,7 @@ static int polymul_batch_wire(nttb200_plan *P, int32_t *c, const int32_t *a, con
    * all of them together: 30.5 M all-narrowed, 47.5 M mixed (a chunk goes out as 32-bit words when
    * the pool is already two chunks behind), 50.8 M all-32-bit.  Hence: >= 12 threads narrow
    * everything, 6..11 mix, fewer leave pinned buffers to the DMA engines. */
-  const int pool = nttb200_wire_threads();
+  const int pool = nttb200_wire_threads() / std::max(1, g_wire_share.load());
   const int ahead = env_int("NTTB200_WIRE_AHEAD", pool >= 12 ? 99 : (pool >= 6 ? 2 : 0), 0, 99);
   P->wire16_chunks = P->wire32_chunks = P->wire_c32_rows = 0;
   uint32_t mask[16] = {0};                             /* per slot: OR of the words with high bits */
@@ -1070,6 +1073,7 @@ extern "C" int nttb200_multi_polymul_batch(nttb200_multi *M, int32_t *c, const i
   std::vector<std::string> errs(G);
   std::vector<int> launches(G, 0);
   std::vector<std::thread> th;
+  g_wire_share.store(G);                              /* the G calls below share one host pool */
   for (int g = 0; g < G; g++) {
     th.emplace_back([&, g]() {
       size_t lo, hi;
@@ -1081,6 +1085,7 @@ extern "C" int nttb200_multi_polymul_batch(nttb200_multi *M, int32_t *c, const i
     });
   }
   for (auto &t : th) t.join();
+  g_wire_share.store(1);
   g_launches = 0;
   for (int g = 0; g < G; g++) {
     g_launches += launches[g];
