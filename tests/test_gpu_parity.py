@@ -733,3 +733,27 @@ def test_pageable_buffers_are_staged_by_the_host_pool(gpu, oracle, n, q, batch, 
     for h in (ha, hb, hc):
         h.free()
     p.close()
+
+
+@pytest.mark.parametrize("n,q,logb", [(256, 7681, 19), (1024, 12289, 16)])
+def test_host_buffer_call_equals_device_resident_call_on_a_large_batch(gpu, oracle, n, q, logb):
+    """Hundreds of chunks through the wire pipeline (ring reuse, ramp, taper): the int32 rows that
+    come back into the caller's buffer must equal, row for row, what the device-resident call
+    gives on the same operands, and sampled rows must equal the oracle."""
+    import torch
+    batch = (1 << logb) + 77                                # not a multiple of anything
+    p = gpu.Plan(n, q)
+    g = torch.Generator(device="cuda").manual_seed(99 + n)
+    da = torch.randint(0, q, (batch, n), dtype=torch.int32, device="cuda", generator=g)
+    db = torch.randint(0, q, (batch, n), dtype=torch.int32, device="cuda", generator=g)
+    dc = torch.empty_like(da)
+    p.polymul_dev(dc.data_ptr(), da.data_ptr(), db.data_ptr(), batch, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    a, b = da.cpu().numpy(), db.cpu().numpy()               # pageable host copies
+    got = p.polymul(a, b)
+    st = p.wire_stats()
+    assert st["rows16"] + st["rows32"] == batch, st
+    assert (got == dc.cpu().numpy()).all()
+    idx = np.unique(np.r_[0:4, batch - 4:batch, np.random.default_rng(3).integers(0, batch, 120)])
+    assert (got[idx] == oracle.product(n, q, a[idx], b[idx], 10)).all()
+    p.close()
