@@ -44,6 +44,15 @@ namespace nttb200 {
 #ifndef PLANT_ADD3
 #define PLANT_ADD3 0
 #endif
+#ifndef PLANT_STAGGER_NS
+#define PLANT_STAGGER_NS 0     /* tuning experiment, see below: +1 % at best, inside the box-to-box spread */
+#endif
+#ifndef PLANT_STAGGER_MIN_TILES
+#define PLANT_STAGGER_MIN_TILES 4
+#endif
+#ifndef PLANT_DYN_MINL
+#define PLANT_DYN_MINL 9   /* sizes from 2^9 up hand the last tiles out dynamically (see PlantParams::sched) */
+#endif
 #ifndef PLANT_QREG
 #define PLANT_QREG 1   /* which constants live in ordinary registers, see PlRegs */
 #endif
@@ -63,6 +72,9 @@ struct PlantParams {
   uint32_t last_y;           /* (-n^-1 2^32 p_inv[1])~ : multiplier of its diff branch         */
   uint32_t qmul[16];         /* i * q, so that "+ b q" is a constant-bank operand         */
   uint32_t zero;             /* always 0 (see add_alu)                                    */
+  unsigned long long *sched; /* tail scheduler: [0] next chunk, [1] warps finished (both 0 between
+                                launches); NULL = static round-robin assignment only          */
+  uint32_t static_rounds;    /* tiles every warp takes round-robin before it turns to sched  */
   uint32_t ufwd[1 << R];     /* entries [1, 2^R) of the forward level table (w~)          */
   uint32_t uinv[1 << R];
 };
@@ -348,6 +360,28 @@ __device__ __forceinline__ void pl_inv_cols(uint32_t (&x)[SmallGeom<L>::NV],
   }
 }
 
+/* Tail scheduler (n >= 2^PLANT_DYN_MINL).  With a purely static assignment every warp gets the
+ * same number of tiles and the grid lasts as long as its slowest SM: two launches kept in flight on
+ * two streams, which lets the fast SMs run ahead into the next launch, measured +8 % at n = 1024
+ * (profiles/r1_two_streams.txt, bench.py "two_streams").  So the last quarter of the tiles is
+ * handed out from a device counter instead: a warp that has done its `static_rounds` round-robin
+ * tiles grabs one tile at a time (one atomic by lane 0, issued a whole tile ahead of the prefetch
+ * that needs it and only looked at when that tile ends): c4 249 -> 263.5 M polymul/s, level with
+ * the two-stream figure.  At n = 256 the same loop measured no gain (tiles are four times shorter,
+ * 2 368 warps on one counter, and the extra loop state costs 1.6 % at the 127-register cap), so
+ * those sizes keep the static loop at compile time.  The last warp to finish zeroes the two words
+ * for the next launch that is handed this slot. */
+__device__ __forceinline__ void plant_sched_done(unsigned long long *sched, int lane, unsigned long long warps) {
+  if (lane == 0) {
+    __threadfence();
+    if (atomicAdd(sched + 1, 1ULL) + 1 == warps) {      /* every warp has made its last grab */
+      sched[0] = 0;
+      sched[1] = 0;
+      __threadfence();
+    }
+  }
+}
+
 /* cp.async (LDGSTS) 16-byte copy global -> shared */
 __device__ __forceinline__ void cp_async16(uint32_t *smem_dst, const uint32_t *gsrc) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -417,7 +451,16 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
 
   const unsigned long long ntiles = (P.batch + Gm::PPW - 1) / Gm::PPW;
   const unsigned long long wstride = (unsigned long long)gridDim.x * WARPS;
+  /* compile-time switch: the sizes below PLANT_DYN_MINL keep the purely static loop */
+  constexpr bool DYN = (L >= PLANT_DYN_MINL);
+  const bool dyn = DYN && P.sched != nullptr;
+  uint32_t rounds_left = dyn ? P.static_rounds : 0xffffffffu;     /* static tiles still to hand out */
+  const unsigned long long dyn_base = (unsigned long long)P.static_rounds * wstride;
   unsigned long long tile = (unsigned long long)blockIdx.x * WARPS + warp;
+  unsigned long long next = tile + wstride;
+  unsigned long long pend = 0;                                     /* lane 0: the grab in flight */
+  /* (static_rounds >= 2, so the first two tiles are static ones) */
+  if (dyn) rounds_left -= 2;
 
   /* programmatic dependent launch: let the next launch on the stream start its CTAs (and
    * their twiddle loads, which depend on nothing) while this grid drains; operands may be the
@@ -429,12 +472,21 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
     twi.load(P.tw_inv, l);
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#if PLANT_STAGGER_NS > 0
+  /* The warps of a launch start together and stay in step from tile to tile, so the four that
+   * share a scheduler want the same pipes at the same time.  Starting them a fraction of a tile
+   * apart measured +1.0 % (batch 2^16) to +1.4 % (2^20) at n = 256 on one box, the same for 450,
+   * 900 and 1800 ns, and nothing on another: off by default. */
+  if (L <= 8 && ntiles > wstride * PLANT_STAGGER_MIN_TILES)
+    __nanosleep((unsigned)(((warp >> 2) + 2 * (blockIdx.x & 1)) * PLANT_STAGGER_NS));
+#endif
   if (tile < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile, P.batch, lane);
 
   /* bulk (TMA) stores need 16-byte aligned rows in shared memory: every size but the tiniest */
   constexpr bool BULK = PLANT_BULK_STORE && (Gm::T >= 4) && (Gm::N * sizeof(IO) >= 16) && sizeof(IO) == sizeof(OIO);
   bool bulk_pending = false;
-  for (; tile < ntiles; tile += wstride) {
+  unsigned long long next2 = 0;
+  for (; tile < ntiles; tile = next, next = next2) {
     const unsigned long long poly = tile * Gm::PPW + sub;
     const bool live = poly < P.batch;
 
@@ -447,7 +499,16 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
       xb[k] = pf_b[sub * Pg::PSTRIDE + (k << Gm::H) + l];
     }
     __syncwarp();                                     /* prefetch buffers are free again */
-    if (tile + wstride < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile + wstride, P.batch, lane);
+    if (next < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, next, P.batch, lane);
+    /* the tile after next: round-robin while static rounds are left, then one grab from the
+     * counter, issued here and only looked at when this tile ends */
+    const bool grab = dyn && rounds_left == 0;
+    if (grab) {
+      if (lane == 0) pend = atomicAdd(P.sched, 1ULL);
+    } else {
+      next2 = next + wstride;
+      if (dyn) rounds_left--;
+    }
 
     pl_fwd_cols<L>(xa, P, G);
     pl_fwd_cols<L>(xb, P, G);
@@ -521,8 +582,10 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
       }
       __syncwarp();                                   /* smem reuse by the next tile */
     }
+    if (grab) next2 = dyn_base + __shfl_sync(0xffffffffu, pend, 0);
   }
   if (BULK && bulk_pending && l == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (dyn) plant_sched_done(P.sched, lane, wstride);
 }
 
 /* bring a value < B q to [0, q) with ceil(log2 B) conditional subtractions */

@@ -185,6 +185,14 @@ extern "C" int nttb200_plan_create(nttb200_plan **out, uint32_t n, uint32_t q, u
   }
   if (rc) { nttb200_plan_destroy(P); return rc; }
   static const char *an[] = {"lazy", "harvey", "canon"};
+  if (P->plant) {
+    if (cudaMalloc(&P->sched_ring, NTTB200_SCHED_SLOTS * 2 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(P->sched_ring, 0, NTTB200_SCHED_SLOTS * 2 * sizeof(unsigned long long)) != cudaSuccess) {
+      cudaGetLastError();
+      if (P->sched_ring) cudaFree(P->sched_ring);
+      P->sched_ring = nullptr;                         /* static tile assignment only */
+    }
+  }
   snprintf(P->desc, sizeof P->desc, "n=%u q=%u %s=%u kernel=%s arith=%s%s device=%d sms=%d", n, q,
            cyclic ? "omega" : "psi", cyclic ? omega : psi,
            P->kernel == PK_SMALL ? "fused-small(regs+smem)" : "large(multi-pass)", an[P->arith],
@@ -210,6 +218,7 @@ extern "C" void nttb200_plan_destroy(nttb200_plan *P) {
     if (s.h_a) cudaFreeHost(s.h_a);
   }
   if (P->scratch) cudaFree(P->scratch);
+  if (P->sched_ring) cudaFree(P->sched_ring);
   if (P->zc_host) cudaFreeHost(P->zc_host);
   for (auto &ln : P->lanes) {
     if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamDestroy(ln.stream); }

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -25,6 +26,7 @@ static inline uint32_t nttb200_plant_form(uint32_t w, uint32_t q, uint32_t qinv)
 }
 
 enum PlanKernel { PK_SMALL = 0, PK_LARGE = 1 };
+constexpr unsigned NTTB200_SCHED_SLOTS = 4096;
 
 struct HostSlot {
   cudaStream_t stream = nullptr;
@@ -77,6 +79,11 @@ struct nttb200_plan {
   std::vector<WireSlot> wslots;
   size_t wire_polys = 0;           /* rows per wire chunk */
   unsigned long long wire16_chunks = 0, wire32_chunks = 0, wire_c32_rows = 0;      /* rows sent on each wire by the last call */
+
+  /* tail scheduler of the Plantard product kernel: ring of (next chunk, warps finished) pairs,
+   * zero between launches; every launch that uses it is handed the next pair */
+  unsigned long long *sched_ring = nullptr;
+  mutable std::atomic<unsigned> sched_seq{0};
 
   /* large-n: internal stream lanes, each with scratch for scratch_polys polynomials */
   uint32_t *scratch = nullptr;

@@ -2,6 +2,8 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "ntt_small_plant.cuh"
 #include "plan.h"
 
@@ -39,6 +41,14 @@ int plant_pdl() {
   return v;
 }
 
+/* tail scheduler knob: NTTB200_PLANT_DYN_PCT = per cent of the tiles handed out dynamically
+ * (0 = static assignment only).  c4 on B200: 0 % 236, 8 % 245, 16 % 259, 24 % 263.5, 32 % 262,
+ * 50 % 260, 100 % 253 M polymul/s */
+int plant_dyn_pct() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("NTTB200_PLANT_DYN_PCT"); v = e ? atoi(e) : 24; if (v < 0) v = 0; if (v > 100) v = 100; }
+  return v;
+}
 template <int L, int MINB, typename IO = uint32_t, typename OIO = IO>
 int run_plant(const nttb200_plan *P, void *c, const void *a, const void *b, size_t batch,
               cudaStream_t st) {
@@ -72,6 +82,14 @@ int run_plant(const nttb200_plan *P, void *c, const void *a, const void *b, size
   const unsigned long long want = (tiles + Cfg::WARPS - 1) / Cfg::WARPS;
   const unsigned long long cap = (unsigned long long)P->sm_count * per_sm;
   const int grid = (int)(want < cap ? (want ? want : 1) : cap);
+  /* more tiles than warps: the last few per cent are handed out from a device counter (PlantTiles) */
+  const unsigned long long warps = (unsigned long long)grid * Cfg::WARPS;
+  p.sched = nullptr;
+  if (P->sched_ring && plant_dyn_pct() > 0 && tiles > 4 * warps) {
+    const unsigned long long stat = tiles * (100 - plant_dyn_pct()) / 100 / warps;      /* whole rounds */
+    p.static_rounds = (uint32_t)std::min<unsigned long long>(std::max<unsigned long long>(stat, 2), 0x7fffffffull);
+    p.sched = P->sched_ring + 2 * (size_t)(P->sched_seq.fetch_add(1) % NTTB200_SCHED_SLOTS);
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(Cfg::WARPS * 32);
