@@ -80,7 +80,17 @@ int run_plant(const nttb200_plan *P, void *c, const void *a, const void *b, size
   if (per_sm < 1) return nttb200_fail(NTTB200_ECUDA, "plant kernel does not fit on an SM");
   const unsigned long long tiles = (batch + Gm::PPW - 1) / Gm::PPW;
   const unsigned long long want = (tiles + Cfg::WARPS - 1) / Cfg::WARPS;
-  const unsigned long long cap = (unsigned long long)P->sm_count * per_sm;
+  /* Sizes that keep the static loop (n <= 256) launch up to 4 times the resident CTAs, as long as
+   * every warp still gets 6 tiles or more: the hardware then hands CTAs to the SMs as they free up,
+   * which evens out the SM-to-SM spread at the price of one start-up per CTA.
+   * Measured: batch 2^20 x1 1 349, x2 1 367, x3 1 375, x4 1 378, x8 1 375 M polymul/s; batch 2^16 x1
+   * 1 223, x2 1 245, x3 1 221, x4 1 210, x8 986 M.  NTTB200_PLANT_GRIDX overrides. */
+  static const int gridx_env = [] { const char *e = getenv("NTTB200_PLANT_GRIDX"); int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 64 ? 64 : v); }();
+  unsigned long long gridx = 1;
+  if (gridx_env > 0) gridx = (unsigned long long)gridx_env;
+  else if (L < PLANT_DYN_MINL)
+    gridx = std::min<unsigned long long>(4, std::max<unsigned long long>(1, tiles / ((unsigned long long)P->sm_count * per_sm * Cfg::WARPS * 6)));
+  const unsigned long long cap = (unsigned long long)P->sm_count * per_sm * gridx;
   const int grid = (int)(want < cap ? (want ? want : 1) : cap);
   /* more tiles than warps: the last few per cent are handed out from a device counter (PlantTiles) */
   const unsigned long long warps = (unsigned long long)grid * Cfg::WARPS;
