@@ -5,6 +5,8 @@
  */
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "ntt_small.cuh"
 #include "plan.h"
 
@@ -42,6 +44,9 @@ int grid_for(K kernel, int threads, int smem, int sm_count, unsigned long long t
   if (per_sm < 1) return nttb200_fail(NTTB200_ECUDA, "kernel does not fit on an SM");
   unsigned long long want = tiles_per_block_unit;
   unsigned long long cap = (unsigned long long)sm_count * per_sm;
+  /* up to 4 times the resident CTAs while a warp still gets 6 tiles or more: the hardware hands
+   * CTAs to the SMs as they free up, which evens out the SM-to-SM spread (small_plant.cu) */
+  cap *= std::min<unsigned long long>(4, std::max<unsigned long long>(1, want / (cap * 6)));
   *grid = (int)(want < cap ? (want ? want : 1) : cap);
   return 0;
 }

@@ -189,7 +189,8 @@ int run_ntt_plant(const nttb200_plan *P, const DevTable &tab, int scale, uint32_
   if (per_sm < 1) return nttb200_fail(NTTB200_ECUDA, "plant transform kernel does not fit on an SM");
   const unsigned long long tiles = (batch + Gm::PPW - 1) / Gm::PPW;
   const unsigned long long want = (tiles + WARPS - 1) / WARPS;
-  const unsigned long long cap = (unsigned long long)P->sm_count * per_sm;
+  unsigned long long cap = (unsigned long long)P->sm_count * per_sm;
+  cap *= std::min<unsigned long long>(4, std::max<unsigned long long>(1, want / (cap * 6)));   /* as run_plant */
   const int grid = (int)(want < cap ? (want ? want : 1) : cap);
   kernel<<<grid, WARPS * 32, smem, st>>>(p);
   nttb200_count_launch(1);
