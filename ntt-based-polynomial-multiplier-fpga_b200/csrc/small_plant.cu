@@ -92,10 +92,11 @@ int run_plant(const nttb200_plan *P, void *c, const void *a, const void *b, size
     gridx = std::min<unsigned long long>(4, std::max<unsigned long long>(1, tiles / ((unsigned long long)P->sm_count * per_sm * Cfg::WARPS * 6)));
   const unsigned long long cap = (unsigned long long)P->sm_count * per_sm * gridx;
   const int grid = (int)(want < cap ? (want ? want : 1) : cap);
-  /* more tiles than warps: the last few per cent are handed out from a device counter (PlantTiles) */
+  /* n >= 2^PLANT_DYN_MINL, many more tiles than warps: the last quarter of the tiles is handed out
+   * from a device counter (PlantParams::sched) */
   const unsigned long long warps = (unsigned long long)grid * Cfg::WARPS;
   p.sched = nullptr;
-  if (P->sched_ring && plant_dyn_pct() > 0 && tiles > 4 * warps) {
+  if (L >= PLANT_DYN_MINL && P->sched_ring && plant_dyn_pct() > 0 && tiles > 4 * warps) {
     const unsigned long long stat = tiles * (100 - plant_dyn_pct()) / 100 / warps;      /* whole rounds */
     p.static_rounds = (uint32_t)std::min<unsigned long long>(std::max<unsigned long long>(stat, 2), 0x7fffffffull);
     p.sched = P->sched_ring + 2 * (size_t)(P->sched_seq.fetch_add(1) % NTTB200_SCHED_SLOTS);
