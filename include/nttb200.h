@@ -99,6 +99,8 @@ int nttb200_polymul_batch(nttb200_plan *plan, int32_t *c, const int32_t *a, cons
  * (NTTB200_WIRE_C32=1: as int32 words written by the kernel and copied straight into a pinned c).
  * Pageable (malloc) buffers of the other plans with n <= 1024 go through the same pipeline with
  * the pool as a parallel 32-bit stager (NTTB200_STAGE_PAGEABLE=0: the driver's pageable path).
+ * How much is narrowed follows the size of the pool: 12 threads or more narrow every chunk, 6 to 11
+ * mix 32-bit chunks in when the pool lags, fewer leave pinned buffers to the DMA engines alone.
  * Environment: NTTB200_WIRE=auto|16|32, NTTB200_HOST_THREADS (default: the CPUs the process may
  * run on, at most 32).  Statistics of the plan's last host-buffer call: polynomials whose
  * operands crossed the link as 16-bit / as 32-bit words (both 0 for calls below the threshold),
@@ -107,7 +109,10 @@ int nttb200_plan_wire_stats(const nttb200_plan *plan, unsigned long long *rows16
                             unsigned long long *rows32, unsigned long long *rows_c16,
                             int *host_threads);
 /* Device-resident buffers (the timed path: no PCIe in the loop).  Asynchronous on
- * `stream` (a cudaStream_t passed as void*, NULL = the legacy default stream). */
+ * `stream` (a cudaStream_t passed as void*, NULL = the legacy default stream).  Calls on one
+ * stream run one after the other; a caller with several independent batches gets 5-12 % more
+ * out of the GPU by alternating between two streams (the tail of one launch then overlaps the
+ * start of the next; bench.py reports both figures). */
 int nttb200_polymul_batch_dev(nttb200_plan *plan, int32_t *c_dev, const int32_t *a_dev,
                               const int32_t *b_dev, size_t batch, void *stream);
 
