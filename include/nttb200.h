@@ -164,6 +164,8 @@ enum nttb200_transform {
    * (R/NTT/ntt256.h:20-26) */
   NTTB200_NTT_REV2STD = 7
 };
+/* (host array, pinned or pageable; a large pageable array is staged through pinned memory by the
+ * host pool, as in nttb200_polymul_batch) */
 int nttb200_ntt_batch(nttb200_plan *plan, int transform, int32_t *a, size_t batch);
 /* a_dev must be 16-byte aligned (NTTB200_EPARAM otherwise): rows move with 128-bit accesses */
 int nttb200_ntt_batch_dev(nttb200_plan *plan, int transform, int32_t *a_dev, size_t batch,

@@ -850,6 +850,74 @@ extern "C" int nttb200_polymul_batch_u16(nttb200_plan *P, uint16_t *c, const uin
   return 0;
 }
 
+/* Standalone transforms of a large batch held in pageable memory: the wire slots and the host
+ * pool as a parallel stager (copy in -> H2D -> transform in place -> D2H -> copy out), the same
+ * state machine as polymul_batch_wire with one array. */
+static int ntt_batch_staged(nttb200_plan *P, int transform, int32_t *a, size_t batch) {
+  int rc = ensure_wire_slots(P);
+  if (rc) return rc;
+  const size_t n = P->n, nsl = P->wslots.size();
+  size_t next = 0, busy = 0;
+  nttb200_wire_begin();
+  while (next < batch || busy > 0) {
+    bool progress = false;
+    for (size_t i = 0; i < nsl && !rc; i++) {
+      WireSlot &s = P->wslots[i];
+      const size_t bytes = s.rows * n * sizeof(uint32_t);
+      if (s.state == WS_STAGING && nttb200_wire_done(s.job_a)) {
+        cudaError_t e = cudaMemcpyAsync(s.d_a, s.h_a, bytes, cudaMemcpyHostToDevice, s.stream);
+        if (e == cudaSuccess) {
+          rc = transform_dev(P, transform, s.d_a, s.rows, s.stream);
+          if (!rc) e = cudaMemcpyAsync(s.h_c, s.d_a, bytes, cudaMemcpyDeviceToHost, s.stream);
+          if (!rc && e == cudaSuccess) e = cudaEventRecord(s.done, s.stream);
+        }
+        if (!rc && e != cudaSuccess) rc = nttb200_fail(NTTB200_ECUDA, "staged transform: %s", cudaGetErrorString(e));
+        s.state = WS_INFLIGHT;
+        progress = true;
+      } else if (s.state == WS_INFLIGHT) {
+        const cudaError_t e = cudaEventQuery(s.done);
+        if (e == cudaSuccess) {
+          s.job_c = nttb200_wire_post_copy(a + s.row0 * n, (const int32_t *)s.h_c, s.rows * n, 1);
+          s.state = WS_WIDENING;
+          progress = true;
+        } else if (e != cudaErrorNotReady) {
+          rc = nttb200_fail(NTTB200_ECUDA, "staged transform: %s", cudaGetErrorString(e));
+        }
+      } else if (s.state == WS_WIDENING && nttb200_wire_done(s.job_c)) {
+        s.state = WS_FREE;
+        busy--;
+        progress = true;
+      }
+    }
+    if (rc) break;
+    if (next < batch) {
+      for (size_t i = 0; i < nsl; i++) {
+        WireSlot &s = P->wslots[i];
+        if (s.state != WS_FREE) continue;
+        s.row0 = next;
+        s.rows = std::min(P->wire_polys, batch - next);
+        next += s.rows;
+        busy++;
+        s.job_a = nttb200_wire_post_copy((int32_t *)s.h_a, a + s.row0 * n, s.rows * n, 0);
+        s.state = WS_STAGING;
+        progress = true;
+        break;
+      }
+    }
+    if (!progress) nttb200_wire_help();
+  }
+  if (rc) {
+    for (auto &s : P->wslots) {
+      if (s.state == WS_STAGING) nttb200_wire_wait(s.job_a);
+      if (s.state == WS_WIDENING) nttb200_wire_wait(s.job_c);
+      cudaStreamSynchronize(s.stream);
+      s.state = WS_FREE;
+    }
+  }
+  nttb200_wire_end();
+  return rc;
+}
+
 extern "C" int nttb200_ntt_batch(nttb200_plan *P, int transform, int32_t *a, size_t batch) {
   if (!P || !a) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
   g_launches = 0;
@@ -858,6 +926,8 @@ extern "C" int nttb200_ntt_batch(nttb200_plan *P, int transform, int32_t *a, siz
   int rc = ensure_slots(P, false);
   if (rc) return rc;
   const size_t n = P->n;
+  if (batch * n >= WIRE_MIN_WORDS && env_int("NTTB200_STAGE_PAGEABLE", 1, 0, 1) && !is_pinned(a))
+    return ntt_batch_staged(P, transform, a, batch);
   size_t k = 0;
   for (size_t done = 0; done < batch; done += P->slot_polys, k++) {
     HostSlot &s = P->slots[k % NSLOT];

@@ -757,3 +757,23 @@ def test_host_buffer_call_equals_device_resident_call_on_a_large_batch(gpu, orac
     idx = np.unique(np.r_[0:4, batch - 4:batch, np.random.default_rng(3).integers(0, batch, 120)])
     assert (got[idx] == oracle.product(n, q, a[idx], b[idx], 10)).all()
     p.close()
+
+
+@pytest.mark.parametrize("n,q,batch", [(256, 12289, 5003), (1024, 8380417, 700), (4096, 2013265921, 301)])
+def test_batch_transforms_from_pageable_memory_are_staged_by_the_pool(gpu, oracle, loader, n, q, batch, monkeypatch):
+    """nttb200_ntt_batch on a large pageable array: the host pool stages the rows through pinned
+    memory; same output as the plain DMA ring, forward then scaled inverse is the identity, and
+    sampled rows of the forward transform equal the oracle's."""
+    p = gpu.Plan(n, q)
+    a = oracle.random((batch, n), q, 77 + batch)
+    monkeypatch.setenv("NTTB200_STAGE_PAGEABLE", "0")
+    ref = p.transform("mulntt_std2rev", a)
+    monkeypatch.setenv("NTTB200_STAGE_PAGEABLE", "1")
+    got = p.transform("mulntt_std2rev", a)
+    assert (got == ref).all()
+    back = p.transform("inttmul_rev2std_scaled", got)
+    assert (back == a).all()
+    idx = np.unique(np.r_[0:3, batch - 3:batch, np.random.default_rng(5).integers(0, batch, 20)])
+    want = oracle.transform("mulntt_ct_std2rev", a[idx], oracle.table(loader.MIXED_POWERS_REV, n, q, p.psi), q)
+    assert (got[idx] == want).all()
+    p.close()
