@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NTTB200_VERSION 100
+#define NTTB200_VERSION 200
 
 /* ---- error codes (0 = OK).  The reference functions are `void` and abort on
  * violated preconditions (assert in R/NTT-RED/ntt_red.c:42,79,94); the nttb200_*
@@ -180,8 +180,13 @@ enum nttb200_dataflow {
   NTTB200_DF_CT_REV2STD = 2,    /* R/NTT/ntt.C:216-278  (ntt_ct_rev2std, mulntt_ct_rev2std)   */
   NTTB200_DF_GS_STD2REV = 3     /* R/NTT/ntt.C:467-525  (ntt_gs_std2rev, nttmul_gs_std2rev)   */
 };
-int nttb200_ntt_table_batch(uint32_t n, uint32_t q, int dataflow, const uint32_t *p, int32_t *a,
-                            size_t batch);
+/* skip_j0 = 1: the UN-MERGED entry points (ntt_ct_std2rev, ntt_ct_rev2std, ntt_gs_std2rev,
+ * ntt_gs_rev2std), which peel the j = 0 block -- its butterflies run without a multiplication
+ * and p[t] is never read (R/NTT/ntt.C:226-231, 313-317, 401-405, 477-481); 0: the psi-merged
+ * ones (mulntt_ct_*, nttmul_gs_*), which multiply every block by p[t+j].  With the reference's
+ * own tables (p[t] = 1) the two coincide. */
+int nttb200_ntt_table_batch(uint32_t n, uint32_t q, int dataflow, int skip_j0, const uint32_t *p,
+                            int32_t *a, size_t batch);
 
 /* ---- exact emulation of the Longa-Naehrig ("RED") surface, q = 12289 hard-wired as in the
  * reference (R/NTT-RED/ntt_red.c:24): signed, UNREDUCED 32-bit outputs, bit-identical to
@@ -224,6 +229,12 @@ enum nttb200_table {
 };
 /* fills out[0..n) */
 int nttb200_make_table(int kind, uint32_t n, uint32_t q, uint32_t psi, uint32_t *out);
+/* The Longa-Naehrig table set (R/NTT-RED/ntt_red256_tables.c:16-469), q = 12289: the table of the
+ * same `kind` times 3^-1, centred to (-q/2, q/2]; SCALED_INV_PSI_POWERS carries n^-1 3^-8
+ * (ntt_red256_tables.h:28, rescale8 = 8822 at n = 256) and the extra kind below n^-1 3^-6
+ * (rescale6 = 5664).  fills out[0..n) */
+#define NTTB200_RED_SCALED_INV_PSI_POWERS_VAR 100
+int nttb200_make_red_table(int kind, uint32_t n, uint32_t psi, int32_t *out);
 uint32_t nttb200_find_psi(uint32_t n, uint32_t q);     /* smallest primitive 2n-th root, 0 if none */
 uint32_t nttb200_find_omega(uint32_t n, uint32_t q);   /* smallest primitive n-th root, 0 if none  */
 int nttb200_is_prime(uint32_t q);

@@ -76,6 +76,24 @@ void nttmul_red_gs_rev2std(int32_t *a, uint32_t n, const int16_t *p);          /
 void ntt_red_gs_std2rev(int32_t *a, uint32_t n, const int16_t *p);             /* ntt_red.c:495-520 */
 void nttmul_red_gs_std2rev(int32_t *a, uint32_t n, const int16_t *p);          /* ntt_red.c:534-554 */
 
+/* ---- the n = 256 tables, under the reference's names (R/NTT/ntt256_tables.h:29-44,
+ * R/NTT-RED/ntt_red256_tables.h:34-51): read-only data of libnttb200.so, generated at build time
+ * from the closed forms (csrc/gen_legacy_tables.c), so that the reference's header-only
+ * wrappers -- ntt256_ct_std2rev(a) = ntt_ct_std2rev(a, 256, ntt256_omega_powers_rev) etc.,
+ * ntt256.h:20-69, ntt_red256.h:21-70 -- link against this library alone.  The scalar
+ * parameters (psi = 1002 ... rescale8 = 8822) are `static const` in the reference headers. */
+extern const uint16_t ntt256_psi_powers[256], ntt256_inv_psi_powers[256], ntt256_scaled_inv_psi_powers[256];
+extern const uint16_t ntt256_omega_powers[256], ntt256_omega_powers_rev[256];
+extern const uint16_t ntt256_inv_omega_powers[256], ntt256_inv_omega_powers_rev[256];
+extern const uint16_t ntt256_mixed_powers[256], ntt256_mixed_powers_rev[256];
+extern const uint16_t ntt256_inv_mixed_powers[256], ntt256_inv_mixed_powers_rev[256];
+extern const int16_t ntt_red256_psi_powers[256], ntt_red256_inv_psi_powers[256];
+extern const int16_t ntt_red256_scaled_inv_psi_powers[256], ntt_red256_scaled_inv_psi_powers_var[256];
+extern const int16_t ntt_red256_omega_powers[256], ntt_red256_omega_powers_rev[256];
+extern const int16_t ntt_red256_inv_omega_powers[256], ntt_red256_inv_omega_powers_rev[256];
+extern const int16_t ntt_red256_mixed_powers[256], ntt_red256_mixed_powers_rev[256];
+extern const int16_t ntt_red256_inv_mixed_powers[256], ntt_red256_inv_mixed_powers_rev[256];
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,3 +11,4 @@ from .capi import (  # noqa: F401
     find_psi, find_omega, is_prime, host_alloc, measure_int_peak, last_launch_count,
     TRANSFORMS, DATAFLOWS, TABLES, ntt_table_batch, legacy, MultiPlan, shard_bounds,
 )
+from . import inputs  # noqa: F401,E402

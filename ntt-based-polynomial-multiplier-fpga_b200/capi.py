@@ -73,10 +73,11 @@ def lib() -> C.CDLL:
                                           C.POINTER(C.c_ulonglong), C.POINTER(C.c_int)]
     L.nttb200_ntt_batch.argtypes = [vp, C.c_int, i32p, sz]
     L.nttb200_ntt_batch_dev.argtypes = [vp, C.c_int, i32p, sz, vp]
-    L.nttb200_ntt_table_batch.argtypes = [C.c_uint32, C.c_uint32, C.c_int, u32p, i32p, sz]
+    L.nttb200_ntt_table_batch.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int, u32p, i32p, sz]
     L.nttb200_mul_array_batch.argtypes = [vp, i32p, i32p, i32p, sz]
     L.nttb200_scalar_mul_array_batch.argtypes = [vp, i32p, C.c_int32, sz]
     L.nttb200_make_table.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, u32p]
+    L.nttb200_make_red_table.argtypes = [C.c_int, C.c_uint32, C.c_uint32, i32p]
     L.nttb200_find_psi.argtypes = [C.c_uint32, C.c_uint32]
     L.nttb200_find_psi.restype = C.c_uint32
     L.nttb200_find_omega.argtypes = [C.c_uint32, C.c_uint32]
@@ -319,10 +320,13 @@ class Plan:
         _check(lib().nttb200_polymul_batch(self._h, c_ptr, a_ptr, b_ptr, batch))
 
 
-def ntt_table_batch(n: int, q: int, dataflow: str, table: np.ndarray, a: np.ndarray) -> np.ndarray:
+def ntt_table_batch(n: int, q: int, dataflow: str, table: np.ndarray, a: np.ndarray,
+                    skip_j0: bool = False) -> np.ndarray:
+    """skip_j0: the un-merged reference entry points (ntt_ct_*, ntt_gs_*), which do the j = 0
+    butterflies without a multiplication and never read p[t] (R/NTT/ntt.C:313-317)."""
     x = np.ascontiguousarray(a, dtype=np.int32).reshape(-1, n).copy()
     p = np.ascontiguousarray(table, dtype=np.uint32)
-    _check(lib().nttb200_ntt_table_batch(n, q, DATAFLOWS[dataflow], _ptr(p), _ptr(x), x.shape[0]))
+    _check(lib().nttb200_ntt_table_batch(n, q, DATAFLOWS[dataflow], int(skip_j0), _ptr(p), _ptr(x), x.shape[0]))
     return x
 
 

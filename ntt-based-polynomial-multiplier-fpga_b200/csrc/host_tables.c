@@ -122,3 +122,27 @@ int nttb200_make_table(int kind, uint32_t n, uint32_t q, uint32_t psi, uint32_t 
     default: return NTTB200_EPARAM;
   }
 }
+
+/* ---- Longa-Naehrig ("RED") table set, q = 12289 = 3 * 2^12 + 1 (R/NTT-RED/ntt_red256_tables.c:16-469,
+ * SURVEY 8a-T): the NTT/ table of the same kind times 3^-1 mod q -- every mul_red() leaves a factor
+ * 3 -- centred to (-q/2, q/2]; scaled_inv_psi_powers carries n^-1 3^-8 (the eight red()s of the
+ * product, ntt_red256_tables.h:28 rescale8) and its _var twin n^-1 3^-6 (rescale6).  p[0] of the
+ * level tables stays 0. */
+#define RED_Q 12289u
+int nttb200_make_red_table(int kind, uint32_t n, uint32_t psi, int32_t *out) {
+  if (!out || n < 2 || (n & (n - 1)) || n > 65536) return NTTB200_EPARAM;
+  const uint32_t inv3 = ht_invmod(3, RED_Q);
+  uint32_t scale = inv3;
+  int base = kind;
+  if (kind == NTTB200_SCALED_INV_PSI_POWERS) scale = ht_powmod(inv3, 8, RED_Q);
+  if (kind == NTTB200_RED_SCALED_INV_PSI_POWERS_VAR) { scale = ht_powmod(inv3, 6, RED_Q); base = NTTB200_SCALED_INV_PSI_POWERS; }
+  uint32_t *u = (uint32_t *)out;                     /* same size: fill in place, then re-centre */
+  const int rc = nttb200_make_table(base, n, RED_Q, psi, u);
+  if (rc) return rc;
+  const int level = (base >= NTTB200_OMEGA_POWERS && base <= NTTB200_INV_MIXED_POWERS_REV);
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t v = (uint32_t)((uint64_t)u[i] * scale % RED_Q);
+    out[i] = (level && i == 0) ? 0 : (v > (RED_Q - 1) / 2 ? (int32_t)v - (int32_t)RED_Q : (int32_t)v);
+  }
+  return 0;
+}

@@ -47,11 +47,11 @@ void ntt_red256_product1(int32_t *c, int32_t *a, int32_t *b) { product(c, a, b, 
 void ntt_red256_product4(int32_t *c, int32_t *a, int32_t *b) { product(c, a, b, 0); }
 
 /* caller's 16-bit table -> the ABI's 32-bit table */
-static void table_transform(int32_t *a, uint32_t n, const uint16_t *p, int dataflow) {
+static void table_transform(int32_t *a, uint32_t n, const uint16_t *p, int dataflow, int skip_j0) {
   uint32_t *p32 = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
   if (!p32) die("malloc");
   for (uint32_t i = 0; i < n; i++) p32[i] = p[i];
-  int rc = nttb200_ntt_table_batch(n, LEGACY_Q, dataflow, p32, a, 1);
+  int rc = nttb200_ntt_table_batch(n, LEGACY_Q, dataflow, skip_j0, p32, a, 1);
   free(p32);
   if (rc != 0) die("nttb200_ntt_table_batch");
 }
@@ -62,22 +62,22 @@ void ntt_ct_rev2std_v1(int32_t *a, uint32_t n, const uint16_t *p) {
   uint32_t *lvl = (uint32_t *)calloc(n ? n : 1, sizeof(uint32_t));
   if (!lvl) die("calloc");
   for (uint32_t t = 1, l = n; t < n; t <<= 1, l >>= 1)
-    for (uint32_t j = 0; j < t; j++) lvl[t + j] = j ? p[j * l] : 1u;
-  int rc = nttb200_ntt_table_batch(n, LEGACY_Q, NTTB200_DF_CT_REV2STD, lvl, a, 1);
+    for (uint32_t j = 1; j < t; j++) lvl[t + j] = p[j * l];   /* j = 0 is peeled: p[0] is never read */
+  int rc = nttb200_ntt_table_batch(n, LEGACY_Q, NTTB200_DF_CT_REV2STD, 1, lvl, a, 1);
   free(lvl);
   if (rc != 0) die("nttb200_ntt_table_batch");
 }
-/* The un-merged entry points skip the multiply of the j = 0 block (twiddle 1,
- * R/NTT/ntt.C:313-317); their tables hold p[t] = 1 there, so running the merged dataflow
- * with the caller's table gives the same canonical values. */
-void ntt_ct_rev2std(int32_t *a, uint32_t n, const uint16_t *p)    { table_transform(a, n, p, NTTB200_DF_CT_REV2STD); }
-void mulntt_ct_rev2std(int32_t *a, uint32_t n, const uint16_t *p) { table_transform(a, n, p, NTTB200_DF_CT_REV2STD); }
-void ntt_ct_std2rev(int32_t *a, uint32_t n, const uint16_t *p)    { table_transform(a, n, p, NTTB200_DF_CT_STD2REV); }
-void mulntt_ct_std2rev(int32_t *a, uint32_t n, const uint16_t *p) { table_transform(a, n, p, NTTB200_DF_CT_STD2REV); }
-void ntt_gs_rev2std(int32_t *a, uint32_t n, const uint16_t *p)    { table_transform(a, n, p, NTTB200_DF_GS_REV2STD); }
-void nttmul_gs_rev2std(int32_t *a, uint32_t n, const uint16_t *p) { table_transform(a, n, p, NTTB200_DF_GS_REV2STD); }
-void ntt_gs_std2rev(int32_t *a, uint32_t n, const uint16_t *p)    { table_transform(a, n, p, NTTB200_DF_GS_STD2REV); }
-void nttmul_gs_std2rev(int32_t *a, uint32_t n, const uint16_t *p) { table_transform(a, n, p, NTTB200_DF_GS_STD2REV); }
+/* The un-merged entry points peel the j = 0 block: its butterflies run without a multiplication
+ * and p[t] is never read (R/NTT/ntt.C:226-231, 313-317, 401-405, 477-481) -- skip_j0 = 1; the
+ * psi-merged ones multiply every block by the caller's p[t+j]. */
+void ntt_ct_rev2std(int32_t *a, uint32_t n, const uint16_t *p)    { table_transform(a, n, p, NTTB200_DF_CT_REV2STD, 1); }
+void mulntt_ct_rev2std(int32_t *a, uint32_t n, const uint16_t *p) { table_transform(a, n, p, NTTB200_DF_CT_REV2STD, 0); }
+void ntt_ct_std2rev(int32_t *a, uint32_t n, const uint16_t *p)    { table_transform(a, n, p, NTTB200_DF_CT_STD2REV, 1); }
+void mulntt_ct_std2rev(int32_t *a, uint32_t n, const uint16_t *p) { table_transform(a, n, p, NTTB200_DF_CT_STD2REV, 0); }
+void ntt_gs_rev2std(int32_t *a, uint32_t n, const uint16_t *p)    { table_transform(a, n, p, NTTB200_DF_GS_REV2STD, 1); }
+void nttmul_gs_rev2std(int32_t *a, uint32_t n, const uint16_t *p) { table_transform(a, n, p, NTTB200_DF_GS_REV2STD, 0); }
+void ntt_gs_std2rev(int32_t *a, uint32_t n, const uint16_t *p)    { table_transform(a, n, p, NTTB200_DF_GS_STD2REV, 1); }
+void nttmul_gs_std2rev(int32_t *a, uint32_t n, const uint16_t *p) { table_transform(a, n, p, NTTB200_DF_GS_STD2REV, 0); }
 
 /* elementwise: a length-n array is one row of an n-coefficient "plan"; these ops do not
  * use the plan's roots, only its modulus, so any n is served through the 256-plan by

@@ -22,10 +22,19 @@ enum { DF_CT_STD2REV = 0, DF_GS_REV2STD = 1, DF_CT_REV2STD = 2, DF_GS_STD2REV = 
  *   twiddle p[(n/2)/half + j].
  * Offset-indexed dataflows (2,3): pair index b -> j = b % half, s = 2*half*(b/half) + j,
  *   twiddle p[half + j]. */
+/* The j = 0 butterfly of the reference's UN-MERGED entry points (ntt_ct_*, ntt_gs_*; e.g.
+ * R/NTT/ntt.C:313-317, 401-405): no multiplication and p[t] is never read -- the same for the
+ * CT and the GS family: (X, Y) -> (X + Y, X - Y), canonical in and out. */
+__device__ __forceinline__ void plain_bfly(uint32_t &X, uint32_t &Y, const ModQ &m) {
+  const uint32_t s = X + Y, d = X - Y;
+  X = csub(s, m.q);
+  Y = min(d, d + m.q);
+}
+
 template <int DF>
 __global__ void __launch_bounds__(256)
 generic_stage_kernel(uint32_t *data, const uint2 *tab, uint32_t n, uint32_t logn, uint32_t half,
-                     uint32_t loghalf, unsigned long long total_pairs, ModQ m) {
+                     uint32_t loghalf, unsigned long long total_pairs, ModQ m, int skip0) {
   unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned long long gstride = (unsigned long long)gridDim.x * blockDim.x;
   for (; gid < total_pairs; gid += gstride) {
@@ -33,13 +42,14 @@ generic_stage_kernel(uint32_t *data, const uint2 *tab, uint32_t n, uint32_t logn
     const uint32_t b = (uint32_t)(gid & ((n >> 1) - 1));
     const uint32_t hi_part = b >> loghalf, lo_part = b & (half - 1);
     const uint32_t s = (hi_part << (loghalf + 1)) | lo_part;
-    uint32_t tidx;
-    if (DF == DF_CT_STD2REV || DF == DF_GS_REV2STD) tidx = ((n >> 1) >> loghalf) + hi_part;
-    else tidx = half + lo_part;
+    uint32_t tidx, j;
+    if (DF == DF_CT_STD2REV || DF == DF_GS_REV2STD) { j = hi_part; tidx = ((n >> 1) >> loghalf) + hi_part; }
+    else { j = lo_part; tidx = half + lo_part; }
     const uint2 w = __ldg(tab + tidx);
     uint32_t *px = data + (poly << logn) + s;
     uint32_t X = px[0], Y = px[half];
-    if (DF == DF_CT_STD2REV || DF == DF_CT_REV2STD) ct_bfly<ARITH_CANON>(X, Y, w.x, w.y, m);
+    if (skip0 && j == 0) plain_bfly(X, Y, m);
+    else if (DF == DF_CT_STD2REV || DF == DF_CT_REV2STD) ct_bfly<ARITH_CANON>(X, Y, w.x, w.y, m);
     else gs_bfly<ARITH_CANON>(X, Y, w.x, w.y, m, 0u);
     px[0] = X;
     px[half] = Y;
@@ -107,7 +117,8 @@ literal_cta_kernel(uint32_t *data, const uint2 *tab, const int32_t *rtab, uint32
         if (!RED) {
           const uint2 w = stab[tidx];
           uint32_t X = sx[p0], Y = sx[p0 + half];
-          if (DF == DF_CT_STD2REV || DF == DF_CT_REV2STD) ct_bfly<ARITH_CANON>(X, Y, w.x, w.y, m);
+          if (skip0 && j == 0) plain_bfly(X, Y, m);
+          else if (DF == DF_CT_STD2REV || DF == DF_CT_REV2STD) ct_bfly<ARITH_CANON>(X, Y, w.x, w.y, m);
           else gs_bfly<ARITH_CANON>(X, Y, w.x, w.y, m, 0u);
           sx[p0] = X;
           sx[p0 + half] = Y;

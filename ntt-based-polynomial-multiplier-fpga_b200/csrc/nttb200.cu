@@ -287,7 +287,7 @@ static int current_sms() {
 }
 
 int launch_generic_transform(uint32_t n, uint32_t logn, const ModQ &m, int dataflow, const uint2 *d_tab,
-                             uint32_t *a, size_t batch, cudaStream_t st) {
+                             uint32_t *a, size_t batch, cudaStream_t st, int skip0) {
   using namespace nttb200;
   const unsigned long long pairs = (unsigned long long)batch * (n / 2);
   const int grid = grid_1d(pairs, 256, current_sms());
@@ -296,10 +296,10 @@ int launch_generic_transform(uint32_t n, uint32_t logn, const ModQ &m, int dataf
     const uint32_t lh = descending ? (logn - 1 - s) : s;
     const uint32_t half = 1u << lh;
     switch (dataflow) {
-      case DF_CT_STD2REV: generic_stage_kernel<DF_CT_STD2REV><<<grid, 256, 0, st>>>(a, d_tab, n, logn, half, lh, pairs, m); break;
-      case DF_GS_REV2STD: generic_stage_kernel<DF_GS_REV2STD><<<grid, 256, 0, st>>>(a, d_tab, n, logn, half, lh, pairs, m); break;
-      case DF_CT_REV2STD: generic_stage_kernel<DF_CT_REV2STD><<<grid, 256, 0, st>>>(a, d_tab, n, logn, half, lh, pairs, m); break;
-      case DF_GS_STD2REV: generic_stage_kernel<DF_GS_STD2REV><<<grid, 256, 0, st>>>(a, d_tab, n, logn, half, lh, pairs, m); break;
+      case DF_CT_STD2REV: generic_stage_kernel<DF_CT_STD2REV><<<grid, 256, 0, st>>>(a, d_tab, n, logn, half, lh, pairs, m, skip0); break;
+      case DF_GS_REV2STD: generic_stage_kernel<DF_GS_REV2STD><<<grid, 256, 0, st>>>(a, d_tab, n, logn, half, lh, pairs, m, skip0); break;
+      case DF_CT_REV2STD: generic_stage_kernel<DF_CT_REV2STD><<<grid, 256, 0, st>>>(a, d_tab, n, logn, half, lh, pairs, m, skip0); break;
+      case DF_GS_STD2REV: generic_stage_kernel<DF_GS_STD2REV><<<grid, 256, 0, st>>>(a, d_tab, n, logn, half, lh, pairs, m, skip0); break;
       default: return nttb200_fail(NTTB200_EPARAM, "unknown dataflow %d", dataflow);
     }
     nttb200_count_launch(1);
@@ -1041,8 +1041,8 @@ static int literal_cta_launch(int dataflow, uint32_t *d_a, const uint2 *d_tab, c
 }
 
 /* Table-driven transform: the literal reference dataflow with the caller's table. */
-extern "C" int nttb200_ntt_table_batch(uint32_t n, uint32_t q, int dataflow, const uint32_t *p, int32_t *a,
-                                       size_t batch) {
+extern "C" int nttb200_ntt_table_batch(uint32_t n, uint32_t q, int dataflow, int skip_j0, const uint32_t *p,
+                                       int32_t *a, size_t batch) {
   if (!p || !a) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
   if (n < 2 || (n & (n - 1)) || q < 3 || q >= (1u << 31) || !(q & 1))
     return nttb200_fail(NTTB200_EPARAM, "bad (n=%u, q=%u)", n, q);
@@ -1069,7 +1069,7 @@ extern "C" int nttb200_ntt_table_batch(uint32_t n, uint32_t q, int dataflow, con
       memcpy(h_tab, h.data(), n * sizeof(uint2));
       memcpy(h_a, a, bytes);
       int rc0 = literal_cta_launch<false>(dataflow, (uint32_t *)(g_zc.d + n * sizeof(uint2)), (const uint2 *)g_zc.d,
-                                          nullptr, n, batch, m, 0, g_zc.st);
+                                          nullptr, n, batch, m, skip_j0 ? 1 : 0, g_zc.st);
       if (rc0) return rc0;
       NTT_CUDA(cudaStreamSynchronize(g_zc.st));
       memcpy(a, h_a, bytes);
@@ -1083,7 +1083,7 @@ extern "C" int nttb200_ntt_table_batch(uint32_t n, uint32_t q, int dataflow, con
   if (e == cudaSuccess) e = cudaMalloc(&d_a, bytes);
   if (e == cudaSuccess) e = cudaMemcpy(d_tab, h.data(), n * sizeof(uint2), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(d_a, a, bytes, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) rc = launch_generic_transform(n, ht_log2(n), m, dataflow, d_tab, d_a, batch, 0);
+  if (e == cudaSuccess) rc = launch_generic_transform(n, ht_log2(n), m, dataflow, d_tab, d_a, batch, 0, skip_j0 ? 1 : 0);
   if (e == cudaSuccess && rc == 0) e = cudaMemcpy(a, d_a, bytes, cudaMemcpyDeviceToHost);
   cudaFree(d_tab);
   cudaFree(d_a);

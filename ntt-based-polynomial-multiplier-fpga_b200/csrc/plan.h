@@ -114,7 +114,7 @@ int launch_polymul_small(const nttb200_plan *P, uint32_t *c, const uint32_t *a, 
 int launch_ntt_small(const nttb200_plan *P, const DevTable &tab, int dir, int scale, uint32_t *a,
                      size_t batch, cudaStream_t st);
 int launch_generic_transform(uint32_t n, uint32_t logn, const ModQ &m, int dataflow, const uint2 *d_tab,
-                             uint32_t *a, size_t batch, cudaStream_t st);
+                             uint32_t *a, size_t batch, cudaStream_t st, int skip0 = 0);
 int launch_pointwise(uint32_t *c, const uint32_t *a, const uint32_t *b, size_t count, const ModQ &m,
                      uint32_t r2, cudaStream_t st);
 int launch_scale(uint32_t *a, const uint2 *d_tab, uint2 sc, uint32_t n, size_t count, const ModQ &m,

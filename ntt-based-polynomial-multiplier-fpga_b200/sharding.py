@@ -29,8 +29,6 @@ def init_distributed(backend: str):
     # bench.py prints exactly one JSON line on stdout: keep NCCL's "NCCL version ..." banner
     # (printed at NCCL_DEBUG=VERSION and at WARN) out of it; whatever NCCL has to say goes to stderr
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    if not os.environ.get("NTTB200_KEEP_NCCL_DEBUG"):
-        os.environ.pop("NCCL_DEBUG", None)
     if world > 1 and not dist.is_initialized():
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return dist

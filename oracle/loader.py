@@ -234,6 +234,36 @@ class Reference:
         L.ref_bench_loop.restype = C.c_double
         L.ref_bench_loop.argtypes = [C.c_int, _i32p, _i32p, C.c_size_t, C.c_double,
                                      C.POINTER(C.c_uint64)]
+        if hasattr(L, "ref_transform_tab"):
+            L.ref_transform_tab.argtypes = [C.c_int, _i32p, C.c_uint32,
+                                            np.ctypeslib.ndpointer(dtype=np.uint16, flags="C_CONTIGUOUS")]
+            L.ref_red_transform_tab.argtypes = [C.c_int, _i32p, C.c_uint32,
+                                                np.ctypeslib.ndpointer(dtype=np.int16, flags="C_CONTIGUOUS")]
+
+    # ids of ref_transform_tab / ref_red_transform_tab -> reference function name
+    TAB_IDS = {0: "ntt_ct_rev2std_v1", 1: "ntt_ct_rev2std", 2: "mulntt_ct_rev2std", 3: "ntt_ct_std2rev",
+               4: "mulntt_ct_std2rev", 5: "ntt_gs_rev2std", 6: "nttmul_gs_rev2std", 7: "ntt_gs_std2rev",
+               8: "nttmul_gs_std2rev"}
+
+    def transform_tab(self, tid: int, a: np.ndarray, p: np.ndarray, red: bool = False) -> np.ndarray:
+        """The generic reference entry point `tid` (TAB_IDS) run with the caller's table."""
+        a = np.ascontiguousarray(a, dtype=np.int32).copy()
+        n = a.shape[-1]
+        p = np.ascontiguousarray(p, dtype=np.int16 if red else np.uint16)
+        fn = self.lib.ref_red_transform_tab if red else self.lib.ref_transform_tab
+        for row in a.reshape(-1, n):
+            if fn(tid, row, n, p) != 0:
+                raise ValueError("bad transform id")
+        return a
+
+    def product_post_state(self, a: np.ndarray, b: np.ndarray, variant: int):
+        """(c, a_after, b_after) of ONE reference product call (the operands are modified)."""
+        a = np.ascontiguousarray(a, dtype=np.int32).copy()
+        b = np.ascontiguousarray(b, dtype=np.int32).copy()
+        c = np.zeros(256, dtype=np.int32)
+        if self.lib.ref_product(variant, c, a, b) != 0:
+            raise ValueError("bad variant")
+        return c, a, b
 
     def product(self, a: np.ndarray, b: np.ndarray, variant: int) -> np.ndarray:
         a = np.ascontiguousarray(a, dtype=np.int32).reshape(-1, 256)

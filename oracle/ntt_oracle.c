@@ -166,16 +166,27 @@ void orc_bitrev_shuffle(int32_t *a, uint32_t n) {
 }
 
 /* ------------------------------------------------------------------------- */
-/* transforms.  The reference's un-merged variants peel the j=0 block (twiddle */
-/* 1) and skip its multiply (e.g. ntt.C:313-317); multiplying by the table's   */
-/* p[t]=1 gives the same canonical value, so each dataflow is stated once and  */
-/* shared by the plain and the psi-merged entry points.                        */
+/* transforms.  The reference's un-merged variants peel the j=0 block and do   */
+/* its butterflies WITHOUT a multiplication and without reading p[t]           */
+/* (ntt.C:178-183, 226-231, 313-317, 401-405, 477-481); the psi-merged ones    */
+/* multiply every block by p[t+j].  With the reference's own tables p[t] = 1   */
+/* and the two agree; with a caller's table they do not, so each dataflow      */
+/* takes `peel0` and the un-merged entry points pass 1.                        */
 /* ------------------------------------------------------------------------- */
 
 /* CT butterfly (ntt.C:323-326): x = a[hi]*w; a[hi] = a[lo]-x; a[lo] = a[lo]+x */
 #define CT_BFLY(lo, hi, w)                      \
   do {                                          \
     int32_t x_ = mul_q(a[hi], (w), q);          \
+    int32_t u_ = a[lo];                         \
+    a[hi] = sub_q(u_, x_, q);                   \
+    a[lo] = add_q(u_, x_, q);                   \
+  } while (0)
+/* the peeled j=0 butterfly of both families (e.g. ntt.C:313-317, 401-405):
+ * x = a[hi]; a[hi] = a[lo]-x; a[lo] = a[lo]+x */
+#define PLAIN_BFLY(lo, hi)                      \
+  do {                                          \
+    int32_t x_ = a[hi];                         \
     int32_t u_ = a[lo];                         \
     a[hi] = sub_q(u_, x_, q);                   \
     a[lo] = add_q(u_, x_, q);                   \
@@ -193,58 +204,78 @@ void orc_bitrev_shuffle(int32_t *a, uint32_t n) {
 void orc_ntt_ct_rev2std_v1(int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) {
   for (uint32_t t = 1, l = n; t < n; t <<= 1, l >>= 1)
     for (uint32_t j = 0; j < t; j++) {
-      uint32_t w = (j == 0) ? 1u : p[j * l];
+      if (j == 0) {                                          /* ntt.C:178-183: p[0] is not read */
+        for (uint32_t s = 0; s < n; s += 2 * t) PLAIN_BFLY(s, s + t);
+        continue;
+      }
+      uint32_t w = p[j * l];
       for (uint32_t s = j; s < n; s += 2 * t) CT_BFLY(s, s + t, w);
     }
 }
 /* ntt.C:216-243 (plain) and ntt.C:253-278 (psi-merged): w = p[t+j], j = offset in block */
-static void ct_rev2std(int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) {
+static void ct_rev2std(int32_t *a, uint32_t n, const uint32_t *p, uint32_t q, int peel0) {
   for (uint32_t t = 1; t < n; t <<= 1)
     for (uint32_t j = 0; j < t; j++) {
+      if (peel0 && j == 0) {                                 /* ntt.C:226-231 */
+        for (uint32_t s = 0; s < n; s += 2 * t) PLAIN_BFLY(s, s + t);
+        continue;
+      }
       uint32_t w = p[t + j];
       for (uint32_t s = j; s < n; s += 2 * t) CT_BFLY(s, s + t, w);
     }
 }
 /* ntt.C:295-329 (plain) and ntt.C:342-371 (psi-merged): w = p[t+j], j = block index,
  * block j spans [2dj, 2dj+2d), d = n/2t */
-static void ct_std2rev(int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) {
+static void ct_std2rev(int32_t *a, uint32_t n, const uint32_t *p, uint32_t q, int peel0) {
   uint32_t d = n;
   for (uint32_t t = 1; t < n; t <<= 1) {
     d >>= 1;
     for (uint32_t j = 0, u = 0; j < t; j++, u += 2 * d) {
+      if (peel0 && j == 0) {                                 /* ntt.C:313-317 */
+        for (uint32_t s = 0; s < d; s++) PLAIN_BFLY(s, s + d);
+        continue;
+      }
       uint32_t w = p[t + j];
       for (uint32_t s = u; s < u + d; s++) CT_BFLY(s, s + d, w);
     }
   }
 }
 /* ntt.C:387-416 (plain) and ntt.C:428-451 (psi-merged) */
-static void gs_rev2std(int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) {
+static void gs_rev2std(int32_t *a, uint32_t n, const uint32_t *p, uint32_t q, int peel0) {
   uint32_t t = n;
   for (uint32_t d = 1; d < n; d <<= 1) {
     t >>= 1;
     for (uint32_t j = 0, u = 0; j < t; j++, u += 2 * d) {
+      if (peel0 && j == 0) {                                 /* ntt.C:401-405 */
+        for (uint32_t s = 0; s < d; s++) PLAIN_BFLY(s, s + d);
+        continue;
+      }
       uint32_t w = p[t + j];
       for (uint32_t s = u; s < u + d; s++) GS_BFLY(s, s + d, w);
     }
   }
 }
 /* ntt.C:467-493 (plain) and ntt.C:505-525 (psi-merged) */
-static void gs_std2rev(int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) {
+static void gs_std2rev(int32_t *a, uint32_t n, const uint32_t *p, uint32_t q, int peel0) {
   for (uint32_t t = n >> 1; t > 0; t >>= 1)
     for (uint32_t j = 0; j < t; j++) {
+      if (peel0 && j == 0) {                                 /* ntt.C:477-481 */
+        for (uint32_t s = 0; s < n; s += 2 * t) PLAIN_BFLY(s, s + t);
+        continue;
+      }
       uint32_t w = p[t + j];
       for (uint32_t s = j; s < n; s += 2 * t) GS_BFLY(s, s + t, w);
     }
 }
 
-void orc_ntt_ct_rev2std   (int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) { ct_rev2std(a, n, p, q); }
-void orc_mulntt_ct_rev2std(int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) { ct_rev2std(a, n, p, q); }
-void orc_ntt_ct_std2rev   (int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) { ct_std2rev(a, n, p, q); }
-void orc_mulntt_ct_std2rev(int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) { ct_std2rev(a, n, p, q); }
-void orc_ntt_gs_rev2std   (int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) { gs_rev2std(a, n, p, q); }
-void orc_nttmul_gs_rev2std(int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) { gs_rev2std(a, n, p, q); }
-void orc_ntt_gs_std2rev   (int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) { gs_std2rev(a, n, p, q); }
-void orc_nttmul_gs_std2rev(int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) { gs_std2rev(a, n, p, q); }
+void orc_ntt_ct_rev2std   (int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) { ct_rev2std(a, n, p, q, 1); }
+void orc_mulntt_ct_rev2std(int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) { ct_rev2std(a, n, p, q, 0); }
+void orc_ntt_ct_std2rev   (int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) { ct_std2rev(a, n, p, q, 1); }
+void orc_mulntt_ct_std2rev(int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) { ct_std2rev(a, n, p, q, 0); }
+void orc_ntt_gs_rev2std   (int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) { gs_rev2std(a, n, p, q, 1); }
+void orc_nttmul_gs_rev2std(int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) { gs_rev2std(a, n, p, q, 0); }
+void orc_ntt_gs_std2rev   (int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) { gs_std2rev(a, n, p, q, 1); }
+void orc_nttmul_gs_std2rev(int32_t *a, uint32_t n, const uint32_t *p, uint32_t q) { gs_std2rev(a, n, p, q, 0); }
 
 /* ------------------------------------------------------------------------- */
 /* plans + products: R/NTT/ntt256.C:5-24                                       */

@@ -90,6 +90,36 @@ int ref_transform(int id, int32_t *a) {
   }
 }
 
+/* the generic entry points with the CALLER's table (ntt.h:71-183, ntt_red.h:174-284): what pins
+ * the j = 0 peel of the un-merged functions, which never read p[t] (ntt.C:313-317 ...) */
+int ref_transform_tab(int id, int32_t *a, uint32_t n, const uint16_t *p) {
+  switch (id) {
+    case 0: ntt_ct_rev2std_v1(a, n, p); return 0;
+    case 1: ntt_ct_rev2std(a, n, p); return 0;
+    case 2: mulntt_ct_rev2std(a, n, p); return 0;
+    case 3: ntt_ct_std2rev(a, n, p); return 0;
+    case 4: mulntt_ct_std2rev(a, n, p); return 0;
+    case 5: ntt_gs_rev2std(a, n, p); return 0;
+    case 6: nttmul_gs_rev2std(a, n, p); return 0;
+    case 7: ntt_gs_std2rev(a, n, p); return 0;
+    case 8: nttmul_gs_std2rev(a, n, p); return 0;
+    default: return -1;
+  }
+}
+int ref_red_transform_tab(int id, int32_t *a, uint32_t n, const int16_t *p) {
+  switch (id) {
+    case 1: ntt_red_ct_rev2std(a, n, p); return 0;
+    case 2: mulntt_red_ct_rev2std(a, n, p); return 0;
+    case 3: ntt_red_ct_std2rev(a, n, p); return 0;
+    case 4: mulntt_red_ct_std2rev(a, n, p); return 0;
+    case 5: ntt_red_gs_rev2std(a, n, p); return 0;
+    case 6: nttmul_red_gs_rev2std(a, n, p); return 0;
+    case 7: ntt_red_gs_std2rev(a, n, p); return 0;
+    case 8: nttmul_red_gs_std2rev(a, n, p); return 0;
+    default: return -1;
+  }
+}
+
 /* tables, by the oracle's enum order (ntt_oracle.h); red != 0 selects the int16 set */
 const void *ref_table(int kind, int red) {
   if (!red) switch (kind) {

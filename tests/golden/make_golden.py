@@ -107,6 +107,30 @@ def main():
         g[f"red_table_{k}"] = R.table(k, red=True)
     g["red_table_100"] = R.table(100, red=True)
     g["params"] = np.array([R.param(i) for i in range(8)], dtype=np.int64)
+    # the generic entry points run with an ARBITRARY caller table (entries in [0, q), p[t] != 1):
+    # pins the j = 0 peel of the un-merged functions (ntt.C:313-317 ...), n = 256 and n = 64
+    rng = np.random.default_rng(20261019)
+    for nn in (256, 64):
+        tab = rng.integers(2, q, size=nn, dtype=np.int64).astype(np.uint16)
+        g[f"arb_table_{nn}"] = tab
+        ain = ra[:8, :nn].copy()
+        g[f"arb_in_{nn}"] = ain
+        for tid in range(9):
+            g[f"arb_transform_{nn}_{tid}"] = R.transform_tab(tid, ain, tab)
+        rtab = (tab.astype(np.int64) % 12289)
+        rtab[rtab > 6144] -= 12289                      # |p| <= 6144 (ntt_red.h:169-173)
+        rtab = rtab.astype(np.int16)
+        g[f"arb_red_table_{nn}"] = rtab
+        rin = ain.copy()
+        rin[rin > 6144] -= q
+        g[f"arb_red_in_{nn}"] = rin
+        for tid in range(1, 9):
+            g[f"arb_red_transform_{nn}_{tid}"] = R.transform_tab(tid, rin, rtab, red=True)
+    # a/b post-state of the optimized products ("a and b are modified", ntt_red256.h:77-86)
+    for v in (101, 104):
+        c1, a1, b1 = R.product_post_state(ra[4], rb[4], v)
+        assert (c1 == rc[4]).all()
+        g[f"clobber_a_after_product{v}"], g[f"clobber_b_after_product{v}"] = a1, b1
     np.savez_compressed(os.path.join(OUT, "ref_256_12289.npz"), **g)
 
     # (6) hardware golden vectors, q = 7681 (PARAM.txt: N, q, w, w_inv, psi, psi_inv, n_inv*R, R)

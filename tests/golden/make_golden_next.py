@@ -69,6 +69,13 @@ def main():
     keep = [ln for ln in out.splitlines() if not ln.startswith("Tempo total")]
     with open(os.path.join(OUT, "time_testing256_stdout.txt"), "w") as f:
         f.write("\n".join(keep) + "\n")
+    # the reference's KAT program NTT/test_prod_ntt256.c, compiled from its own sources
+    exe = os.path.join(ROOT, "oracle", "_ref", "test_prod_ntt256_ref")
+    subprocess.run(["gcc", "-O2", "-I", N256, "-o", exe, "-x", "c", f"{N256}/NTT/test_prod_ntt256.c",
+                    f"{N256}/NTT/ntt.C", f"{N256}/NTT/ntt256.C", f"{N256}/NTT/ntt256_tables.C"], check=True)
+    kat = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    with open(os.path.join(OUT, "test_prod_ntt256_stdout.txt"), "w") as f:
+        f.write(kat)
     print("params:", g["ref_params"], "lines of stdout kept:", len(keep))
 
 

@@ -51,6 +51,63 @@ def test_host_tables_match_reference(nttb200, golden, kind):
     assert (nttb200.make_table(kind, N, Q, PSI).astype(np.int64) == golden[f"table_{kind}"]).all()
 
 
+TABLE_NAMES = ["psi_powers", "inv_psi_powers", "scaled_inv_psi_powers", "omega_powers", "omega_powers_rev",
+               "inv_omega_powers", "inv_omega_powers_rev", "mixed_powers", "mixed_powers_rev",
+               "inv_mixed_powers", "inv_mixed_powers_rev"]
+
+
+def test_library_exports_the_reference_table_symbols(nttb200, golden):
+    """ntt256_tables.h:29-44 / ntt_red256_tables.h:34-51: the 11 + 12 `extern const` arrays the
+    reference's header-only n = 256 wrappers read, word for word the reference's literals."""
+    lib = ctypes.CDLL(nttb200.lib_path())
+    for k, nm in enumerate(TABLE_NAMES):
+        t = (ctypes.c_uint16 * 256).in_dll(lib, "ntt256_" + nm)
+        assert (np.ctypeslib.as_array(t).astype(np.int64) == golden[f"table_{k}"]).all(), nm
+        r = (ctypes.c_int16 * 256).in_dll(lib, "ntt_red256_" + nm)
+        assert (np.ctypeslib.as_array(r).astype(np.int64) == golden[f"red_table_{k}"]).all(), nm
+    r = (ctypes.c_int16 * 256).in_dll(lib, "ntt_red256_scaled_inv_psi_powers_var")
+    assert (np.ctypeslib.as_array(r).astype(np.int64) == golden["red_table_100"]).all()
+    # every table name the legacy header declares is really exported
+    text = open(os.path.join(ROOT, "include", "nttb200_legacy.h")).read()
+    declared = re.findall(r"\b(ntt(?:_red)?256_\w+)\[256\]", text)
+    assert len(set(declared)) == 23
+    for nm in declared:
+        (ctypes.c_int16 * 256).in_dll(lib, nm)
+
+
+@pytest.mark.parametrize("kind", list(range(11)) + [100])
+def test_red_table_generator_matches_reference(nttb200, golden, oracle, kind):
+    """nttb200_make_red_table: value x 3^-1 centred; n^-1 3^-8 / 3^-6 for the two scaled tables."""
+    L = nttb200.lib()
+    out = np.zeros(256, np.int32)
+    assert L.nttb200_make_red_table(kind, 256, PSI, out.ctypes.data) == 0
+    assert (out.astype(np.int64) == golden[f"red_table_{kind}"]).all()
+    for n in (8, 64, 1024):
+        psi = oracle.psi(n, Q, 0)
+        out = np.zeros(n, np.int32)
+        assert L.nttb200_make_red_table(kind, n, psi, out.ctypes.data) == 0
+        assert (out == oracle.red_table(kind, n, psi)).all()
+    if kind == 2:
+        assert golden["params"][6] == 8822 and out.dtype == np.int32
+
+
+def test_reference_headers_link_against_the_library_alone(nttb200, tmp_path):
+    """A program written against the reference's n = 256 headers (static inline wrappers over
+    extern tables) links with -lnttb200 and nothing else (where the reference tree exists)."""
+    import subprocess
+    n256 = "/root/reference/Multiplier_NTT_Based/NTT_Software/NTT_Software_Evaluations/NTT-256"
+    if not os.path.isdir(n256):
+        pytest.skip("reference tree not present")
+    exe = str(tmp_path / "wrappers")
+    pkg = os.path.dirname(nttb200.lib_path())
+    for opt in ("-O0", "-O2"):
+        subprocess.run(["gcc", opt, "-I", n256, "-o", exe, os.path.join(ROOT, "tests", "ref_wrappers_client.c"),
+                        "-L", pkg, "-lnttb200", f"-Wl,-rpath,{pkg}"], check=True)
+    dyn = subprocess.run(["nm", "-D", exe], capture_output=True, text=True).stdout
+    for sym in ("ntt256_omega_powers_rev", "ntt_red256_mixed_powers_rev", "ntt_ct_std2rev", "mulntt_red_ct_std2rev"):
+        assert sym in dyn, sym          # resolved from libnttb200.so at load time
+
+
 @pytest.mark.parametrize("n,q", [(64, 257), (256, 7681), (1024, 12289), (4096, 469762049), (65536, 2013265921)])
 def test_host_tables_match_oracle(nttb200, oracle, n, q):
     psi = nttb200.find_psi(n, q)

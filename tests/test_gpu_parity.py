@@ -268,14 +268,40 @@ def test_hw_golden_vectors_q7681(gpu, hw_golden):
     p.close()
 
 
-@pytest.mark.parametrize("df,fn", [("ct_std2rev", "ntt_ct_std2rev"), ("gs_rev2std", "ntt_gs_rev2std"),
-                                    ("ct_rev2std", "ntt_ct_rev2std"), ("gs_std2rev", "ntt_gs_std2rev")])
-def test_table_driven_dataflows(gpu, oracle, df, fn):
-    """nttb200_ntt_table_batch: the reference dataflow with an ARBITRARY caller table."""
-    for n, q in ((256, 12289), (64, 257), (2048, 12289)):
-        tab = oracle.random((n,), q, SEED + n).astype(np.uint32)      # not even roots of unity
+# dataflow -> (un-merged reference function, psi-merged twin, ids of ref_shim.c:ref_transform_tab)
+TABLE_DATAFLOWS = {"ct_rev2std": ("ntt_ct_rev2std", "mulntt_ct_rev2std", 1, 2),
+                   "ct_std2rev": ("ntt_ct_std2rev", "mulntt_ct_std2rev", 3, 4),
+                   "gs_rev2std": ("ntt_gs_rev2std", "nttmul_gs_rev2std", 5, 6),
+                   "gs_std2rev": ("ntt_gs_std2rev", "nttmul_gs_std2rev", 7, 8)}
+
+
+@pytest.mark.parametrize("df", sorted(TABLE_DATAFLOWS))
+def test_table_driven_dataflows(gpu, oracle, golden, df):
+    """nttb200_ntt_table_batch: the reference dataflow with an ARBITRARY caller table (p[t] != 1),
+    against the compiled reference's outputs (golden arb_*) for both the un-merged (j = 0 peeled,
+    p[t] never read -- R/NTT/ntt.C:313-317) and the psi-merged entry points, and against the
+    oracle at other (n, q)."""
+    plain, merged, id_plain, id_merged = TABLE_DATAFLOWS[df]
+    for nn in (256, 64):
+        tab, a = golden[f"arb_table_{nn}"].astype(np.uint32), golden[f"arb_in_{nn}"]
+        assert (gpu.ntt_table_batch(nn, Q, df, tab, a, skip_j0=True) == golden[f"arb_transform_{nn}_{id_plain}"]).all()
+        assert (gpu.ntt_table_batch(nn, Q, df, tab, a, skip_j0=False) == golden[f"arb_transform_{nn}_{id_merged}"]).all()
+        # the reference's own names (legacy surface) with the same caller table
+        for fn, tid in ((plain, id_plain), (merged, id_merged)):
+            got = gpu.legacy.transform(fn, a[3], tab)
+            assert (got == golden[f"arb_transform_{nn}_{tid}"][3]).all(), fn
+    for n, q in ((256, 12289), (64, 257), (2048, 12289), (8192, 12289)):
+        tab = (oracle.random((n,), q - 2, SEED + n) + 2).astype(np.uint32)      # not even roots of unity
         a = oracle.random((5, n), q, SEED + 7)
-        assert (gpu.ntt_table_batch(n, q, df, tab, a) == oracle.transform(fn, a, tab, q)).all(), (n, q)
+        assert (gpu.ntt_table_batch(n, q, df, tab, a, skip_j0=True) == oracle.transform(plain, a, tab, q)).all(), (n, q)
+        assert (gpu.ntt_table_batch(n, q, df, tab, a, skip_j0=False) == oracle.transform(merged, a, tab, q)).all(), (n, q)
+
+
+def test_v1_table_layout_with_an_arbitrary_table(gpu, golden):
+    """ntt_ct_rev2std_v1 reads psi-power entries p[j*l] and peels j = 0 (R/NTT/ntt.C:168-197)."""
+    for nn in (256, 64):
+        got = gpu.legacy.transform("ntt_ct_rev2std_v1", golden[f"arb_in_{nn}"][2], golden[f"arb_table_{nn}"])
+        assert (got == golden[f"arb_transform_{nn}_0"][2]).all()
 
 
 def test_legacy_surface(gpu, golden, oracle):

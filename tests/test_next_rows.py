@@ -208,3 +208,81 @@ def test_terasic_plugin_protocol(gpu, oracle, tmp_path, n, q, cyclic):
             assert list(got[:4]) == [2, 4, 6, 0]
         if i == 1:
             assert list(got[:5]) == [2, 6, 10, 6, 0]
+
+
+# ------------------------------------------------------------------------------------------
+# the reference's OWN programs, unmodified, on the GPU library (prebuilt by oracle/Makefile into
+# oracle/_ref/, which travels to the GPU box; /root/reference is not needed at run time)
+REFBIN = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _refbin(name):
+    path = os.path.join(REFBIN, name)
+    assert os.path.exists(path), f"{path} missing: run __graft_entry__.build() where /root/reference exists"
+    return path
+
+
+def _write_coeffs(L, path, v):
+    v = np.ascontiguousarray(v, dtype=np.int32)
+    assert L.nttb200_write_coeff_file(str(path).encode(), v.ctypes.data, v.size) == 0
+
+
+@pytest.mark.gpu
+def test_reference_benchmark_main_relinked_against_the_gpu_library(gpu, L, golden, tmp_path):
+    """NTT-256/time_testing256.c (its main(), file reader and printer, unmodified) linked with
+    -lnttb200 instead of the reference's C: same stdout as the reference binary, the time aside."""
+    _write_coeffs(L, tmp_path / "coeficientes_a.txt", golden["fixture_a"])
+    _write_coeffs(L, tmp_path / "coeficientes_b.txt", golden["fixture_b"])
+    out = subprocess.run([_refbin("time_testing256_gpu")], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    got = "\n".join(ln for ln in out.stdout.splitlines() if not ln.startswith("Tempo total")) + "\n"
+    assert got == open(os.path.join(GOLD, "time_testing256_stdout.txt")).read()
+    assert "Tempo total" in out.stdout
+
+
+@pytest.mark.gpu
+def test_reference_kat_program_relinked_against_the_gpu_library(gpu, tmp_path):
+    """NTT/test_prod_ntt256.c:48-57: (1 + 2x) * 3 = 3 + 6x, printed by the reference's own main()."""
+    out = subprocess.run([_refbin("test_prod_ntt256_gpu")], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout == open(os.path.join(GOLD, "test_prod_ntt256_stdout.txt")).read()
+    nums = [int(t) for t in out.stdout.split("Polin")[1].split(":")[1].split()]
+    assert nums[:3] == [3, 6, 0] and len(nums) == 256 and not any(nums[2:])
+
+
+@pytest.mark.gpu
+def test_reference_fpga_host_program_runs_on_the_plugin(gpu, tmp_path):
+    """linux_app/NTT_PCIECommunicationv2.c + PCIE.c, unmodified: PCIE_Load() dlopens
+    ./terasic_pcie_qsys.so (our plugin), streams W/W_INV/q/n_inv, A, B, pulses GO, polls STATUS,
+    reads C back and checks {2, 4, 6} itself (v2.c:232-238)."""
+    os.symlink(os.path.join(PKG_DIR, "terasic_pcie_qsys.so"), tmp_path / "terasic_pcie_qsys.so")
+    out = subprocess.run([_refbin("ntt_pcie_v2")], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    text = out.stdout + out.stderr
+    assert out.returncode == 0 and "PCIE_Load failed" not in text and "PCIE_Open failed" not in text, text
+    assert "TB: Sinal 'done_all' recebido!" in text
+    assert "0 erros encontrados" in text
+
+
+WRAPPER_IDS = list(range(13)) + list(range(100, 112))
+
+
+@pytest.mark.gpu
+def test_reference_header_wrappers_on_the_gpu_library(gpu, golden, tmp_path):
+    """tests/ref_wrappers_client.c, compiled against the reference's ntt256.h / ntt_red256.h and
+    linked with -lnttb200 only: every `static inline` wrapper (ntt256.h:20-69, ntt_red256.h:21-70)
+    binds one of OUR exported tables to one of OUR generic transforms; outputs = the compiled
+    reference's (golden transform_*), products = fixture_c."""
+    exe = _refbin("ref_wrappers_gpu")
+    fin, fout = tmp_path / "in.txt", tmp_path / "out.txt"
+    for tid in WRAPPER_IDS:
+        row = 5
+        src = golden["rand_a"][row] if tid < 100 else golden["red_transform_in"][row]
+        np.savetxt(fin, src[None], fmt="%d")
+        r = subprocess.run([exe, str(tid), str(fin), str(fout)], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, (tid, r.stderr)
+        assert (np.loadtxt(fout, dtype=np.int64) == golden[f"transform_{tid}"][row]).all(), tid
+    np.savetxt(fin, np.concatenate([golden["fixture_a"], golden["fixture_b"]])[None], fmt="%d")
+    for pid in (200, 201, 202, 203):
+        r = subprocess.run([exe, str(pid), str(fin), str(fout)], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, (pid, r.stderr)
+        assert (np.loadtxt(fout, dtype=np.int64) == golden["fixture_c"]).all(), pid

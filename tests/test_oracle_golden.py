@@ -92,6 +92,34 @@ def test_red_transforms(golden, oracle, tid):
     assert (got == golden[f"transform_{tid}"]).all()
 
 
+# ids of ref_shim.c:ref_transform_tab -> oracle function (same names as the reference)
+TAB_IDS = {0: "ntt_ct_rev2std_v1", 1: "ntt_ct_rev2std", 2: "mulntt_ct_rev2std", 3: "ntt_ct_std2rev",
+           4: "mulntt_ct_std2rev", 5: "ntt_gs_rev2std", 6: "nttmul_gs_rev2std", 7: "ntt_gs_std2rev",
+           8: "nttmul_gs_std2rev"}
+RED_TAB_IDS = {1: "ct_rev2std", 2: "mulntt_ct_rev2std", 3: "ct_std2rev", 4: "mulntt_ct_std2rev",
+               5: "gs_rev2std", 6: "nttmul_gs_rev2std", 7: "gs_std2rev", 8: "nttmul_gs_std2rev"}
+
+
+@pytest.mark.parametrize("nn", [256, 64])
+@pytest.mark.parametrize("tid", sorted(TAB_IDS))
+def test_transforms_with_an_arbitrary_caller_table(golden, oracle, nn, tid):
+    """The un-merged entry points never read p[t] (j = 0 peel, ntt.C:313-317 ...): with a table
+    whose p[t] != 1 they differ from the merged ones, and the oracle follows the reference."""
+    tab = golden[f"arb_table_{nn}"].astype(np.uint32)
+    assert (tab[[1, 2, 4, 8]] != 1).all()
+    got = oracle.transform(TAB_IDS[tid], golden[f"arb_in_{nn}"], tab, Q)
+    assert (got == golden[f"arb_transform_{nn}_{tid}"]).all()
+    if tid in (1, 3, 5, 7):      # and the peel matters: the merged twin gives something else
+        assert (golden[f"arb_transform_{nn}_{tid}"] != golden[f"arb_transform_{nn}_{tid + 1}"]).any()
+
+
+@pytest.mark.parametrize("nn", [256, 64])
+@pytest.mark.parametrize("tid", sorted(RED_TAB_IDS))
+def test_red_transforms_with_an_arbitrary_caller_table(golden, oracle, nn, tid):
+    got = oracle.red_transform(RED_TAB_IDS[tid], golden[f"arb_red_in_{nn}"], golden[f"arb_red_table_{nn}"])
+    assert (got == golden[f"arb_red_transform_{nn}_{tid}"]).all()
+
+
 def test_ct_and_gs_agree_and_invert(golden, oracle):
     a = golden["rand_a"][:8]
     f1 = golden["transform_2"][:8]      # ntt256_ct_std2rev

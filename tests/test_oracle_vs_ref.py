@@ -66,3 +66,23 @@ def test_bitrev_shuffle(ref, oracle):
     ref.lib.ref_bitrev_shuffle(r, N)
     oracle.lib.orc_bitrev_shuffle(o, N)
     assert (r == o).all()
+
+
+def test_generic_entry_points_with_arbitrary_tables_live(ref, oracle):
+    """Every generic transform of ntt.h / ntt_red.h with random caller tables (entries in
+    [0, q), p[t] != 1): the oracle restates the j = 0 peel of the un-merged functions."""
+    from test_oracle_golden import RED_TAB_IDS, TAB_IDS
+    rng = np.random.default_rng(7)
+    for nn in (8, 32, 256):
+        for trial in range(4):
+            tab = rng.integers(2, Q, size=nn).astype(np.uint16)
+            a = oracle.random((5, nn), Q, 100 + trial)
+            for tid, name in TAB_IDS.items():
+                assert (oracle.transform(name, a, tab.astype(np.uint32), Q) == ref.transform_tab(tid, a, tab)).all(), (nn, name)
+            rtab = tab.astype(np.int64)
+            rtab[rtab > 6144] -= Q
+            c = a.copy()
+            c[c > 6144] -= Q
+            for tid, name in RED_TAB_IDS.items():
+                assert (oracle.red_transform(name, c, rtab.astype(np.int32)) ==
+                        ref.transform_tab(tid, c, rtab.astype(np.int16), red=True)).all(), (nn, name)
