@@ -40,7 +40,8 @@ enum {
   NTTB200_EPARAM = -1,   /* bad (n, q, psi), NULL pointer, unsupported size       */
   NTTB200_ECUDA = -2,    /* CUDA runtime/driver error, or no device               */
   NTTB200_ENOMEM = -3,   /* host or device allocation failed                      */
-  NTTB200_ERANGE = -4    /* an input coefficient outside [0, q) (checked on request) */
+  NTTB200_ERANGE = -4    /* an input coefficient outside [0, q): looked for by plans created
+                            with NTTB200_PLAN_CHECK_RANGE only                     */
 };
 const char *nttb200_last_error(void);
 int nttb200_version(void);
@@ -61,6 +62,13 @@ typedef struct nttb200_plan nttb200_plan;
 
 #define NTTB200_PLAN_NO_PLANTARD 2u /* diagnostics: products of half-word moduli (q <= 12385) use the
                                       generic Shoup/Montgomery kernel instead of the Plantard one */
+
+#define NTTB200_PLAN_CHECK_RANGE 4u /* products and transforms first verify that every input coefficient
+                                     lies in [0, q) -- the reference's unchecked precondition
+                                     (R/NTT/ntt256.h:82-83) -- and return NTTB200_ERANGE naming the
+                                     first offender.  Host arrays are scanned where they lie; for
+                                     device arrays the call waits for a checking kernel (it is then
+                                     synchronous).  A debugging aid: off on the timed path.           */
 
 /* n: power of two, 8 <= n <= 2^17.  q: odd prime < 2^31 with 2n | q-1 (n | q-1 when
  * CYCLIC).  psi: primitive 2n-th root of unity mod q, or 0 for the smallest one -- the

@@ -31,9 +31,10 @@ void ntt_red256_product1(int32_t *c, int32_t *a, int32_t *b);  /* R/NTT-RED/ntt_
 void ntt_red256_product4(int32_t *c, int32_t *a, int32_t *b);  /* R/NTT-RED/ntt_red256.h:90, ntt_red256.C:30-52 */
 /* The reference documents "arrays a and b are modified" (R/NTT/ntt256.h:80): after
  * ntt256_product1/4 they hold the psi-twisted forward NTT in bit-reversed order.  By
- * default the drop-ins leave a and b untouched; nttb200_legacy_set_clobber(1) reproduces
- * that post-state for ntt256_product1/4 (for the RED variants the post-state is an
- * unreduced representative and is not reproduced). */
+ * default the drop-ins leave a and b untouched; nttb200_legacy_set_clobber(1) reproduces the
+ * reference's post-state for all four: the canonical transform for ntt256_product1/4, and for
+ * the optimized pair the UNREDUCED representative their pipeline leaves behind (shift -> x psi^i
+ * -> forward transform -> reduce_array, R/NTT-RED/ntt_red256.C:5-13, 31-39), bit for bit. */
 void nttb200_legacy_set_clobber(int on);
 
 /* ---- generic-n transforms with the caller's table (R/NTT/ntt.h:71-183) ---------------- */

@@ -27,6 +27,7 @@ TABLES = {
 }
 PLAN_CYCLIC = 1
 PLAN_NO_PLANTARD = 2
+PLAN_CHECK_RANGE = 4
 
 
 class NttError(RuntimeError):
@@ -243,9 +244,11 @@ class MultiPlan:
 class Plan:
     """One (n, q, psi) parameter set on the current CUDA device."""
 
-    def __init__(self, n: int, q: int, psi: int = 0, cyclic: bool = False, no_plantard: bool = False) -> None:
+    def __init__(self, n: int, q: int, psi: int = 0, cyclic: bool = False, no_plantard: bool = False,
+                 check_range: bool = False) -> None:
         h = C.c_void_p()
-        flags = (PLAN_CYCLIC if cyclic else 0) | (PLAN_NO_PLANTARD if no_plantard else 0)
+        flags = ((PLAN_CYCLIC if cyclic else 0) | (PLAN_NO_PLANTARD if no_plantard else 0) |
+                 (PLAN_CHECK_RANGE if check_range else 0))
         _check(lib().nttb200_plan_create(C.byref(h), n, q, psi, flags))
         self._h = h
         self.n, self.q = n, q

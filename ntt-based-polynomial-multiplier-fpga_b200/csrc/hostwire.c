@@ -326,6 +326,12 @@ static uint64_t post(int kind, void *dst, const void *src, size_t words, _Atomic
     atomic_store_explicit(&G.retired, r, memory_order_release);
     if (p - r < RING) {
       job_t *J = &G.jobs[p % RING];
+      /* Invalidate the cursor BEFORE the fields change: a worker that still holds the previous
+       * job's cursor value (same slot, RING jobs ago) may read the new fields, but its
+       * compare-and-swap then meets a cursor that is neither its stale value nor (yet) the new
+       * job's, fails, and re-reads.  Without this it could win the CAS on the stale value while the
+       * fields were half rewritten. */
+      atomic_store_explicit(&J->cursor, ~0ull, memory_order_release);
       J->kind = kind;
       J->dst = dst;
       J->src = src;

@@ -32,19 +32,36 @@ static nttb200_plan *default_plan(void) {
 
 void nttb200_legacy_set_clobber(int on) { g_clobber = on; }
 
+/* Post-state of an operand of the optimized products ("a and b are modified",
+ * R/NTT-RED/ntt_red256.h:77-86): shift -> x psi^i (mul_red) -> forward transform -> reduce,
+ * R/NTT-RED/ntt_red256.C:5-13 (CT, product1) and :31-39 (GS, product4) -- an UNREDUCED
+ * representative, reproduced with the exact Longa-Naehrig pieces below. */
+static void red_post_state(int32_t *x, int gs) {
+  shift_array(x, 256);
+  mul_reduce_array16(x, 256, ntt_red256_psi_powers);
+  if (gs) ntt_red_gs_std2rev(x, 256, ntt_red256_omega_powers);
+  else ntt_red_ct_std2rev(x, 256, ntt_red256_omega_powers_rev);
+  reduce_array(x, 256);
+}
+
+/* clobber: 0 none, 1 the canonical post-state of ntt256_product1/4 (psi-twisted NTT, bit-reversed
+ * order: R/NTT/ntt256.C:6-9), 2 / 3 the post-state of ntt_red256_product1 / 4 */
 static void product(int32_t *c, int32_t *a, int32_t *b, int clobber) {
   nttb200_plan *P = default_plan();
   if (nttb200_polymul_batch(P, c, a, b, 1) != 0) die("nttb200_polymul_batch");
-  if (clobber) {
+  if (clobber == 1) {
     if (nttb200_ntt_batch(P, NTTB200_MULNTT_STD2REV, a, 1) != 0) die("nttb200_ntt_batch");
     if (nttb200_ntt_batch(P, NTTB200_MULNTT_STD2REV, b, 1) != 0) die("nttb200_ntt_batch");
+  } else if (clobber >= 2) {
+    red_post_state(a, clobber == 3);
+    red_post_state(b, clobber == 3);
   }
 }
 
-void ntt256_product1(int32_t *c, int32_t *a, int32_t *b) { product(c, a, b, g_clobber); }
-void ntt256_product4(int32_t *c, int32_t *a, int32_t *b) { product(c, a, b, g_clobber); }
-void ntt_red256_product1(int32_t *c, int32_t *a, int32_t *b) { product(c, a, b, 0); }
-void ntt_red256_product4(int32_t *c, int32_t *a, int32_t *b) { product(c, a, b, 0); }
+void ntt256_product1(int32_t *c, int32_t *a, int32_t *b) { product(c, a, b, g_clobber ? 1 : 0); }
+void ntt256_product4(int32_t *c, int32_t *a, int32_t *b) { product(c, a, b, g_clobber ? 1 : 0); }
+void ntt_red256_product1(int32_t *c, int32_t *a, int32_t *b) { product(c, a, b, g_clobber ? 2 : 0); }
+void ntt_red256_product4(int32_t *c, int32_t *a, int32_t *b) { product(c, a, b, g_clobber ? 3 : 0); }
 
 /* caller's 16-bit table -> the ABI's 32-bit table */
 static void table_transform(int32_t *a, uint32_t n, const uint16_t *p, int dataflow, int skip_j0) {

@@ -337,6 +337,48 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+/* NTTB200_PLAN_CHECK_RANGE: the reference leaves out-of-range inputs undefined (R/NTT/ntt256.h:82-83
+ * "must contain elements in the range [0 .. Q-1]"); a plan created with the flag looks first.
+ * Host arrays are scanned where they lie; device arrays by a kernel whose verdict the call waits
+ * for (which makes the _dev call synchronous -- it is a debugging aid, not the timed path). */
+static int check_range_host(const nttb200_plan *P, const int32_t *x, size_t count, const char *what) {
+  const uint32_t q = P->q;
+  uint32_t bad = 0;
+  const uint32_t *u = (const uint32_t *)x;
+  for (size_t i = 0; i < count; i++) bad |= (uint32_t)(u[i] >= q);
+  if (!bad) return 0;
+  size_t i = 0;
+  while (u[i] < q) i++;
+  return nttb200_fail(NTTB200_ERANGE, "%s[%zu] = %d is outside [0, %u)", what, i, x[i], q);
+}
+__global__ void __launch_bounds__(256)
+range_check_kernel(const uint32_t *a, const uint32_t *b, unsigned long long count, uint32_t q,
+                   unsigned long long *first_bad) {
+  unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long gstride = (unsigned long long)gridDim.x * blockDim.x;
+  for (; gid < count; gid += gstride) {
+    if (a[gid] >= q) atomicMin(first_bad, gid);
+    if (b && b[gid] >= q) atomicMin(first_bad, count + gid);
+  }
+}
+static int check_range_dev(const nttb200_plan *P, const uint32_t *a, const uint32_t *b, size_t count,
+                           cudaStream_t st) {
+  unsigned long long *flag = nullptr, h = ~0ull;
+  NTT_CUDA(cudaMalloc(&flag, sizeof h));
+  cudaError_t e = cudaMemcpyAsync(flag, &h, sizeof h, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    range_check_kernel<<<grid_1d(count, 256, P->sm_count), 256, 0, st>>>(a, b, count, P->q, flag);
+    nttb200_count_launch(1);
+    e = cudaMemcpyAsync(&h, flag, sizeof h, cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(flag);
+  if (e != cudaSuccess) return nttb200_fail(NTTB200_ECUDA, "range check: %s", cudaGetErrorString(e));
+  if (h == ~0ull) return 0;
+  return nttb200_fail(NTTB200_ERANGE, "%s[%llu] is outside [0, %u)", h >= count ? "b" : "a",
+                      h >= count ? h - count : h, P->q);
+}
+
 static int polymul_dev(nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b, size_t batch,
                        cudaStream_t st) {
   if (batch == 0) return 0;
@@ -465,6 +507,10 @@ extern "C" int nttb200_polymul_batch_dev(nttb200_plan *P, int32_t *c, const int3
   if (!P || !c || !a || !b) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
   g_launches = 0;
   DeviceGuard guard(P->device);
+  if ((P->flags & NTTB200_PLAN_CHECK_RANGE) && batch) {
+    const int rc = check_range_dev(P, (const uint32_t *)a, (const uint32_t *)b, batch * P->n, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
   return polymul_dev(P, (uint32_t *)c, (const uint32_t *)a, (const uint32_t *)b, batch,
                      (cudaStream_t)stream);
 }
@@ -476,6 +522,10 @@ extern "C" int nttb200_ntt_batch_dev(nttb200_plan *P, int transform, int32_t *a,
   if (((uintptr_t)a & 15u) != 0) return nttb200_fail(NTTB200_EPARAM, "a_dev must be 16-byte aligned");
   g_launches = 0;
   DeviceGuard guard(P->device);
+  if ((P->flags & NTTB200_PLAN_CHECK_RANGE) && batch) {
+    const int rc = check_range_dev(P, (const uint32_t *)a, nullptr, batch * P->n, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
   return transform_dev(P, transform, (uint32_t *)a, batch, (cudaStream_t)stream);
 }
 
@@ -512,15 +562,30 @@ static int ensure_slots(nttb200_plan *P, bool need_b) {
     }
   }
   const size_t target_bytes = (size_t)env_int("NTTB200_SLOT_MB", 16, 1, 256) << 20;   /* per operand per slot */
-  P->slot_polys = std::max<size_t>(1, target_bytes / (P->n * sizeof(uint32_t)));
-  P->slots.resize(NSLOT);
-  for (auto &s : P->slots) {
-    NTT_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    NTT_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-    NTT_CUDA(cudaMalloc(&s.d_a, P->slot_polys * P->n * sizeof(uint32_t)));
-    NTT_CUDA(cudaMalloc(&s.d_b, P->slot_polys * P->n * sizeof(uint32_t)));
-    NTT_CUDA(cudaMalloc(&s.d_c, P->slot_polys * P->n * sizeof(uint32_t)));
+  const size_t polys = std::max<size_t>(1, target_bytes / (P->n * sizeof(uint32_t)));
+  /* built aside and moved into the plan only when every allocation succeeded: a half-built ring
+   * must not look initialised to the next call */
+  std::vector<HostSlot> ring(NSLOT);
+  cudaError_t e = cudaSuccess;
+  for (auto &s : ring) {
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&s.d_a, polys * P->n * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&s.d_b, polys * P->n * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&s.d_c, polys * P->n * sizeof(uint32_t));
   }
+  if (e != cudaSuccess) {
+    for (auto &s : ring) {
+      if (s.stream) cudaStreamDestroy(s.stream);
+      if (s.done) cudaEventDestroy(s.done);
+      cudaFree(s.d_a); cudaFree(s.d_b); cudaFree(s.d_c);
+    }
+    cudaGetLastError();
+    return nttb200_fail(e == cudaErrorMemoryAllocation ? NTTB200_ENOMEM : NTTB200_ECUDA,
+                        "staging ring: %s", cudaGetErrorString(e));
+  }
+  P->slot_polys = polys;
+  P->slots = std::move(ring);
   (void)need_b;
   return 0;
 }
@@ -557,21 +622,39 @@ static int wire_mode() {                               /* read per call: tests s
 static int ensure_wire_slots(nttb200_plan *P) {
   if (!P->wslots.empty()) return 0;
   const size_t words = (size_t)env_int("NTTB200_WIRE_KWORDS", 1024, 16, 65536) << 10;   /* per operand */
-  P->wire_polys = std::max<size_t>(1, words / P->n);
-  const size_t w = P->wire_polys * P->n;
-  P->wslots.resize(env_int("NTTB200_WIRE_SLOTS", 6, 2, 16));
-  for (auto &s : P->wslots) {
-    NTT_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    NTT_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-    NTT_CUDA(cudaMalloc(&s.d_a, w * sizeof(uint32_t)));
-    NTT_CUDA(cudaMalloc(&s.d_b, w * sizeof(uint32_t)));
-    NTT_CUDA(cudaMalloc(&s.d_c, w * sizeof(uint32_t)));
+  const size_t polys = std::max<size_t>(1, words / P->n);
+  const size_t w = polys * P->n;
+  /* as ensure_slots: nothing is published until every slot is complete (a worker of the host
+   * pool handed a slot without staging memory would write through NULL) */
+  std::vector<WireSlot> ring(env_int("NTTB200_WIRE_SLOTS", 6, 2, 16));
+  cudaError_t e = cudaSuccess;
+  for (auto &s : ring) {
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&s.d_a, w * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&s.d_b, w * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&s.d_c, w * sizeof(uint32_t));
     void *h = nullptr;                                 /* staging holds words of either width */
-    NTT_CUDA(cudaHostAlloc(&h, 3 * w * sizeof(uint32_t), cudaHostAllocPortable));
-    s.h_a = (uint32_t *)h;
-    s.h_b = s.h_a + w;
-    s.h_c = s.h_b + w;
+    if (e == cudaSuccess) e = cudaHostAlloc(&h, 3 * w * sizeof(uint32_t), cudaHostAllocPortable);
+    if (e == cudaSuccess) {
+      s.h_a = (uint32_t *)h;
+      s.h_b = s.h_a + w;
+      s.h_c = s.h_b + w;
+    }
   }
+  if (e != cudaSuccess) {
+    for (auto &s : ring) {
+      if (s.stream) cudaStreamDestroy(s.stream);
+      if (s.done) cudaEventDestroy(s.done);
+      cudaFree(s.d_a); cudaFree(s.d_b); cudaFree(s.d_c);
+      if (s.h_a) cudaFreeHost(s.h_a);
+    }
+    cudaGetLastError();
+    return nttb200_fail(e == cudaErrorMemoryAllocation ? NTTB200_ENOMEM : NTTB200_ECUDA,
+                        "wire pipeline slots: %s", cudaGetErrorString(e));
+  }
+  P->wire_polys = polys;
+  P->wslots = std::move(ring);
   return 0;
 }
 
@@ -761,6 +844,11 @@ extern "C" int nttb200_polymul_batch(nttb200_plan *P, int32_t *c, const int32_t 
                                      size_t batch) {
   if (!P || !c || !a || !b) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
   g_launches = 0;
+  if (P->flags & NTTB200_PLAN_CHECK_RANGE) {
+    int rcr = check_range_host(P, a, batch * P->n, "a");
+    if (!rcr) rcr = check_range_host(P, b, batch * P->n, "b");
+    if (rcr) return rcr;
+  }
   std::lock_guard<std::mutex> lock(P->mu);
   DeviceGuard guard(P->device);
   int rc = ensure_slots(P, true);
@@ -921,6 +1009,10 @@ static int ntt_batch_staged(nttb200_plan *P, int transform, int32_t *a, size_t b
 extern "C" int nttb200_ntt_batch(nttb200_plan *P, int transform, int32_t *a, size_t batch) {
   if (!P || !a) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
   g_launches = 0;
+  if (P->flags & NTTB200_PLAN_CHECK_RANGE) {
+    const int rcr = check_range_host(P, a, batch * P->n, "a");
+    if (rcr) return rcr;
+  }
   std::lock_guard<std::mutex> lock(P->mu);
   DeviceGuard guard(P->device);
   int rc = ensure_slots(P, false);

@@ -165,7 +165,7 @@ BOOL PCIE_Write32(PCIE_HANDLE h, PCIE_BAR bar, DWORD addr, DWORD data) {
   (void)h;
   if (!S.open) return 0;
   if (bar == 0 && addr == ADDR_CONTROL) { control_write(data); return 1; }
-  if (addr + 4 > REGFILE_BYTES) return 0;
+  if (addr > REGFILE_BYTES - 4) return 0;
   memcpy(S.regs + addr, &data, 4);
   return 1;
 }
@@ -178,31 +178,31 @@ BOOL PCIE_Read32(PCIE_HANDLE h, PCIE_BAR bar, DWORD addr, DWORD *data) {
     return 1;
   }
   if (bar == 0 && addr == ADDR_CONTROL) { *data = S.control; return 1; }
-  if (addr + 4 > REGFILE_BYTES) return 0;
+  if (addr > REGFILE_BYTES - 4) return 0;
   memcpy(data, S.regs + addr, 4);
   return 1;
 }
 BOOL PCIE_Write16(PCIE_HANDLE h, PCIE_BAR bar, DWORD addr, WORD data) {
   (void)h; (void)bar;
-  if (!S.open || addr + 2 > REGFILE_BYTES) return 0;
+  if (!S.open || addr > REGFILE_BYTES - 2) return 0;
   memcpy(S.regs + addr, &data, 2);
   return 1;
 }
 BOOL PCIE_Read16(PCIE_HANDLE h, PCIE_BAR bar, DWORD addr, WORD *data) {
   (void)h; (void)bar;
-  if (!S.open || !data || addr + 2 > REGFILE_BYTES) return 0;
+  if (!S.open || !data || addr > REGFILE_BYTES - 2) return 0;
   memcpy(data, S.regs + addr, 2);
   return 1;
 }
 BOOL PCIE_Write8(PCIE_HANDLE h, PCIE_BAR bar, DWORD addr, BYTE data) {
   (void)h; (void)bar;
-  if (!S.open || addr + 1 > REGFILE_BYTES) return 0;
+  if (!S.open || addr > REGFILE_BYTES - 1) return 0;
   S.regs[addr] = data;
   return 1;
 }
 BOOL PCIE_Read8(PCIE_HANDLE h, PCIE_BAR bar, DWORD addr, BYTE *data) {
   (void)h; (void)bar;
-  if (!S.open || !data || addr + 1 > REGFILE_BYTES) return 0;
+  if (!S.open || !data || addr > REGFILE_BYTES - 1) return 0;
   *data = S.regs[addr];
   return 1;
 }

@@ -57,3 +57,26 @@ def gpu(nttb200):
     if nttb200.device_count() < 1:
         pytest.fail("no CUDA device visible to libnttb200.so (gpu-marked test on a CPU box?)")
     return nttb200
+
+
+def oracle_product_mt(oracle, n, q, a, b, variant=10, psi=0, threads=None):
+    """oracle.product over the rows of (a, b), split over the host cores (the ctypes call releases
+    the GIL and the oracle's plans are read-only)."""
+    from concurrent.futures import ThreadPoolExecutor
+    a = np.ascontiguousarray(a, dtype=np.int32).reshape(-1, n)
+    b = np.ascontiguousarray(b, dtype=np.int32).reshape(-1, n)
+    rows = a.shape[0]
+    threads = threads or min(32, len(os.sched_getaffinity(0)))
+    oracle.plan(n, q, psi)                       # create the plan once, outside the pool
+    if rows < 2 * threads:
+        return oracle.product(n, q, a, b, variant, psi)
+    cuts = [rows * i // threads for i in range(threads + 1)]
+    with ThreadPoolExecutor(threads) as ex:
+        parts = list(ex.map(lambda i: oracle.product(n, q, a[cuts[i]:cuts[i + 1]], b[cuts[i]:cuts[i + 1]], variant, psi),
+                            range(threads)))
+    return np.concatenate(parts)
+
+
+@pytest.fixture(scope="session")
+def oracle_mt(oracle):
+    return lambda n, q, a, b, variant=10, psi=0: oracle_product_mt(oracle, n, q, a, b, variant, psi)

@@ -55,6 +55,37 @@ def test_ragged_batches(plan256, oracle, batch):
     assert (plan256.polymul(a, b) == oracle.product(N, Q, a, b, 10, PSI)).all()
 
 
+@pytest.mark.parametrize("n,q", [(256, 12289), (1024, 2013265921), (2048, 12289)])
+def test_range_check_on_request(gpu, oracle, n, q):
+    """NTTB200_PLAN_CHECK_RANGE: the reference's unchecked precondition "elements in [0 .. Q-1]"
+    (ntt256.h:82-83) is verified first and NTTB200_ERANGE names the first offender -- host and
+    device buffers, products and transforms; without the flag nothing is looked at."""
+    import torch
+    p = gpu.Plan(n, q, check_range=True)
+    a, b = oracle.random((5, n), q, 1), oracle.random((5, n), q, 2)
+    assert (p.polymul(a, b) == oracle.product(n, q, a, b, 10)).all()
+    for arr, name, val in ((a, "a", q), (b, "b", -1)):
+        bad = arr.copy()
+        bad[3, 7] = val
+        with pytest.raises(gpu.NttError) as e:
+            p.polymul(bad if name == "a" else a, bad if name == "b" else b)
+        assert "error -4" in str(e.value) and f"{name}[{3 * n + 7}]" in str(e.value), str(e.value)
+        with pytest.raises(gpu.NttError) as e:
+            p.transform("ntt_std2rev", bad)
+        assert "error -4" in str(e.value)
+        da, db = torch.from_numpy(bad if name == "a" else a).cuda(), torch.from_numpy(bad if name == "b" else b).cuda()
+        dc = torch.empty_like(da)
+        with pytest.raises(gpu.NttError) as e:
+            p.polymul_dev(dc.data_ptr(), da.data_ptr(), db.data_ptr(), 5)
+        assert "error -4" in str(e.value) and f"{name}[{3 * n + 7}]" in str(e.value), str(e.value)
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    dc = torch.empty_like(da)
+    p.polymul_dev(dc.data_ptr(), da.data_ptr(), db.data_ptr(), 5)
+    torch.cuda.synchronize()
+    assert (dc.cpu().numpy() == oracle.product(n, q, a, b, 10)).all()
+    p.close()
+
+
 def test_empty_batch(plan256):
     out = plan256.polymul(np.zeros((0, N), np.int32), np.zeros((0, N), np.int32))
     assert out.shape == (0, N)
@@ -67,15 +98,16 @@ def test_inputs_are_left_untouched(plan256, oracle):
     assert (a == a0).all() and (b == b0).all()
 
 
-def test_config2_batch_2e16_vs_all_four_reference_variants(plan256, oracle, loader):
-    """BASELINE config 2: batch 2^16 at the reference default (n,q), bit-exact vs all four C variants."""
+def test_config2_batch_2e16_vs_all_four_reference_variants(plan256, oracle, loader, nttb200, golden):
+    """BASELINE config 2: batch 2^16 at the reference default (n,q) on the SURVEY 8d batch (splitmix64
+    stream, edge rows 0..7, the reference's coefficient files in row 8), EVERY row bit-exact vs all
+    four C variants of the compiled, unmodified reference."""
     batch = 1 << 16
-    a, b = oracle.random((batch, N), Q, SEED + 2), oracle.random((batch, N), Q, SEED + 102)
-    a[0], b[0] = 0, 0
-    a[1], b[1] = Q - 1, Q - 1
-    a[2], b[2] = 0, 0
-    a[2][0], b[2][N - 1] = 1, 1
+    ta, tb = nttb200.inputs.survey_batch(N, Q, batch, 2, fixture=(golden["fixture_a"], golden["fixture_b"]))
+    a, b = ta.numpy(), tb.numpy()
+    assert (a[8] == golden["fixture_a"]).all() and not a[0].any() and (b[1] == Q - 1).all()
     got = plan256.polymul(a, b)
+    assert (got[8] == golden["fixture_c"]).all() and (got[4:8] == golden["kat_c"]).all()
     if loader.reference_available():
         ref = loader.Reference()
         for v in (loader.REF_CT, loader.REF_GS, loader.REF_RED_CT, loader.REF_RED_GS):
@@ -177,27 +209,24 @@ def test_large_n_standalone_transforms(gpu, oracle, loader, n, q):
     p.close()
 
 
-def test_config5_full_batch_properties(gpu, oracle):
-    """BASELINE config 5: n=2^16, 31-bit prime, batch 2^10, device-resident: sampled rows against
-    the oracle, delta rows, commutativity over the whole batch."""
+def test_config5_full_batch_every_row(gpu, oracle_mt, nttb200):
+    """BASELINE config 5: n=2^16, 31-bit prime, batch 2^10, device-resident, on the SURVEY 8d batch
+    (splitmix64 stream, edge rows 0..7): EVERY row against the oracle, plus commutativity."""
     import torch
     n, q, batch = 65536, 2013265921, 1 << 10
     p = gpu.Plan(n, q)
-    g = torch.Generator(device="cuda").manual_seed(99)
-    a = torch.randint(0, q, (batch, n), dtype=torch.int32, device="cuda", generator=g)
-    b = torch.randint(0, q, (batch, n), dtype=torch.int32, device="cuda", generator=g)
-    a[0].zero_(); a[1].fill_(q - 1); b[1].fill_(q - 1)
-    a[2].zero_(); a[2, 0] = 1
+    a, b = nttb200.inputs.survey_batch(n, q, batch, 5, device="cuda")
     c = torch.empty_like(a)
     st = torch.cuda.current_stream().cuda_stream
     p.polymul_dev(c.data_ptr(), a.data_ptr(), b.data_ptr(), batch, st)
     torch.cuda.synchronize()
     assert int(c.min()) >= 0 and int(c.max()) < q
     assert bool((c[0] == 0).all()) and bool((c[2] == b[2]).all())
-    idx = np.array([1, 3, 63, 64, 65, 500, batch - 1])
-    ti = torch.from_numpy(idx).cuda()
-    want = oracle.product(n, q, a[ti].cpu().numpy(), b[ti].cpu().numpy(), 10)
-    assert (c[ti].cpu().numpy() == want).all()
+    assert int(c[3, n - 2]) == q - 1 and int(c[3].long().sum()) == q - 1
+    assert c[5, :4].tolist() == [2, 4, 6, 0] and c[6, :5].tolist() == [2, 6, 10, 6, 0]
+    want = oracle_mt(n, q, a.cpu().numpy(), b.cpu().numpy(), 10)
+    got = c.cpu().numpy()
+    assert (got == want).all(), np.nonzero((got != want).any(axis=1))[0][:8]
     c2 = torch.empty_like(a)
     p.polymul_dev(c2.data_ptr(), b.data_ptr(), a.data_ptr(), batch, st)
     torch.cuda.synchronize()
@@ -316,6 +345,14 @@ def test_legacy_surface(gpu, golden, oracle):
     assert (c == golden["rand_c"][4]).all()
     assert (a_after == golden["clobber_a_after_product1"]).all()
     assert (b_after == golden["clobber_b_after_product1"]).all()
+    # ... and of the optimized pair: the UNREDUCED representative their pipeline leaves behind
+    # ("a and b are modified", ntt_red256.h:77-86), golden from the compiled reference
+    for name, v in (("ntt_red256_product1", 101), ("ntt_red256_product4", 104)):
+        c, a_after, b_after = gpu.legacy.product(name, golden["rand_a"][4], golden["rand_b"][4], clobber=True)
+        assert (c == golden["rand_c"][4]).all(), name
+        assert (a_after == golden[f"clobber_a_after_product{v}"]).all(), name
+        assert (b_after == golden[f"clobber_b_after_product{v}"]).all(), name
+    assert (golden["clobber_a_after_product101"] != golden["clobber_a_after_product1"]).any()
     a = golden["rand_a"][0:16]
     names = {0: ("ntt_ct_rev2std", 3), 1: ("ntt_gs_rev2std", 4), 2: ("ntt_ct_std2rev", 4), 3: ("ntt_gs_std2rev", 3),
              4: ("ntt_ct_rev2std", 5), 5: ("ntt_gs_rev2std", 6), 6: ("ntt_ct_std2rev", 6), 7: ("ntt_gs_std2rev", 5),
@@ -503,31 +540,38 @@ def _dev_buffers(torch, *arrays):
     return [torch.from_numpy(x).cuda() for x in arrays]
 
 
-@pytest.mark.parametrize("n,q,logb", [(256, 12289, 20), (256, 7681, 20), (1024, 12289, 18), (256, 3329, 20)])
-def test_full_size_batches_properties(gpu, oracle, n, q, logb):
-    """BASELINE configs 3/4 at full batch, device-resident: sampled rows against the oracle plus
-    size-independent properties (commutativity, linearity in a, delta rows).  q = 3329 has no
-    512-th root of unity: that case is the cyclic product."""
+@pytest.mark.parametrize("n,q,logb,cfg", [(256, 12289, 20, 2), (256, 7681, 20, 3), (1024, 12289, 18, 4),
+                                           (256, 3329, 20, 3)])
+def test_full_size_batches_properties(gpu, oracle_mt, nttb200, golden, n, q, logb, cfg):
+    """BASELINE configs 3/4 at full batch, device-resident, on the SURVEY 8d batch (splitmix64
+    stream, edge rows 0..7, the fixture pair in row 8): 2^13 sampled rows + every edge row + the
+    last rows against the oracle, plus size-independent properties over the WHOLE batch
+    (commutativity, linearity in a).  q = 3329 has no 512-th root of unity: that case is the
+    cyclic product."""
     import torch
     batch = 1 << logb
     cyclic = (q - 1) % (2 * n) != 0
     variant = 30 if cyclic else 10
     p = gpu.Plan(n, q, cyclic=cyclic)
-    g = torch.Generator(device="cuda").manual_seed(1234 + n + q)
-    a = torch.randint(0, q, (batch, n), dtype=torch.int32, device="cuda", generator=g)
-    b = torch.randint(0, q, (batch, n), dtype=torch.int32, device="cuda", generator=g)
-    a[0].zero_(); b[1].fill_(q - 1); a[1].fill_(q - 1)
-    a[2].zero_(); a[2, 0] = 1
+    a, b = nttb200.inputs.survey_batch(n, q, batch, cfg, device="cuda",
+                                       fixture=(golden["fixture_a"], golden["fixture_b"]))
     c = torch.empty_like(a)
     st = torch.cuda.current_stream().cuda_stream
     p.polymul_dev(c.data_ptr(), a.data_ptr(), b.data_ptr(), batch, st)
     torch.cuda.synchronize()
     assert int(c.min()) >= 0 and int(c.max()) < q
     assert bool((c[0] == 0).all()) and bool((c[2] == b[2]).all())
-    idx = np.unique(np.concatenate([np.arange(0, 8), np.random.default_rng(1).integers(0, batch, 2048),
-                                    np.arange(batch - 8, batch)]))
+    if not cyclic:
+        assert int(c[3, n - 2]) == q - 1 and int(c[3].long().sum()) == q - 1
+        assert c[4, :3].tolist() == [3, 6, 0] and c[5, :4].tolist() == [2, 4, 6, 0]
+        assert c[6, :5].tolist() == [2, 6, 10, 6, 0] and c[7, :8].tolist() == [3, 9, 6, 1, 8, 6, 0, 2]
+    if (n, q) == (256, 12289):
+        assert (c[8].cpu().numpy() == golden["fixture_c"]).all()
+    idx = np.unique(np.concatenate([np.arange(0, 16), np.random.default_rng(1).integers(0, batch, 1 << 13),
+                                    np.arange(batch - 16, batch)]))
+    assert idx.size >= 1 << 12
     ti = torch.from_numpy(idx).cuda()
-    want = oracle.product(n, q, a[ti].cpu().numpy(), b[ti].cpu().numpy(), variant)
+    want = oracle_mt(n, q, a[ti].cpu().numpy(), b[ti].cpu().numpy(), variant)
     assert (c[ti].cpu().numpy() == want).all()
     # commutativity on the whole batch
     c2 = torch.empty_like(a)
