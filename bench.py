@@ -3,6 +3,12 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl reference]
 
+The default run (workload c2) also measures, inside the same JSON line, `sustained` (c2 back to
+back for >= 1 s with the clocks sampled throughout), `workloads` {c3, c4, c5} (every other GPU
+configuration of BASELINE.json: value, ms per step, both roofline fractions, clocks, parity) and
+`strong_scaling` {c3, c4} (ONE fixed batch of 2^20 / 2^18 rows sliced over the N ranks by
+nttb200_shard_bounds, as BASELINE.json configs[2]/[3] state them).
+
 One "step" = one pass of the hot path (fused NTT -> pointwise -> INTT kernel) over one batch
 of synthetic polynomial pairs.  Default workload = BASELINE.json configs[1]: batch 2^16 at
 the reference default (n=256, q=12289).  With N>1 (torchrun, one process per GPU) every rank
@@ -268,6 +274,170 @@ def run_reference_arm(args, n, q, psi, logb, desc):
 # --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
+def load_fixture():
+    """The reference's coefficient files (row 8 of the (256, 12289) batch); the committed
+    copy under tests/golden (a fixture file, not the oracle)."""
+    try:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "ref_256_12289.npz"))
+        return g["fixture_a"], g["fixture_b"]
+    except Exception:
+        return None
+
+
+def slots_per_polymul(n: int, plantard: bool) -> int:
+    """fmaheavy issue slots per product as the kernels are written: Shoup butterfly = IMAD.HI (2 slots:
+    measured half rate) + 2 IMAD; pointwise Montgomery = 2 IMAD.HI + 2 IMAD; the n^-1 scaling costs one
+    extra multiplication on the sum branch of the last stage.  Plantard (q <= 12385): butterfly 3,
+    pointwise 4, scale 3; at n <= 256 butterfly and scale 2 (IMAD, SHF, IMAD, SHF)."""
+    bflies = 3 * (n // 2) * (n.bit_length() - 1)
+    if plantard and n <= 256:
+        return 2 * bflies + 4 * n + 2 * (n // 2)
+    if plantard:
+        return 3 * bflies + 4 * n + 3 * (n // 2)
+    return 4 * bflies + 6 * n + 4 * (n // 2)
+
+
+def check_rows(mod, n, q, cyclic, a, b, c, rows, fixture_c=None):
+    """Rows of the timed output against the CPU checker: the compiled unmodified reference
+    (oracle/_ref: optimized CT and plain GS variants) at (256, 12289), the oracle port elsewhere."""
+    from oracle import loader
+    import torch
+    ti = torch.as_tensor(rows, device=a.device)
+    ha, hb, hc = a[ti].cpu().numpy(), b[ti].cpu().numpy(), c[ti].cpu().numpy()
+    if (n, q) == (256, 12289) and loader.reference_available():
+        R = loader.Reference()
+        ok = all(bool((R.product(ha, hb, v) == hc).all()) for v in (loader.REF_RED_CT, loader.REF_GS))
+        return ok, "oracle/_ref (ntt_red256_product1, ntt256_product4)"
+    from concurrent.futures import ThreadPoolExecutor
+    O = loader.Oracle()
+    variant = loader.PRODUCT_CYCLIC if cyclic else loader.PRODUCT_MERGED
+    O.plan(n, q, 0)
+    th = max(1, min(host_cores(), len(rows) // 2))
+    cuts = [len(rows) * i // th for i in range(th + 1)]
+    with ThreadPoolExecutor(th) as ex:
+        parts = list(ex.map(lambda i: O.product(n, q, ha[cuts[i]:cuts[i + 1]], hb[cuts[i]:cuts[i + 1]], variant), range(th)))
+    return bool((np.concatenate(parts) == hc).all()), "oracle port (ntt_oracle.c, merged CT-fwd/GS-inv)"
+
+
+class Workload:
+    """One BASELINE configuration resident on this rank's GPU: plan, rotating operand sets built
+    from the SURVEY 8d generator, and the timing loops over it."""
+
+    def __init__(self, mod, sh, torch, name, dev, rank, world, rows_per_gpu=None, row_offset=None):
+        self.mod, self.sh, self.torch, self.name, self.dev, self.rank, self.world = mod, sh, torch, name, dev, rank, world
+        self.n, self.q, self.psi, logb, self.desc = WORKLOADS[name]
+        self.full_batch = 1 << logb
+        self.batch = rows_per_gpu if rows_per_gpu is not None else self.full_batch
+        self.cyclic = (self.q - 1) % (2 * self.n) != 0          # q=3329, n=256: no 512-th root of unity
+        self.plan = mod.Plan(self.n, self.q, self.psi, cyclic=self.cyclic)
+        self.plantard = "plantard" in self.plan.describe()
+        row_bytes = self.n * 4
+        # distinct buffer sets so that successive steps never find their inputs in the 126 MB L2
+        self.sets = max(2, -(-3 * L2_BYTES // (3 * self.batch * row_bytes)) + 1)
+        cfg = {"c2": 2, "c3": 3, "c3c": 3, "c4": 4, "c5": 5, "c5h": 5}[name]
+        off = row_offset if row_offset is not None else rank * self.batch
+        fixture = load_fixture()
+        self.bufs = []
+        for k in range(self.sets):
+            # set 0 is the SURVEY 8d batch itself (splitmix64 stream of config `cfg`, edge rows 0..7,
+            # the reference's coefficient files in row 8); the other sets continue the same stream
+            a, b = mod.inputs.survey_batch(self.n, self.q, self.batch, cfg, device=dev, fixture=fixture,
+                                           row_offset=off + k * (self.full_batch * max(1, world)))
+            self.bufs.append((a, b, torch.empty_like(a)))
+        self.stream = torch.cuda.current_stream().cuda_stream
+        self.alg_bytes = 12 * self.n * self.batch               # read a, read b, write c (int32 API)
+        self.launches_per_step = None
+
+    def step(self, i):
+        a, b, c = self.bufs[i % self.sets]
+        self.plan.polymul_dev(c.data_ptr(), a.data_ptr(), b.data_ptr(), self.batch, self.stream)
+
+    def timed(self, steps, warmup, local, clocks=True):
+        """K steps between two events, barrier + synchronize on both sides, max over ranks."""
+        torch, sh = self.torch, self.sh
+        sampler = ClockSampler(local) if clocks else None
+        if sampler:
+            sampler.start()
+        for i in range(warmup):
+            self.step(i)
+        self.launches_per_step = self.mod.last_launch_count()
+        torch.cuda.synchronize()
+        sh.barrier(local)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler:
+            sampler.timed(True)
+        e0.record()
+        for i in range(steps):
+            self.step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.timed(False)
+        sh.barrier(local)
+        ms_local = e0.elapsed_time(e1)
+        ms = sh.max_over_ranks(ms_local, self.dev)
+        return ms, ms_local, (sampler.stop() if sampler else None)
+
+    def per_launch_ms(self, steps):
+        torch = self.torch
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(steps, 50))]
+        for i, (s, e) in enumerate(evs):
+            s.record()
+            self.step(i)
+            e.record()
+        torch.cuda.synchronize()
+        return statistics.mean(s.elapsed_time(e) for s, e in evs)
+
+    def parity(self, last_step, nrows):
+        """The output of the last timed step against the CPU checker: edge rows 0..8, the last rows and
+        `nrows` rows drawn over the batch."""
+        a, b, c = self.bufs[last_step % self.sets]
+        rng = np.random.default_rng(7)
+        rows = np.unique(np.r_[0:min(9, self.batch), max(0, self.batch - 4):self.batch,
+                               rng.integers(0, self.batch, nrows)])
+        ok, checker = check_rows(self.mod, self.n, self.q, self.cyclic, a, b, c, rows)
+        return ok, checker, int(rows.size)
+
+    def fractions(self, rate_per_gpu, peak_gbs, imad_peak):
+        n = self.n
+        modmuls = 3 * (n // 2) * (n.bit_length() - 1) + n      # SURVEY 8d: M
+        slots = slots_per_polymul(n, self.plantard)
+        return {"hbm_frac": rate_per_gpu * 12 * n / 1e9 / peak_gbs,
+                "imad_frac_survey_3_per_modmul": rate_per_gpu * 3 * modmuls / imad_peak if imad_peak else None,
+                "imad_slot_frac_as_written": rate_per_gpu * slots / imad_peak if imad_peak else None}
+
+    def close(self):
+        self.plan.close()
+        self.bufs = []
+        self.torch.cuda.empty_cache()
+
+
+def side_workload(mod, sh, torch, name, dev, rank, world, local, peak_gbs, imad_peak, budget_s=0.35,
+                  rows_per_gpu=None, row_offset=None, parity_rows=None):
+    """A non-headline BASELINE configuration, measured in the same run: value, time per step, both
+    roofline fractions, clocks during its timed region, parity of its last output."""
+    w = Workload(mod, sh, torch, name, dev, rank, world, rows_per_gpu=rows_per_gpu, row_offset=row_offset)
+    try:
+        ms1, _, _ = w.timed(2, 3, local, clocks=False)              # sizing run
+        steps = int(max(5, min(400, budget_s * 1e3 / max(ms1 / 2, 1e-3))))
+        ms, ms_local, clocks = w.timed(steps, 3, local)
+        total_rows = sh.sum_over_ranks(float(w.batch), dev)
+        value = total_rows * steps / (ms * 1e-3)
+        if parity_rows is None:
+            parity_rows = 4096 if w.n <= 1024 else 24
+        ok, checker, nchecked = w.parity(steps - 1, parity_rows)
+        rec = {"workload": w.desc, "n": w.n, "q": w.q, "rows_per_gpu": w.batch, "rows_total": int(total_rows),
+               "value": value, "unit": "polymul/s", "steps": steps, "warmup": 3, "ms_per_step": ms / steps,
+               "launches_per_step": w.launches_per_step, "plan": w.plan.describe(), "clocks": clocks,
+               "parity_ok": ok, "parity_rows_checked": nchecked, "parity_checker": checker,
+               "l2": f"{w.sets} rotating buffer sets ({w.sets * 3 * w.batch * w.n * 4 >> 20} MiB)"}
+        rec.update(w.fractions(w.batch * steps / (ms_local * 1e-3), peak_gbs, imad_peak))
+        return rec
+    finally:
+        w.close()
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -276,6 +446,8 @@ def main() -> int:
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-workloads", action="store_true",
+                    help="skip the c3/c4/c5 records and the strong-scaling record of the default run")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
     args = ap.parse_args()
     n, q, psi, logb, desc = WORKLOADS[args.workload]
@@ -299,57 +471,32 @@ def main() -> int:
     # narrow / widen the rows of the host-buffer call (csrc/hostwire.c)
     os.environ.setdefault("NTTB200_HOST_THREADS", str(max(1, host_cores() // max(1, world))))
     warmup = max(3, args.warmup)
+    peak_gbs, peak_src = measured_peaks()
+    imad_peak = mod.measure_int_peak(0)
+    imadhi_peak = mod.measure_int_peak(1)
+    bfly_peak = mod.measure_int_peak(3)
 
-    cyclic = (q - 1) % (2 * n) != 0                  # q=3329, n=256: no 512-th root of unity
-    plan = mod.Plan(n, q, psi, cyclic=cyclic)
+    W = Workload(mod, sh, torch, args.workload, dev, rank, world)
+    plan, bufs, sets, stream = W.plan, W.bufs, W.sets, W.stream
     row_bytes = n * 4
-    # distinct buffer sets so that successive steps never find their inputs in the 126 MB L2
-    sets = max(2, -(-3 * L2_BYTES // (3 * batch * row_bytes)) + 1)
-    g = torch.Generator(device=dev).manual_seed(SEED % (2**31) + rank)
-    bufs = []
-    for _ in range(sets):
-        a = torch.randint(0, q, (batch, n), dtype=torch.int32, device=dev, generator=g)
-        b = torch.randint(0, q, (batch, n), dtype=torch.int32, device=dev, generator=g)
-        c = torch.empty_like(a)
-        bufs.append((a, b, c))
-    stream = torch.cuda.current_stream().cuda_stream
-
-    def step(i):
-        a, b, c = bufs[i % sets]
-        plan.polymul_dev(c.data_ptr(), a.data_ptr(), b.data_ptr(), batch, stream)
-
-    sampler = ClockSampler(local)
-    sampler.start()
-    for i in range(warmup):
-        step(i)
-    launches_per_step = mod.last_launch_count()
-    torch.cuda.synchronize()
-    sh.barrier(local)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.timed(True)
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    e1.record()
-    torch.cuda.synchronize()
-    sampler.timed(False)
-    sh.barrier(local)
-    ms_local = e0.elapsed_time(e1)
-    ms = sh.max_over_ranks(ms_local, dev)
-    clocks = sampler.stop()
+    ms, ms_local, clocks = W.timed(args.steps, warmup, local)
+    launches_per_step = W.launches_per_step
     value = world * batch * args.steps / (ms * 1e-3)
+    parity_ok, parity_checker, parity_rows = W.parity(args.steps - 1, 4096 if n <= 1024 else 24)
 
     # per-launch duration of the dominant kernel, CUDA events on the launching stream
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 50))]
-    for i, (s, e) in enumerate(evs):
-        s.record()
-        step(i)
-        e.record()
-    torch.cuda.synchronize()
-    launch_ms = statistics.mean(s.elapsed_time(e) for s, e in evs)
+    launch_ms = W.per_launch_ms(args.steps)
     # a back-to-back stream hides launch gaps: the K-step region gives the better per-launch figure
     per_launch_ms = min(launch_ms, ms_local / args.steps) / max(1, launches_per_step)
+
+    # sustained: the same step back to back for >= 1 s (the K-step region above can be as short as a
+    # millisecond), with the clocks sampled every 2 ms throughout
+    sust_steps = int(max(args.steps, min(200000, 1.25e3 / max(ms_local / args.steps, 1e-3))))
+    ms_s, ms_s_local, clocks_s = W.timed(sust_steps, 3, local)
+    sustained = {"value": world * batch * sust_steps / (ms_s * 1e-3), "unit": "polymul/s", "steps": sust_steps,
+                 "seconds": ms_s * 1e-3, "ms_per_step": ms_s / sust_steps, "clocks": clocks_s,
+                 "hbm_frac": batch * sust_steps / (ms_s_local * 1e-3) * 12 * n / 1e9 / peak_gbs,
+                 "vs_value": (world * batch * sust_steps / (ms_s * 1e-3)) / value}
 
     # supplementary: the same K steps issued alternately on two streams (consecutive batches are
     # independent), which hides the start-up and drain of one launch behind the other -- what a
@@ -375,15 +522,6 @@ def main() -> int:
         two = {"value": world * batch * args.steps / (ms2 * 1e-3), "unit": "polymul/s", "streams": 2,
                "hbm_frac": None, "note": "same steps, alternating over two streams; not the headline value"}
 
-    # parity spot check of what was just timed (never skip work silently)
-    from oracle import loader
-    O = loader.Oracle()
-    a, b, c = bufs[(args.steps - 1) % sets]
-    idx = torch.tensor([0, 1, batch // 2, batch - 1], device=dev)
-    variant = loader.PRODUCT_CYCLIC if cyclic else loader.PRODUCT_MERGED
-    want = O.product(n, q, a[idx].cpu().numpy(), b[idx].cpu().numpy(), variant)
-    parity_ok = bool((c[idx].cpu().numpy() == want).all())
-
     # e2e: host buffers (pinned) through nttb200_polymul_batch: H2D + kernel + D2H per step
     e2e_steps = args.e2e_steps or min(args.steps, 20)
     ha, hb, hc = mod.host_alloc((batch, n)), mod.host_alloc((batch, n)), mod.host_alloc((batch, n))
@@ -396,9 +534,10 @@ def main() -> int:
     for _ in range(e2e_steps):
         plan.polymul_host_ptr(hc.ptr, ha.ptr, hb.ptr, batch)
     e2e_s = sh.max_over_ranks(time.perf_counter() - t0, dev)
-    rows = np.unique(np.r_[0:2, batch // 2 - 1:batch // 2 + 1, batch - 2:batch,
-                           np.random.default_rng(7).integers(0, batch, 26)])
-    e2e_ok = bool((hc.array[rows] == O.product(n, q, ha.array[rows], hb.array[rows], variant)).all())
+    hcd = torch.from_numpy(hc.array).to(dev)
+    rows = np.unique(np.r_[0:9, batch - 4:batch, np.random.default_rng(11).integers(0, batch, 4096 if n <= 1024 else 24)])
+    e2e_ok, _ = check_rows(mod, n, q, W.cyclic, bufs[0][0], bufs[0][1], hcd, rows)
+    del hcd
     e2e_value = world * batch * e2e_steps / e2e_s
     # what crossed the PCIe link in the last timed call: 16-bit words for the rows the host pool
     # narrowed (half-word moduli, csrc/hostwire.c), the caller's 32-bit words for the rest
@@ -408,7 +547,6 @@ def main() -> int:
     h2d_bytes = 2 * (2 * ws["rows16"] + 4 * ws["rows32"]) * n
     d2h_bytes = (2 * ws["result_rows16"] + 4 * (batch - ws["result_rows16"])) * n
 
-    peak_gbs, peak_src = measured_peaks()
     # the standalone NTT call surface (in place, 8n bytes per transform): HBM-bound kernels.
     # Run on the a-buffers of the rotating sets (after the product has been timed and checked).
     ntt_lines = {}
@@ -429,39 +567,59 @@ def main() -> int:
             ntt_lines[kind] = {"transforms_per_s": batch / (tms * 1e-3), "achieved_GBs": gbs, "frac_of_hbm_peak": gbs / peak_gbs}
     except Exception as ex:
         ntt_lines = {"error": repr(ex)}
-    alg_bytes = 12 * n * batch                      # read a, read b, write c (int32 API)
-    # n <= 1024: one fused kernel per step.  n > 1024: the step is a pipeline of 3 kernels per
-    # L2-resident batch chunk; the roofline is then stated for the whole pipeline (step time).
+    alg_bytes = W.alg_bytes
+    # n <= 1024: one fused kernel per step.  n > 1024: the step is a pipeline of kernels; the
+    # roofline is then stated for the whole pipeline (step time).
     roof_ms = per_launch_ms if launches_per_step == 1 else min(launch_ms, ms_local / args.steps)
     achieved = alg_bytes / (roof_ms * 1e-3) / 1e9
     logn = n.bit_length() - 1
     bflies = 3 * (n // 2) * logn
     modmuls = bflies + n                            # M
-    # fmaheavy issue slots per product as the kernels are written: Shoup butterfly = IMAD.HI
-    # (2 slots: measured half rate) + 2 IMAD; pointwise Montgomery = 2 IMAD.HI + 2 IMAD; the
-    # n^-1 scaling costs one extra Shoup multiplication on the sum branch of the last stage
-    plantard = "plantard" in plan.describe()
-    if plantard and n <= 256:   # half-word second product: 2 IMAD (+ 2 shifts on the ALU pipe) per butterfly
-        slots = 2 * bflies + 4 * n + 2 * (n // 2)
-    elif plantard:    # IMAD + IMAD.HI per butterfly (3), 2 IMAD + IMAD.HI pointwise (4), 3 per n^-1 scale
-        slots = 3 * bflies + 4 * n + 3 * (n // 2)
-    else:
-        slots = 4 * bflies + 6 * n + 4 * (n // 2)
-    imad_peak = mod.measure_int_peak(0)
-    imadhi_peak = mod.measure_int_peak(1)
-    bfly_peak = mod.measure_int_peak(3)
+    plantard = W.plantard
+    slots = slots_per_polymul(n, plantard)
     rate = batch / (roof_ms * 1e-3)
     int_achieved = rate * 3 * modmuls
     slot_achieved = rate * slots
     traffic = TRAFFIC_NCU.get(args.workload)
+    plan_desc, plan_psi = plan.describe(), plan.psi
+    for h in (ha, hb, hc):
+        h.free()
+    W.close()
+
+    # the other BASELINE configurations, measured by the same run (each a few hundred ms of device
+    # time), and -- for N > 1 -- configs[2]/[3] as BASELINE.json states them: ONE fixed batch sliced
+    # by nttb200_shard_bounds over the ranks (strong scaling)
+    side, strong = {}, {}
+    if args.workload == "c2" and not args.no_side_workloads:
+        for name in ("c3", "c4", "c5"):
+            try:
+                side[name] = side_workload(mod, sh, torch, name, dev, rank, world, local, peak_gbs, imad_peak)
+            except Exception as ex:
+                side[name] = {"error": repr(ex)}
+        for name in ("c3", "c4"):
+            if world == 1:
+                if "value" in side.get(name, {}):
+                    strong[name] = {k: side[name][k] for k in ("value", "ms_per_step", "rows_per_gpu", "rows_total", "parity_ok")}
+                continue
+            try:
+                full = 1 << WORKLOADS[name][3]
+                lo, hi = mod.shard_bounds(full, world, rank)
+                r = side_workload(mod, sh, torch, name, dev, rank, world, local, peak_gbs, imad_peak,
+                                  rows_per_gpu=hi - lo, row_offset=lo)
+                strong[name] = {k: r[k] for k in ("value", "ms_per_step", "rows_per_gpu", "rows_total", "parity_ok",
+                                                  "steps", "clocks")}
+            except Exception as ex:
+                strong[name] = {"error": repr(ex)}
 
     line = {
         "metric": "polymul/s", "value": value, "unit": "polymul/s", "n_gpus": world,
         "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
         "data": "synthetic",
-        "config": {"workload": desc, "n": n, "q": q, "psi": plan.psi, "batch_per_gpu": batch,
-                   "plan": plan.describe(),
+        "config": {"workload": desc, "n": n, "q": q, "psi": plan_psi, "batch_per_gpu": batch,
+                   "plan": plan_desc,
+                   "inputs": "SURVEY 8d batch: splitmix64 stream, coefficient = next() % q, edge rows 0..7 "
+                             "(0, q-1, delta_0, delta_{n-1}, KATs 1-4), the reference's coefficient files in row 8",
                    "l2": f"inputs rotate over {sets} buffer sets ({sets * 3 * batch * row_bytes >> 20} MiB) "
                          f"> 126 MB L2, so no step finds its operands cached",
                    "parallelism": f"batch-sharded x{world}, no collective"},
@@ -474,10 +632,11 @@ def main() -> int:
                 "host_bytes_per_step": 3 * batch * row_bytes, "parity_ok": e2e_ok},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
+        "sustained": sustained,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                      "kernel": ("polymul_plant_kernel" if plantard else "polymul_small_kernel") if n <= 1024 else
-                               "large_cols_fwd + large_rows_polymul + large_cols_inv (whole step)",
+                               "large-n product pipeline (whole step)",
                      "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": roof_ms,
                      "traffic_source": TRAFFIC_SRC.get(args.workload)},
         "int_roofline": {"bound": "multiplier (fmaheavy) pipe; the n<=256 Plantard kernel trades multiplier slots for "
@@ -491,12 +650,13 @@ def main() -> int:
                          "imad_hi_peak": imadhi_peak, "lazy_butterflies_per_s_peak": bfly_peak,
                          "note": "peak = independent IMAD chains on every SM, measured live "
                                  "(nttb200_measure_int_peak); IMAD.HI measured at half that rate so it "
-                                 "counts 2 slots. Shoup kernels: butterfly 4, pointwise 6, n^-1 scale 4 per "
-                                 "pair; Plantard kernel (q<=12385): butterfly 3, pointwise 4, scale 3 at n=512/1024; at n<=256 butterfly and scale 2 (IMAD, SHF, IMAD, SHF: the second product takes only the upper half of the first)",
+                                 "counts 2 slots (slots_per_polymul in bench.py)",
                          "arith": "plantard" if plantard else "shoup"},
-        "parity_ok": parity_ok,
+        "parity_ok": parity_ok, "parity_rows_checked": parity_rows, "parity_checker": parity_checker,
         "two_streams": two,
         "standalone_ntt": ntt_lines,
+        "workloads": side,
+        "strong_scaling": strong,
     }
     if two:
         two["hbm_frac"] = two["value"] / world * 12 * n / 1e9 / peak_gbs
@@ -505,15 +665,13 @@ def main() -> int:
             line["cpu_baseline"] = cpu_baseline(n, q, psi)
         except Exception as ex:  # the baseline is a report, never a reason to lose the GPU line
             line["cpu_baseline"] = {"value": None, "error": repr(ex)}
-    for h in (ha, hb, hc):
-        h.free()
-    plan.close()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
-    return 0 if (parity_ok and e2e_ok) else 1
+    side_ok = all(r.get("parity_ok", False) for r in list(side.values()) + list(strong.values()) if "error" not in r)
+    return 0 if (parity_ok and e2e_ok and side_ok) else 1
 
 
 if __name__ == "__main__":
