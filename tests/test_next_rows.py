@@ -256,7 +256,9 @@ def test_reference_fpga_host_program_runs_on_the_plugin(gpu, tmp_path):
     ./terasic_pcie_qsys.so (our plugin), streams W/W_INV/q/n_inv, A, B, pulses GO, polls STATUS,
     reads C back and checks {2, 4, 6} itself (v2.c:232-238)."""
     os.symlink(os.path.join(PKG_DIR, "terasic_pcie_qsys.so"), tmp_path / "terasic_pcie_qsys.so")
-    out = subprocess.run([_refbin("ntt_pcie_v2")], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    # the plugin finds libnttb200.so next to itself ($ORIGIN); through the symlink it needs the path
+    env = dict(os.environ, LD_LIBRARY_PATH=PKG_DIR + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    out = subprocess.run([_refbin("ntt_pcie_v2")], cwd=tmp_path, capture_output=True, text=True, timeout=300, env=env)
     text = out.stdout + out.stderr
     assert out.returncode == 0 and "PCIE_Load failed" not in text and "PCIE_Open failed" not in text, text
     assert "TB: Sinal 'done_all' recebido!" in text
