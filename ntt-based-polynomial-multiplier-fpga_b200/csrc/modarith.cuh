@@ -73,8 +73,13 @@ __device__ __forceinline__ uint32_t mont_mul(uint32_t a, uint32_t b, const ModQ 
  * callers (LAZY); HARVEY/CANON keep fixed ranges.
  * ------------------------------------------------------------------------------- */
 
-/* Cooley-Tukey: (X, Y) -> (X + wY, X - wY)     [reference: R/NTT/ntt.C:323-326] */
-template <int ARITH>
+/* Cooley-Tukey: (X, Y) -> (X + wY, X - wY)     [reference: R/NTT/ntt.C:323-326]
+ * CANON class, LAZYOUT: a Shoup multiplication takes ANY 32-bit input, so the two results of a
+ * butterfly need their conditional subtractions only if the NEXT stage adds to them (its X leg);
+ * when both go into the next stage's multiplication (its Y leg) they may stay in [0, 2q) --
+ * 2q < 2^32 for every q < 2^31 -- which saves two of the eight instructions.  The callers know
+ * at compile time which butterflies those are (the next stage's index bit of their registers). */
+template <int ARITH, bool LAZYOUT = false>
 __device__ __forceinline__ void ct_bfly(uint32_t &X, uint32_t &Y, uint32_t w, uint32_t wp,
                                         const ModQ &m) {
   if (ARITH == ARITH_LAZY) {
@@ -88,9 +93,14 @@ __device__ __forceinline__ void ct_bfly(uint32_t &X, uint32_t &Y, uint32_t w, ui
     X = X + T;
   } else {
     uint32_t T = csub(shoup_mul(Y, w, wp, m), m.q);   /* [0,q) */
-    uint32_t s = X + T, d = X - T;
-    X = csub(s, m.q);
-    Y = min(d, d + m.q);
+    if (LAZYOUT) {
+      Y = X - T + m.q;                                /* (0, 2q) */
+      X = X + T;                                      /* [0, 2q) */
+    } else {
+      uint32_t s = X + T, d = X - T;
+      X = csub(s, m.q);
+      Y = min(d, d + m.q);
+    }
   }
 }
 
@@ -108,9 +118,8 @@ __device__ __forceinline__ void gs_bfly(uint32_t &X, uint32_t &Y, uint32_t w, ui
     X = csub(X + Y, m.q2);
     Y = shoup_mul(d, w, wp, m);
   } else {
-    uint32_t s = X + Y, d = X - Y;               /* X,Y in [0,q) */
+    uint32_t s = X + Y, d = X - Y + m.q;         /* X,Y in [0,q); d in (0, 2q): any 32-bit value may be multiplied */
     X = csub(s, m.q);
-    d = min(d, d + m.q);
     Y = csub(shoup_mul(d, w, wp, m), m.q);
   }
 }

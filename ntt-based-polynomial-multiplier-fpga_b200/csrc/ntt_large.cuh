@@ -48,6 +48,9 @@ struct LargeParams {
   uint2 last_y;               /* K3: multiplier of its diff branch (twiddle p[1] * scale)    */
   uint2 one;                  /* (1, floor(2^32/q)): Shoup pair that only reduces            */
   uint32_t zero;              /* always 0 (modq_regs)                                        */
+  uint2 utw[32];              /* column passes: entries [1, 32) of the table of this launch's
+                                 direction -- the twiddles of the register phase on the high row
+                                 bits, whose indices are compile-time numbers (constant bank)   */
 };
 
 constexpr int LARGE_LR = 8;       /* rows of 2^8 coefficients: fixed, so row strides are immediates */
@@ -63,6 +66,9 @@ struct ColGeom {
   static constexpr int TILE_COLS = 32 * CPL;                  /* adjacent columns per CTA                  */
   static constexpr int LOG_TILE = (CPL == 2) ? 6 : 5;
   static constexpr int SMEM_BYTES = (RB > 0) ? ROWS * TILE_COLS * 4 : 0;
+  /* resident CTAs asked of ptxas: every warp slot of the SM while a thread holds <= 16 vectors of one
+   * column (32 registers then suffice); the latency of the strided row loads is hidden by warps only */
+  static constexpr int MINB = (NV * CPL <= 16) ? ((2048 / (WARPS * 32)) > 32 ? 32 : (2048 / (WARPS * 32))) : 1;
 };
 /* columns per lane: 1 (32-bit accesses, 128-byte row segments per warp) or 2 (64-bit accesses,
  * 256-byte segments, half the load/store instructions; operands must be 8-byte aligned).
@@ -99,10 +105,16 @@ __device__ __forceinline__ void cv_st(uint32_t *p, const CVec<CPL> &x) {
   if (CPL == 1) *p = x.v[0];
   else *reinterpret_cast<uint2 *>(p) = make_uint2(x.v[0], x.v[CPL - 1]);
 }
-template <int ARITH, int CPL>
+template <int ARITH, int CPL, bool LAZYOUT = false>
 __device__ __forceinline__ void cv_ct(CVec<CPL> &X, CVec<CPL> &Y, uint2 tw, const ModQ &m) {
 #pragma unroll
-  for (int c = 0; c < CPL; c++) ct_bfly<ARITH>(X.v[c], Y.v[c], tw.x, tw.y, m);
+  for (int c = 0; c < CPL; c++) ct_bfly<ARITH, LAZYOUT>(X.v[c], Y.v[c], tw.x, tw.y, m);
+}
+/* CANON: the results may stay in [0, 2q) when the next stage (register bit `bit` - 1) multiplies both */
+template <int ARITH, int CPL>
+__device__ __forceinline__ void cv_ct_at(CVec<CPL> &X, CVec<CPL> &Y, uint2 tw, const ModQ &m, int k, int bit) {
+  if (ARITH == ARITH_CANON && bit > 0 && ((k >> (bit - 1)) & 1)) cv_ct<ARITH, CPL, true>(X, Y, tw, m);
+  else cv_ct<ARITH, CPL>(X, Y, tw, m);
 }
 template <int ARITH, int CPL>
 __device__ __forceinline__ void cv_gs(CVec<CPL> &X, CVec<CPL> &Y, uint2 tw, const ModQ &m, uint32_t yb) {
@@ -125,7 +137,7 @@ __device__ __forceinline__ uint32_t canon_fwd(uint32_t x, uint2 one, const ModQ 
  * in the same class, so nothing is reduced here.
  * ===================================================================================== */
 template <int K1, int ARITH, int CPL>
-__global__ void __launch_bounds__(ColGeom<K1>::WARPS * 32)
+__global__ void __launch_bounds__(ColGeom<K1>::WARPS * 32, ColGeom<K1, CPL>::MINB)
 large_cols_fwd_kernel(const __grid_constant__ LargeParams P) {
   using G = ColGeom<K1, CPL>;
   using V = CVec<CPL>;
@@ -155,8 +167,8 @@ large_cols_fwd_kernel(const __grid_constant__ LargeParams P) {
 #pragma unroll
     for (int k = 0; k < G::NV; k++) {
       if (k & (1 << bit)) continue;
-      const uint2 tw = __ldg(P.tab + (1 << s) + (k >> (bit + 1)));
-      cv_ct<ARITH, CPL>(x[k], x[k | (1 << bit)], tw, m);
+      const uint2 tw = P.utw[(1 << s) + (k >> (bit + 1))];      /* constant bank: the index is a compile-time number */
+      cv_ct_at<ARITH, CPL>(x[k], x[k | (1 << bit)], tw, m, k, bit);
     }
   }
   if (G::RB == 0) {
@@ -185,7 +197,7 @@ large_cols_fwd_kernel(const __grid_constant__ LargeParams P) {
       for (int kk = 0; kk < (1 << G::RB); kk++) {
         if (kk & (1 << bit)) continue;
         const uint2 tw = __ldg(P.tab + (1 << (G::RA + s)) + (hfix << s) + (kk >> (bit + 1)));
-        cv_ct<ARITH, CPL>(x[(g << G::RB) + kk], x[(g << G::RB) + (kk | (1 << bit))], tw, m);
+        cv_ct_at<ARITH, CPL>(x[(g << G::RB) + kk], x[(g << G::RB) + (kk | (1 << bit))], tw, m, kk, bit);
       }
     }
   }
@@ -210,13 +222,13 @@ __device__ __forceinline__ void gs_last(uint32_t &X, uint32_t &Y, uint32_t yb, u
   uint32_t s, d;
   if (ARITH == ARITH_LAZY) { d = X - Y + yb; s = X + Y; }
   else if (ARITH == ARITH_HARVEY) { d = X - Y + m.q2; s = X + Y; }
-  else { s = X + Y; d = X - Y; d = min(d, d + m.q); }
+  else { s = X + Y; d = X - Y + m.q; }
   Y = csub(shoup_mul(d, ly.x, ly.y, m), m.q);
   X = csub(shoup_mul(s, lx.x, lx.y, m), m.q);
 }
 
 template <int K1, int ARITH, int CPL>
-__global__ void __launch_bounds__(ColGeom<K1>::WARPS * 32)
+__global__ void __launch_bounds__(ColGeom<K1>::WARPS * 32, ColGeom<K1, CPL>::MINB)
 large_cols_inv_kernel(const __grid_constant__ LargeParams P) {
   using G = ColGeom<K1, CPL>;
   using V = CVec<CPL>;
@@ -279,7 +291,7 @@ large_cols_inv_kernel(const __grid_constant__ LargeParams P) {
     for (int k = 0; k < G::NV; k++) {
       if (k & (1 << bit)) continue;
       if (bit < G::RA - 1) {
-        const uint2 tw = __ldg(P.tab_inv + (1 << (G::RA - 1 - bit)) + (k >> (bit + 1)));
+        const uint2 tw = P.utw[(1 << (G::RA - 1 - bit)) + (k >> (bit + 1))];
         cv_gs<ARITH, CPL>(x[k], x[k | (1 << bit)], tw, m, yb);
       } else {
 #pragma unroll
@@ -375,7 +387,7 @@ large_rows_polymul_kernel(const __grid_constant__ LargeParams P) {
   {
     LaneTw<LR> twl;
     load_row_lane_tw<LR>(twl, P.tab, l, k1, j);
-    fwd_phase_rows<LR, ARITH>(xa, twl, m);
+    fwd_phase_rows<LR, ARITH, true>(xa, twl, m);
     fwd_phase_rows<LR, ARITH>(xb, twl, m);
   }
 #pragma unroll

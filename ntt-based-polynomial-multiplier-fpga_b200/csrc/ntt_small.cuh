@@ -253,13 +253,19 @@ __device__ __forceinline__ void fwd_phase_cols(uint32_t (&x)[SmallGeom<L>::NV],
       if (k & (1 << kb)) continue;
       const int j = k >> (kb + 1);
       const uint2 w = tw[(1 << s) + j];
-      ct_bfly<ARITH>(x[k], x[k | (1 << kb)], w.x, w.y, m);
+      /* both results go into the next stage's multiplication when the next register bit is set */
+      if (ARITH == ARITH_CANON && kb > 0 && ((k >> (kb - 1)) & 1))
+        ct_bfly<ARITH, true>(x[k], x[k | (1 << kb)], w.x, w.y, m);
+      else
+        ct_bfly<ARITH>(x[k], x[k | (1 << kb)], w.x, w.y, m);
     }
   }
 }
 
-/* forward, layout 2: index bits H-1 .. 0 (register bits H-1 .. 0 of r_lo), lane twiddles */
-template <int L, int ARITH>
+/* forward, layout 2: index bits H-1 .. 0 (register bits H-1 .. 0 of r_lo), lane twiddles.
+ * LASTLAZY (CANON): the results of the very last stage stay in [0, 2q) -- for the ONE operand of
+ * the pointwise Montgomery product that may (a b < 2q q < q 2^32). */
+template <int L, int ARITH, bool LASTLAZY = false>
 __device__ __forceinline__ void fwd_phase_rows(uint32_t (&x)[SmallGeom<L>::NV], const LaneTw<L> &tw,
                                                const ModQ &m) {
   using Gm = SmallGeom<L>;
@@ -272,7 +278,10 @@ __device__ __forceinline__ void fwd_phase_rows(uint32_t (&x)[SmallGeom<L>::NV], 
       const int g = r >> Gm::H;
       const int u = (r & (Gm::T - 1)) >> (bit + 1);
       const uint2 w = tw.get(g, lv, u);
-      ct_bfly<ARITH>(x[r], x[r | (1 << bit)], w.x, w.y, m);
+      if (ARITH == ARITH_CANON && ((bit > 0 && ((r >> (bit - 1)) & 1)) || (bit == 0 && LASTLAZY)))
+        ct_bfly<ARITH, true>(x[r], x[r | (1 << bit)], w.x, w.y, m);
+      else
+        ct_bfly<ARITH>(x[r], x[r | (1 << bit)], w.x, w.y, m);
     }
   }
 }
@@ -328,8 +337,7 @@ __device__ __forceinline__ void inv_phase_cols(uint32_t (&x)[SmallGeom<L>::NV],
           Y = shoup_mul(d, last_y.x, last_y.y, m);
           X = SCALE ? shoup_mul(s, last_x.x, last_x.y, m) : csub(s, m.q2);
         } else {
-          uint32_t s = X + Y, d = X - Y;
-          d = min(d, d + m.q);
+          uint32_t s = X + Y, d = X - Y + m.q;
           Y = shoup_mul(d, last_y.x, last_y.y, m);
           X = SCALE ? shoup_mul(s, last_x.x, last_x.y, m) : csub(s, m.q);
         }
@@ -394,7 +402,7 @@ polymul_small_kernel(const __grid_constant__ SmallParams<SmallGeom<L>::R> P) {
       load_rows<L>(xa, sm_a, l);
       load_rows<L>(xb, sm_b, l);
       if (!TWREG) twf.load(P.tw_fwd, l);
-      fwd_phase_rows<L, ARITH>(xa, twf, m);
+      fwd_phase_rows<L, ARITH, true>(xa, twf, m);
       fwd_phase_rows<L, ARITH>(xb, twf, m);
     }
 

@@ -218,6 +218,7 @@ extern "C" void nttb200_plan_destroy(nttb200_plan *P) {
     if (s.h_a) cudaFreeHost(s.h_a);
   }
   if (P->scratch) cudaFree(P->scratch);
+  if (P->flow_ctl) cudaFree(P->flow_ctl);
   if (P->sched_ring) cudaFree(P->sched_ring);
   if (P->zc_host) cudaFreeHost(P->zc_host);
   for (auto &ln : P->lanes) {
@@ -417,7 +418,13 @@ static int env_int(const char *name, int dflt, int lo, int hi);
   int launch_polymul_large_chunk_##name(const nttb200_plan *, uint32_t *, const uint32_t *,       \
                                         const uint32_t *, uint32_t *, uint32_t *, size_t, cudaStream_t); \
   int launch_ntt_large_##name(const nttb200_plan *, const DevTable &, int, int, uint32_t *, size_t, \
-                              cudaStream_t);
+                              cudaStream_t);                                                        \
+  int large_fused_clusters_##name(const nttb200_plan *, int *);                                     \
+  int large_flow_slots_##name(void);                                                                \
+  int launch_polymul_large_flow_##name(const nttb200_plan *, uint32_t *, const uint32_t *,          \
+                                       const uint32_t *, uint32_t *, unsigned *, size_t, cudaStream_t); \
+  int launch_polymul_large_fused_##name(const nttb200_plan *, uint32_t *, const uint32_t *,         \
+                                        const uint32_t *, uint32_t *, unsigned, size_t, cudaStream_t);
 DECL_LARGE(lazy)
 DECL_LARGE(harvey)
 DECL_LARGE(canon)
@@ -431,6 +438,9 @@ static size_t large_scratch_budget() {
   static size_t v = (size_t)env_int("NTTB200_LARGE_SCRATCH_MB", 32, 1, 65536) << 20;
   return v;
 }
+/* 0: three launches per batch chunk; 1: one persistent cluster kernel (n = 2^15, 2^16);
+ * 2: one persistent dataflow kernel (n = 2^16).  Read per call: tests switch it. */
+static int large_mode() { return env_int("NTTB200_LARGE_FUSED", 0, 0, 2); }
 static int large_lanes() { static int v = env_int("NTTB200_LARGE_LANES", 3, 1, 8); return v; }
 
 static int ensure_scratch(nttb200_plan *P, size_t polys, int lanes) {
@@ -457,6 +467,56 @@ int launch_polymul_large(nttb200_plan *P, uint32_t *c, const uint32_t *a, const 
   std::lock_guard<std::mutex> lock(P->large_mu);
   if (!P->scratch_done) NTT_CUDA(cudaEventCreateWithFlags(&P->scratch_done, cudaEventDisableTiming));
   else NTT_CUDA(cudaStreamWaitEvent(st, P->scratch_done, 0));
+  /* n = 2^15, 2^16: one persistent cluster kernel for the whole batch (ntt_large_fused.cuh); its
+   * scratch is (resident clusters) x 2n words and lives in L2.  NTTB200_LARGE_FUSED=0 keeps the
+   * three-launch pipeline below (the comparison point, and the path of every other n). */
+  const int mode = large_mode();
+  if (mode == 2 && P->logn == 16) {                       /* the ticket dataflow kernel */
+    const int slots = large_flow_slots_canon();
+    int rcf = ensure_scratch(P, (size_t)slots, 1);
+    if (rcf) return rcf;
+    const size_t words = 1 + 3 * batch;
+    if (P->flow_ctl_words < words) {
+      if (P->flow_ctl) cudaFree(P->flow_ctl);
+      P->flow_ctl = nullptr; P->flow_ctl_words = 0;
+      NTT_CUDA(cudaMalloc(&P->flow_ctl, words * sizeof(unsigned)));
+      P->flow_ctl_words = words;
+    }
+    NTT_CUDA(cudaMemsetAsync(P->flow_ctl, 0, words * sizeof(unsigned), st));
+    switch (P->arith) {
+      case ARITH_LAZY: rcf = launch_polymul_large_flow_lazy(P, c, a, b, P->scratch, P->flow_ctl, batch, st); break;
+      case ARITH_HARVEY: rcf = launch_polymul_large_flow_harvey(P, c, a, b, P->scratch, P->flow_ctl, batch, st); break;
+      default: rcf = launch_polymul_large_flow_canon(P, c, a, b, P->scratch, P->flow_ctl, batch, st); break;
+    }
+    if (rcf) return rcf;
+    NTT_CUDA(cudaEventRecord(P->scratch_done, st));
+    return 0;
+  }
+  if (mode >= 1) {
+    if (P->fused_clusters < 0) {
+      int nc = 0, rcq;
+      switch (P->arith) {
+        case ARITH_LAZY: rcq = large_fused_clusters_lazy(P, &nc); break;
+        case ARITH_HARVEY: rcq = large_fused_clusters_harvey(P, &nc); break;
+        default: rcq = large_fused_clusters_canon(P, &nc); break;
+      }
+      if (rcq) { cudaGetLastError(); nc = 0; }
+      P->fused_clusters = nc;
+    }
+    if (P->fused_clusters > 0) {
+      const unsigned clusters = (unsigned)std::min<size_t>(batch, (size_t)P->fused_clusters);
+      int rcf = ensure_scratch(P, (size_t)P->fused_clusters, 1);
+      if (rcf) return rcf;
+      switch (P->arith) {
+        case ARITH_LAZY: rcf = launch_polymul_large_fused_lazy(P, c, a, b, P->scratch, clusters, batch, st); break;
+        case ARITH_HARVEY: rcf = launch_polymul_large_fused_harvey(P, c, a, b, P->scratch, clusters, batch, st); break;
+        default: rcf = launch_polymul_large_fused_canon(P, c, a, b, P->scratch, clusters, batch, st); break;
+      }
+      if (rcf) return rcf;
+      NTT_CUDA(cudaEventRecord(P->scratch_done, st));
+      return 0;
+    }
+  }
   const size_t chunk = std::max<size_t>(1, std::min<size_t>(batch, large_scratch_budget() / (P->n * 8ull)));
   const size_t nchunks = (batch + chunk - 1) / chunk;
   const int lanes = (int)std::min<size_t>((size_t)large_lanes(), nchunks);

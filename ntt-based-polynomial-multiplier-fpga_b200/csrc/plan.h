@@ -88,6 +88,9 @@ struct nttb200_plan {
   /* large-n: internal stream lanes, each with scratch for scratch_polys polynomials */
   uint32_t *scratch = nullptr;
   size_t scratch_polys = 0;
+  unsigned *flow_ctl = nullptr;    /* ticket + per-polynomial completion counters of the dataflow kernel */
+  size_t flow_ctl_words = 0;
+  int fused_clusters = -1;         /* resident clusters of the fused large-n kernel (-1: not asked yet, 0: not covered) */
   std::vector<LargeLane> lanes;
   cudaEvent_t fork = nullptr;
   cudaEvent_t scratch_done = nullptr;   /* end of the last call that used the scratch */

@@ -164,10 +164,20 @@ LARGE_CASES = [(2048, 12289), (4096, 40961), (8192, 65537), (16384, 65537),     
                (2048, 2013265921), (65536, 2013265921), (131072, 2013265921)]     # CANON class
 
 
+FUSED_N = (32768, 65536)      # one persistent cluster kernel (ntt_large_fused.cuh)
+
+
+@pytest.mark.parametrize("fused", [2, 1, 0])
 @pytest.mark.parametrize("n,q", LARGE_CASES)
-def test_large_n_multipass_products(gpu, oracle, n, q):
+def test_large_n_multipass_products(gpu, oracle, monkeypatch, n, q, fused):
     """n > 1024: column pass / row pass / column pass (ntt_large.cuh) against the oracle's
-    merged CT-fwd/GS-inv pipeline; ragged batch (odd, not a multiple of the CTA's 16 rows)."""
+    merged CT-fwd/GS-inv pipeline; ragged batch (odd, not a multiple of the CTA's 16 rows).
+    n = 2^15, 2^16 run the three passes inside ONE persistent kernel (1 launch): the ticket
+    dataflow kernel (NTTB200_LARGE_FUSED=2, the default; n = 2^16) or the cluster kernel (=1);
+    NTTB200_LARGE_FUSED=0 asks for the three-launch pipeline."""
+    if fused != 2 and n not in FUSED_N:
+        pytest.skip("only n = 2^15, 2^16 have the fused kernels")
+    monkeypatch.setenv("NTTB200_LARGE_FUSED", str(fused))
     batch = 21 if n <= 16384 else 5
     p = gpu.Plan(n, q)
     assert "large(multi-pass)" in p.describe()
@@ -183,7 +193,44 @@ def test_large_n_multipass_products(gpu, oracle, n, q):
     assert (got == want).all(), p.describe()
     assert (got[2] == b[2]).all()
     assert got[3][n - 2] == q - 1 and int(got[3].astype(np.int64).sum()) == q - 1
-    assert gpu.last_launch_count() == 3
+    assert gpu.last_launch_count() == (1 if (fused and n in FUSED_N) else 3)
+    if fused == 2 and n == 65536:
+        # more polynomials than scratch slots (48) and than the delay between a polynomial's passes
+        batch = 131
+        a, b = oracle.random((batch, n), q, SEED + 5), oracle.random((batch, n), q, SEED + 6)
+        assert (p.polymul(a, b) == oracle.product(n, q, a, b, 10)).all()
+    p.close()
+
+
+@pytest.mark.parametrize("n,q", [(65536, 2013265921), (65536, 469762049), (65536, 786433), (32768, 2013265921),
+                                 (32768, 786433)])
+@pytest.mark.parametrize("mode", [2, 1])
+def test_fused_kernels_many_polynomials(gpu, oracle_mt, nttb200, monkeypatch, n, q, mode):
+    """More polynomials than resident clusters / scratch slots (every cluster loops and the split
+    barrier between one polynomial's pass 3 and the next one's pass 1 is exercised; the dataflow
+    kernel recycles every scratch slot several times), device-resident, every row against the
+    oracle, twice in a row on the same scratch, and equal to the three-launch pipeline."""
+    import os
+    import torch
+    monkeypatch.setenv("NTTB200_LARGE_FUSED", str(mode))
+    batch = 301
+    p = gpu.Plan(n, q)
+    a, b = nttb200.inputs.survey_batch(n, q, batch, 5, device="cuda")
+    c = torch.empty_like(a)
+    st = torch.cuda.current_stream().cuda_stream
+    want = oracle_mt(n, q, a.cpu().numpy(), b.cpu().numpy(), 10)
+    for _ in range(2):
+        c.zero_()
+        p.polymul_dev(c.data_ptr(), a.data_ptr(), b.data_ptr(), batch, st)
+        torch.cuda.synchronize()
+        assert gpu.last_launch_count() == 1
+        got = c.cpu().numpy()
+        assert (got == want).all(), np.nonzero((got != want).any(axis=1))[0][:8]
+    monkeypatch.setenv("NTTB200_LARGE_FUSED", "0")
+    c2 = torch.empty_like(a)
+    p.polymul_dev(c2.data_ptr(), a.data_ptr(), b.data_ptr(), batch, st)
+    torch.cuda.synchronize()
+    assert gpu.last_launch_count() > 1 and bool((c2 == c).all())
     p.close()
 
 
