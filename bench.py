@@ -332,8 +332,12 @@ class Workload:
         self.plan = mod.Plan(self.n, self.q, self.psi, cyclic=self.cyclic)
         self.plantard = "plantard" in self.plan.describe()
         row_bytes = self.n * 4
-        # distinct buffer sets so that successive steps never find their inputs in the 126 MB L2
+        # distinct buffer sets so that successive steps never find their inputs in the 126 MB L2; a
+        # stream of fresh batches is also what the call is for, so rotate over 8 sets (24 GiB at most):
+        # consecutive steps then share no buffer, as in a pipeline that never reuses one in flight
         self.sets = max(2, -(-3 * L2_BYTES // (3 * self.batch * row_bytes)) + 1)
+        want = int(os.environ.get("NTTB200_BENCH_SETS", "8"))
+        self.sets = max(self.sets, min(want, (24 << 30) // (3 * self.batch * row_bytes)))
         cfg = {"c2": 2, "c3": 3, "c3c": 3, "c4": 4, "c5": 5, "c5h": 5}[name]
         off = row_offset if row_offset is not None else rank * self.batch
         fixture = load_fixture()

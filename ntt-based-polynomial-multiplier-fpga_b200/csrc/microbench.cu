@@ -102,6 +102,25 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *sink, uint32_t 
         } else if (WHICH == 12) {
           asm volatile("shr.s32 %0, %0, 1;" : "+r"(x[i]));
           asm volatile("add.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(a));
+        } else if (WHICH == 14 || (WHICH == 17 && (i & 1))) {
+          /* signed half-word Plantard butterfly with the last shift folded into the add:
+           * IMAD, SHF.R.S32, IMAD, LEA.HI.SX32 (X' = X + (u >> 16)), IADD3 (Y' = 2X - X') */
+          const int p = (int)(y[i] * a);
+          const int u = (p >> 16) * (int)m.q + (int)b;
+          const int xn = (int)x[i] + (u >> 16);
+          y[i] = 2u * x[i] - (uint32_t)xn;
+          x[i] = (uint32_t)xn;
+        } else if (WHICH == 16 || WHICH == 17) {
+          /* the same with a full-word second product: IMAD, IMAD.HI (q << 16), LEA.HI.SX32, IADD3 */
+          const int p = (int)(y[i] * a);
+          const int u = __mulhi(p, (int)m.q2 << 15) + (int)b;
+          const int xn = (int)x[i] + (u >> 16);
+          y[i] = 2u * x[i] - (uint32_t)xn;
+          x[i] = (uint32_t)xn;
+        } else if (WHICH == 15) {
+          /* LEA.HI.SX32 alone: x += y >> 16 */
+          x[i] = (uint32_t)((int)x[i] + ((int)y[i] >> 16));
+          asm volatile("" : "+r"(x[i]));
         }
       }
     }
@@ -161,6 +180,10 @@ extern "C" int nttb200_measure_int_peak(int which, double *lane_ops_per_s) {
     case 11: return run<11>(1, lane_ops_per_s); /* half-word Plantard butterflies / s              */
     case 13: return run<13>(1, lane_ops_per_s); /* unsigned Plantard butterflies / s (IMAD + IMAD.HI + 2 IADD3) */
     case 12: return run<12>(2, lane_ops_per_s); /* SHF + IADD pairs, counted as 2                  */
+    case 14: return run<14>(1, lane_ops_per_s); /* signed half-word Plantard butterflies / s, 5 instructions (LEA.HI.SX32) */
+    case 15: return run<15>(1, lane_ops_per_s); /* LEA.HI.SX32                                     */
+    case 16: return run<16>(1, lane_ops_per_s); /* signed Plantard butterflies / s: IMAD, IMAD.HI, LEA.HI.SX32, IADD3 */
+    case 17: return run<17>(1, lane_ops_per_s); /* 14 and 16 alternating                           */
     default: return nttb200_fail(NTTB200_EPARAM, "unknown microbenchmark %d", which);
   }
 }

@@ -75,6 +75,9 @@ struct PlantParams {
   unsigned long long *sched; /* tail scheduler: [0] next chunk, [1] warps finished (both 0 between
                                 launches); NULL = static round-robin assignment only          */
   uint32_t static_rounds;    /* tiles every warp takes round-robin before it turns to sched  */
+  uint32_t nowait;           /* 1: this launch neither reads what the launches still in flight on its
+                                stream write nor writes what they touch (nttb200_launch_independent):
+                                it does not wait for them before it starts, only before it ENDS     */
   uint32_t ufwd[1 << R];     /* entries [1, 2^R) of the forward level table (w~)          */
   uint32_t uinv[1 << R];
 };
@@ -466,12 +469,19 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
    * their twiddle loads, which depend on nothing) while this grid drains; operands may be the
    * previous kernel's output, so they are only touched after griddepcontrol.wait */
   asm volatile("griddepcontrol.launch_dependents;");
+  /* A launch whose operands have nothing to do with the launches still running on the stream (the
+   * host compares address ranges, nttb200.cu:launch_independent) starts its first prefetch right
+   * away: its CTAs fill the SMs that the previous grid's tail leaves idle -- what a caller with two
+   * streams gets (+8 % at batch 2^16), for a single-stream caller.  Such a launch waits for its
+   * predecessors at its END instead, so completion on the stream stays in order. */
+  const bool nowait = P.nowait != 0;
+  if (nowait && tile < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile, P.batch, lane);
   LaneTw1<L> twf, twi;
   if (TWREG) {
     twf.load(P.tw_fwd, l);
     twi.load(P.tw_inv, l);
   }
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (!nowait) asm volatile("griddepcontrol.wait;" ::: "memory");
 #if PLANT_STAGGER_NS > 0
   /* The warps of a launch start together and stay in step from tile to tile, so the four that
    * share a scheduler want the same pipes at the same time.  Starting them a fraction of a tile
@@ -480,7 +490,7 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
   if (L <= 8 && ntiles > wstride * PLANT_STAGGER_MIN_TILES)
     __nanosleep((unsigned)(((warp >> 2) + 2 * (blockIdx.x & 1)) * PLANT_STAGGER_NS));
 #endif
-  if (tile < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile, P.batch, lane);
+  if (!nowait && tile < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile, P.batch, lane);
 
   /* bulk (TMA) stores need 16-byte aligned rows in shared memory: every size but the tiniest */
   constexpr bool BULK = PLANT_BULK_STORE && (Gm::T >= 4) && (Gm::N * sizeof(IO) >= 16) && sizeof(IO) == sizeof(OIO);
@@ -586,6 +596,7 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
   }
   if (BULK && bulk_pending && l == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   if (dyn) plant_sched_done(P.sched, lane, wstride);
+  if (nowait) asm volatile("griddepcontrol.wait;" ::: "memory");   /* no grid ends before its predecessors */
 }
 
 /* bring a value < B q to [0, q) with ceil(log2 B) conditional subtractions */

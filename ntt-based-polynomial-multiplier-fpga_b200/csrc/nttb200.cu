@@ -93,10 +93,16 @@ static int upload_table(DevTable &t, const std::vector<uint32_t> &w, uint32_t q,
     for (size_t i = 0; i < w.size(); i++) t.h1[i] = nttb200_plant_form(w[i], q, plant_qinv);
     NTT_CUDA(cudaMalloc(&t.d1, t.h1.size() * sizeof(uint32_t)));
     NTT_CUDA(cudaMemcpy(t.d1, t.h1.data(), t.h1.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    t.h2.resize(w.size());
+    for (size_t i = 0; i < w.size(); i++) t.h2[i] = nttb200_plant_form_centred(w[i], q, plant_qinv);
+    NTT_CUDA(cudaMalloc(&t.d2, t.h2.size() * sizeof(uint32_t)));
+    NTT_CUDA(cudaMemcpy(t.d2, t.h2.data(), t.h2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
   }
   return 0;
 }
 static void free_table(DevTable &t) {
+  if (t.d2) cudaFree(t.d2);
+  t.d2 = nullptr;
   if (t.d) cudaFree(t.d);
   if (t.d1) cudaFree(t.d1);
   t.d = nullptr;
@@ -240,6 +246,62 @@ extern "C" uint32_t nttb200_plan_psi(const nttb200_plan *P) {
 }
 extern "C" int nttb200_plan_device(const nttb200_plan *P) { return P ? P->device : -1; }
 extern "C" const char *nttb200_plan_describe(const nttb200_plan *P) { return P ? P->desc : ""; }
+
+/* ------------------------------------------------------------------------------------ */
+/* Independent launches on one stream.                                                     */
+/* The fused product kernel is launched with programmatic stream serialization: its CTAs  */
+/* may start while the previous kernel of the stream drains.  Whether they may also READ   */
+/* AND WRITE before that kernel has finished depends on the data: the library remembers,   */
+/* per stream, the address ranges of its launches since the last one that waited; a new    */
+/* launch is independent when it reads nothing they write and writes nothing they read or   */
+/* write.  An independent launch skips the wait at its start (and waits at its end, so the  */
+/* stream still completes in order); any other launch waits as before and becomes the new   */
+/* base of the history.  Foreign work on the stream (other kernels, copies) never triggers  */
+/* early, so it is fully ordered against both kinds.  NTTB200_PDL_NOWAIT=0 turns it off.    */
+/* ------------------------------------------------------------------------------------ */
+namespace {
+struct RangeSet { uintptr_t rlo[2], rhi[2], wlo, whi; };
+struct StreamHistory {
+  cudaStream_t st = nullptr;
+  bool used = false;
+  int n = 0;
+  unsigned long long stamp = 0;
+  RangeSet e[8];
+};
+std::mutex g_hist_mu;
+StreamHistory g_hist[16];
+unsigned long long g_hist_clock = 0;
+inline bool overlap(uintptr_t alo, uintptr_t ahi, uintptr_t blo, uintptr_t bhi) { return alo < bhi && blo < ahi; }
+}  // namespace
+
+bool nttb200_launch_independent(cudaStream_t st, const void *a, size_t abytes, const void *b, size_t bbytes,
+                                const void *c, size_t cbytes) {
+  static const bool enabled = [] { const char *e = getenv("NTTB200_PDL_NOWAIT"); return !e || atoi(e) != 0; }();
+  RangeSet r;
+  r.rlo[0] = (uintptr_t)a; r.rhi[0] = r.rlo[0] + abytes;
+  r.rlo[1] = (uintptr_t)b; r.rhi[1] = r.rlo[1] + bbytes;
+  r.wlo = (uintptr_t)c; r.whi = r.wlo + cbytes;
+  std::lock_guard<std::mutex> lock(g_hist_mu);
+  StreamHistory *h = nullptr, *spare = nullptr;
+  for (auto &x : g_hist) {
+    if (x.used && x.st == st) { h = &x; break; }
+    if (!spare || (spare->used && (!x.used || x.stamp < spare->stamp))) spare = &x;   /* unused first, else oldest */
+  }
+  if (!h) { h = spare; h->st = st; h->used = true; h->n = 0; }
+  h->stamp = ++g_hist_clock;
+  bool indep = enabled && h->n > 0 && h->n < (int)(sizeof h->e / sizeof h->e[0]);
+  for (int i = 0; indep && i < h->n; i++) {
+    const RangeSet &p = h->e[i];
+    for (int k = 0; k < 2; k++) {
+      if (overlap(r.rlo[k], r.rhi[k], p.wlo, p.whi)) indep = false;          /* read after write  */
+      if (overlap(r.wlo, r.whi, p.rlo[k], p.rhi[k])) indep = false;          /* write after read  */
+    }
+    if (overlap(r.wlo, r.whi, p.wlo, p.whi)) indep = false;                  /* write after write */
+  }
+  if (!indep) h->n = 0;                                 /* this launch waits for everything before it */
+  h->e[h->n++] = r;
+  return indep;
+}
 
 /* ------------------------------------------------------------------------------------ */
 /* dispatch                                                                              */

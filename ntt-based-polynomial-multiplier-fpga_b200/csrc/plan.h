@@ -17,12 +17,21 @@ struct DevTable {
   std::vector<uint2> h;          /* host mirror (entries < 64 feed the kernel-parameter block)     */
   uint32_t *d1 = nullptr;        /* device: the same table in Plantard form w~ (half-word moduli)  */
   std::vector<uint32_t> h1;
+  uint32_t *d2 = nullptr;        /* device: Plantard form with W centred (signed kernel, ntt_small_splant.cuh) */
+  std::vector<uint32_t> h2;
 };
 
 /* Plantard form of a constant: ((-w 2^32) mod q) * q^-1 mod 2^32  (ntt_small_plant.cuh) */
 static inline uint32_t nttb200_plant_form(uint32_t w, uint32_t q, uint32_t qinv) {
   const uint64_t W = (q - (((uint64_t)(w % q)) << 32) % q) % q;
   return (uint32_t)W * qinv;
+}
+
+/* the same with W = (-w 2^32) mod q taken in (-q/2, q/2]: since q q^-1 = 1 (mod 2^32), one less
+ * where W was above q/2 */
+static inline uint32_t nttb200_plant_form_centred(uint32_t w, uint32_t q, uint32_t qinv) {
+  const uint64_t W = (q - (((uint64_t)(w % q)) << 32) % q) % q;
+  return (uint32_t)W * qinv - (W > q / 2 ? 1u : 0u);
 }
 
 enum PlanKernel { PK_SMALL = 0, PK_LARGE = 1 };
@@ -108,6 +117,11 @@ int nttb200_fail(int code, const char *fmt, ...);
   } while (0)
 
 void nttb200_count_launch(int k);
+/* Is a launch on `st` that reads [a, a+abytes), [b, b+bbytes) and writes [c, c+cbytes) independent of
+ * every launch of this library that may still be running on that stream?  Records the launch either
+ * way (nttb200.cu). */
+bool nttb200_launch_independent(cudaStream_t st, const void *a, size_t abytes, const void *b, size_t bbytes,
+                                const void *c, size_t cbytes);
 
 /* dispatchers implemented in the kernel translation units */
 int launch_polymul_small(const nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b,

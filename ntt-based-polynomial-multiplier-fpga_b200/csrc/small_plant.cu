@@ -5,6 +5,7 @@
 #include <algorithm>
 
 #include "ntt_small_plant.cuh"
+#include "ntt_small_splant.cuh"
 #include "plan.h"
 
 namespace {
@@ -74,10 +75,16 @@ int run_plant(const nttb200_plan *P, void *c, const void *a, const void *b, size
   }
   auto kernel = polymul_plant_kernel<L, Cfg::WARPS, MINB, Cfg::TWREG, IO, OIO>;
   const int smem = Cfg::WARPS * Pg::WARP_WORDS * (int)sizeof(uint32_t);
-  int per_sm = 0;
-  NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  NTT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, Cfg::WARPS * 32, smem));
-  if (per_sm < 1) return nttb200_fail(NTTB200_ECUDA, "plant kernel does not fit on an SM");
+  /* attributes and occupancy are asked once per kernel instance and device, not per launch */
+  static int per_sm_dev[64] = {0};
+  int &per_sm = per_sm_dev[P->device & 63];
+  if (!per_sm) {
+    int v = 0;
+    NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    NTT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, Cfg::WARPS * 32, smem));
+    if (v < 1) return nttb200_fail(NTTB200_ECUDA, "plant kernel does not fit on an SM");
+    per_sm = v;
+  }
   const unsigned long long tiles = (batch + Gm::PPW - 1) / Gm::PPW;
   const unsigned long long want = (tiles + Cfg::WARPS - 1) / Cfg::WARPS;
   /* Sizes that keep the static loop (n <= 256) launch up to 4 times the resident CTAs, as long as
@@ -109,6 +116,83 @@ int run_plant(const nttb200_plan *P, void *c, const void *a, const void *b, size
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = plant_pdl() ? 1 : 0;
+  p.nowait = (plant_pdl() && nttb200_launch_independent(st, a, batch * Gm::N * sizeof(IO), b, batch * Gm::N * sizeof(IO),
+                                                        c, batch * Gm::N * sizeof(OIO))) ? 1u : 0u;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NTT_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+  nttb200_count_launch(1);
+  NTT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+/* NTTB200_PLANT_SIGNED=1 runs the signed five-instruction-butterfly kernel of ntt_small_splant.cuh for
+ * n <= 256.  Measured on B200: 5 % fewer instructions per tile and +1.6 % at batch
+ * 2^16 for a few milliseconds (1 362 vs 1 340 M polymul/s), but both kernels run into the 1000 W
+ * power cap when the load lasts a second, and the signed one, with more of its work on the
+ * multiplier pipe, is clocked lower there (1 890 vs 1 965 MHz: 1 321 vs 1 334 M sustained).  The
+ * unsigned kernel therefore stays the default; read per call so that the tests cover both. */
+int plant_signed() {
+  const char *e = getenv("NTTB200_PLANT_SIGNED");
+  return e ? atoi(e) != 0 : 0;
+}
+
+/* the signed kernel, n <= 256 */
+template <int L, typename IO = uint32_t, typename OIO = IO>
+int run_splant(const nttb200_plan *P, void *c, const void *a, const void *b, size_t batch, cudaStream_t st) {
+  using Gm = SmallGeom<L>;
+  using Pg = PlantGeom<L, IO>;
+  constexpr int WARPS = PLANT_WARPS;
+  const bool cyclic = (P->flags & NTTB200_PLAN_CYCLIC) != 0;
+  const DevTable &fwd = cyclic ? P->fwd_plain : P->fwd_mixed;
+  const DevTable &inv = cyclic ? P->inv_plain : P->inv_mixed;
+  SPlantParams<Gm::R> p{};
+  p.a = a; p.b = b; p.c = c; p.batch = batch;
+  p.tw_fwd = fwd.d2; p.tw_inv = inv.d2;
+  const uint32_t q = P->q;
+  p.q = q; p.qinv = P->m.qinv;
+  /* |Y W| <= mmax is what the second product tolerates (ntt_small_splant.cuh); the kernel multiplies
+   * differences up to 16 q by |W| <= q/2 */
+  const uint64_t mmax = ((1ull << 32) - 65536ull * (q + 4)) / 2;
+  if (8ull * q * q > mmax) return nttb200_fail(NTTB200_EPARAM, "q=%u is too large for the signed Plantard kernel", q);
+  p.dd = (uint32_t)((mmax + 65535ull * q + 65535ull) / 65536ull);
+  p.cbar = (uint32_t)(((1ull << SP_RED_SHIFT) + q / 2) / q);
+  /* -n^-1 2^32: cancels the -2^-32 of the Plantard pointwise product */
+  const uint64_t fs = (q - (uint64_t)P->n_inv * ((1ull << 32) % q) % q) % q;
+  p.last_x = nttb200_plant_form_centred((uint32_t)fs, q, p.qinv);
+  p.last_y = nttb200_plant_form_centred((uint32_t)(fs * inv.h[1].x % q), q, p.qinv);
+  for (int i = 0; i < (1 << Gm::R); i++) {
+    p.ufwd[i] = (size_t)i < fwd.h2.size() ? fwd.h2[i] : 0;
+    p.uinv[i] = (size_t)i < inv.h2.size() ? inv.h2[i] : 0;
+  }
+  auto kernel = polymul_splant_kernel<L, WARPS, 2, IO, OIO>;
+  const int smem = WARPS * Pg::WARP_WORDS * (int)sizeof(uint32_t);
+  static int per_sm_dev[64] = {0};
+  int &per_sm = per_sm_dev[P->device & 63];
+  if (!per_sm) {
+    int v = 0;
+    NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    NTT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, WARPS * 32, smem));
+    if (v < 1) return nttb200_fail(NTTB200_ECUDA, "signed plant kernel does not fit on an SM");
+    per_sm = v;
+  }
+  const unsigned long long tiles = (batch + Gm::PPW - 1) / Gm::PPW;
+  const unsigned long long want = (tiles + WARPS - 1) / WARPS;
+  static const int gridx_env = [] { const char *e = getenv("NTTB200_PLANT_GRIDX"); int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 64 ? 64 : v); }();
+  unsigned long long gridx = gridx_env > 0 ? (unsigned long long)gridx_env
+      : std::min<unsigned long long>(4, std::max<unsigned long long>(1, tiles / ((unsigned long long)P->sm_count * per_sm * WARPS * 6)));
+  const unsigned long long cap = (unsigned long long)P->sm_count * per_sm * gridx;
+  const int grid = (int)(want < cap ? (want ? want : 1) : cap);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(WARPS * 32);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = plant_pdl() ? 1 : 0;
+  p.nowait = (plant_pdl() && nttb200_launch_independent(st, a, batch * Gm::N * sizeof(IO), b, batch * Gm::N * sizeof(IO),
+                                                        c, batch * Gm::N * sizeof(OIO))) ? 1u : 0u;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   NTT_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
@@ -146,20 +230,34 @@ int info_plant(int *regs, int *smem_bytes, int *blocks_per_sm) {
     default: return nttb200_fail(NTTB200_EPARAM, "small kernels cover 8 <= n <= 1024"); \
   }
 
+#define SPLANT_SWITCH(expr_of_L)                     \
+  switch (P->logn) {                                 \
+    case 3: { constexpr int L = 3; expr_of_L; }      \
+    case 4: { constexpr int L = 4; expr_of_L; }      \
+    case 5: { constexpr int L = 5; expr_of_L; }      \
+    case 6: { constexpr int L = 6; expr_of_L; }      \
+    case 7: { constexpr int L = 7; expr_of_L; }      \
+    case 8: { constexpr int L = 8; expr_of_L; }      \
+    default: break;                                  \
+  }
+
 int launch_polymul_small_plant(const nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b,
                                size_t batch, cudaStream_t st) {
+  if (plant_signed() && P->logn <= 8) { SPLANT_SWITCH(return (run_splant<L>(P, c, a, b, batch, st))) }
   if (plant_minb(P->logn) == 2) { PLANT_SWITCH(return (run_plant<L, 2>(P, c, a, b, batch, st))) }
   PLANT_SWITCH(return (run_plant<L, 3>(P, c, a, b, batch, st)))
 }
 /* packed 16-bit operands and result (extension outside the reference API) */
 int launch_polymul_small_plant_u16(const nttb200_plan *P, uint16_t *c, const uint16_t *a, const uint16_t *b,
                                    size_t batch, cudaStream_t st) {
+  if (plant_signed() && P->logn <= 8) { SPLANT_SWITCH(return (run_splant<L, uint16_t>(P, c, a, b, batch, st))) }
   PLANT_SWITCH(return (run_plant<L, 2, uint16_t>(P, c, a, b, batch, st)))
 }
 /* 16-bit operands, 32-bit result: the wire pipeline of the host-buffer call narrows a and b on
  * the host and lets the kernel write the caller's int32 rows (nttb200.cu, polymul_batch_wire) */
 int launch_polymul_small_plant_u16in(const nttb200_plan *P, uint32_t *c, const uint16_t *a, const uint16_t *b,
                                      size_t batch, cudaStream_t st) {
+  if (plant_signed() && P->logn <= 8) { SPLANT_SWITCH(return (run_splant<L, uint16_t, uint32_t>(P, c, a, b, batch, st))) }
   PLANT_SWITCH(return (run_plant<L, 2, uint16_t, uint32_t>(P, c, a, b, batch, st)))
 }
 template <int L, int DIR>

@@ -1,0 +1,20 @@
+#!/usr/bin/env python3
+"""Butterfly-level issue rates on the B200 integer pipes (nttb200_measure_int_peak): how many
+lane-butterflies per second each candidate instruction mix sustains, 8 independent chains per
+thread.  python profiles/microbench_butterflies.py > profiles/<round>_microbench_butterflies.txt"""
+import importlib
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+m = importlib.import_module("ntt-based-polynomial-multiplier-fpga_b200")
+NAMES = {0: "IMAD", 1: "IMAD.HI", 2: "IADD", 12: "SHF + IADD pairs (x2)", 15: "LEA.HI.SX32",
+         3: "Shoup LAZY butterfly (IMAD.HI, 2 IMAD, 2 IADD)", 13: "unsigned Plantard, full word (IMAD, IMAD.HI, 2 IADD3)",
+         11: "Plantard half word, 6 instructions (IMAD, SHF, IMAD, SHF, 2 IADD)",
+         14: "signed Plantard half word, 5 instructions (IMAD, SHF, IMAD, LEA.HI.SX32, IADD3)",
+         16: "signed Plantard full word, 4 instructions (IMAD, IMAD.HI, LEA.HI.SX32, IADD3)",
+         17: "14 and 16 alternating"}
+sms, clk = 148, 1.965e9
+for k, name in NAMES.items():
+    r = m.measure_int_peak(k)
+    print(f"{k:3d} {name:90s} {r / 1e12:7.3f} T lane-ops/s  = {r / sms / clk:6.2f} lanes/clk/SM")

@@ -119,10 +119,14 @@ def test_config2_batch_2e16_vs_all_four_reference_variants(plan256, oracle, load
 
 @pytest.mark.parametrize("n,q", [(8, 17), (16, 97), (32, 193), (64, 257), (128, 3329), (256, 12289),
                                  (256, 7681), (512, 12289), (1024, 12289), (256, 10753), (128, 12289)])
-def test_half_word_moduli_plantard_vs_shoup_kernels(gpu, oracle, n, q):
-    """q <= 12385: the product runs the Plantard kernel (ntt_small_plant.cuh); the same plan with
-    NTTB200_PLAN_NO_PLANTARD runs the Shoup/Montgomery kernel.  Both against the oracle, with
-    worst-case rows (all q-1: every lazy bound is attained) and ragged batch sizes."""
+@pytest.mark.parametrize("signed", [0, 1])
+def test_half_word_moduli_plantard_vs_shoup_kernels(gpu, oracle, monkeypatch, n, q, signed):
+    """q <= 12385: the product runs the Plantard kernel (ntt_small_plant.cuh; with
+    NTTB200_PLANT_SIGNED=1 and n <= 256 the signed five-instruction-butterfly kernel of
+    ntt_small_splant.cuh); the same plan with NTTB200_PLAN_NO_PLANTARD runs the Shoup/Montgomery
+    kernel.  All against the oracle, with worst-case rows (all q-1 and alternating 0 / q-1: every
+    lazy bound is attained) and ragged batch sizes."""
+    monkeypatch.setenv("NTTB200_PLANT_SIGNED", str(signed))
     pl, sh = gpu.Plan(n, q), gpu.Plan(n, q, no_plantard=True)
     assert "plantard" in pl.describe() and "plantard" not in sh.describe()
     for batch in (1, 2, 31, 32, 33, 257, 1031):
@@ -131,11 +135,39 @@ def test_half_word_moduli_plantard_vs_shoup_kernels(gpu, oracle, n, q):
         if batch > 2:
             a[1] = q - 1
             b[2] = q - 1
+        if batch > 8:
+            alt = np.where(np.arange(n) % 2 == 0, q - 1, 0).astype(np.int32)
+            a[3], b[3] = alt, alt
+            a[4], b[4] = alt, (q - 1) - alt
+            a[5] = np.where(np.arange(n) < n // 2, q - 1, 0)
+            b[5] = np.where(np.arange(n) % 4 < 2, q - 1, 0)
         want = oracle.product(n, q, a, b, 10)
         assert (pl.polymul(a, b) == want).all(), (pl.describe(), batch)
         assert (sh.polymul(a, b) == want).all(), (sh.describe(), batch)
     pl.close()
     sh.close()
+
+
+def test_signed_plantard_kernel_on_config2_vs_the_compiled_reference(gpu, loader, nttb200, golden, monkeypatch):
+    """NTTB200_PLANT_SIGNED=1 (ntt_small_splant.cuh) on the whole SURVEY 8d batch of config 2: every
+    one of the 2^16 rows equals the compiled reference (optimized CT and plain GS variants), device-
+    resident and through the host-buffer call (16-bit wire included)."""
+    import torch
+    monkeypatch.setenv("NTTB200_PLANT_SIGNED", "1")
+    batch = 1 << 16
+    p = gpu.Plan(N, Q, PSI)
+    a, b = nttb200.inputs.survey_batch(N, Q, batch, 2, device="cuda", fixture=(golden["fixture_a"], golden["fixture_b"]))
+    c = torch.empty_like(a)
+    p.polymul_dev(c.data_ptr(), a.data_ptr(), b.data_ptr(), batch, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ha, hb, got = a.cpu().numpy(), b.cpu().numpy(), c.cpu().numpy()
+    assert (got[8] == golden["fixture_c"]).all() and (got[4:8] == golden["kat_c"]).all()
+    if loader.reference_available():
+        ref = loader.Reference()
+        for v in (loader.REF_RED_CT, loader.REF_GS):
+            assert (ref.product(ha, hb, v) == got).all(), v
+    assert (p.polymul(ha, hb) == got).all()
+    p.close()
 
 
 @pytest.mark.parametrize("n,q", SMALL_CASES)
@@ -893,4 +925,59 @@ def test_batch_transforms_from_pageable_memory_are_staged_by_the_pool(gpu, oracl
     idx = np.unique(np.r_[0:3, batch - 3:batch, np.random.default_rng(5).integers(0, batch, 20)])
     want = oracle.transform("mulntt_ct_std2rev", a[idx], oracle.table(loader.MIXED_POWERS_REV, n, q, p.psi), q)
     assert (got[idx] == want).all()
+    p.close()
+
+
+def test_independent_launches_skip_the_wait_dependent_ones_do_not(gpu, oracle, nttb200):
+    """Launches on one stream whose operands share nothing with the launches in flight start before
+    those finish (programmatic dependent launch without the initial wait); a launch that reads the
+    previous result, or writes over anything in flight, waits.  Chains of both kinds, interleaved
+    with a foreign kernel, give the oracle's values."""
+    import torch
+    n, q, batch = 256, 12289, 1 << 14
+    p = gpu.Plan(n, q)
+    st = torch.cuda.current_stream().cuda_stream
+    sets = []
+    for k in range(4):
+        a, b = nttb200.inputs.survey_batch(n, q, batch, 2, device="cuda", row_offset=k * batch)
+        sets.append((a, b, torch.empty_like(a)))
+    for rep in range(3):                               # independent: rotating buffer sets
+        for a, b, c in sets:
+            p.polymul_dev(c.data_ptr(), a.data_ptr(), b.data_ptr(), batch, st)
+    torch.cuda.synchronize()
+    rows = np.r_[0:9, batch - 3:batch, np.random.default_rng(3).integers(0, batch, 200)]
+    for a, b, c in sets:
+        want = oracle.product(n, q, a[rows].cpu().numpy(), b[rows].cpu().numpy(), 10)
+        assert (c[rows].cpu().numpy() == want).all()
+    # dependent chain: c1 = a*b, c2 = c1*b, c3 = c2*c1 (reads two earlier results), then overwrite a
+    a, b, c1 = sets[0]
+    c2, c3 = sets[1][2], sets[2][2]
+    a0 = a.clone()
+    p.polymul_dev(c1.data_ptr(), a.data_ptr(), b.data_ptr(), batch, st)
+    p.polymul_dev(c2.data_ptr(), c1.data_ptr(), b.data_ptr(), batch, st)      # RAW on c1
+    c1.add_(0)                                                                 # a foreign kernel in between
+    p.polymul_dev(c3.data_ptr(), c2.data_ptr(), c1.data_ptr(), batch, st)      # RAW on c2 and c1
+    p.polymul_dev(a.data_ptr(), c3.data_ptr(), b.data_ptr(), batch, st)        # WAR on a (read by the first)
+    torch.cuda.synchronize()
+    r = rows[:64]
+    w1 = oracle.product(n, q, a0[r].cpu().numpy(), b[r].cpu().numpy(), 10)
+    w2 = oracle.product(n, q, w1, b[r].cpu().numpy(), 10)
+    w3 = oracle.product(n, q, w2, w1, 10)
+    w4 = oracle.product(n, q, w3, b[r].cpu().numpy(), 10)
+    assert (c1[r].cpu().numpy() == w1).all() and (c2[r].cpu().numpy() == w2).all()
+    assert (c3[r].cpu().numpy() == w3).all() and (a[r].cpu().numpy() == w4).all()
+    # an event recorded after an independent launch fires only when every earlier launch is done too
+    big = [nttb200.inputs.survey_batch(n, q, 1 << 18, 3, device="cuda") for _ in range(1)]
+    ab, bb = big[0]
+    cb = torch.empty_like(ab)
+    small_a, small_b, small_c = sets[3]
+    p.polymul_dev(cb.data_ptr(), ab.data_ptr(), bb.data_ptr(), 1 << 18, st)     # long
+    small_c.zero_()
+    p.polymul_dev(small_c.data_ptr(), small_a.data_ptr(), small_b.data_ptr(), 64, st)   # short, independent
+    ev = torch.cuda.Event()
+    ev.record()
+    ev.synchronize()
+    rr = np.r_[(1 << 18) - 64:(1 << 18)]
+    want = oracle.product(n, q, ab[rr].cpu().numpy(), bb[rr].cpu().numpy(), 10)
+    assert (cb[rr].cpu().numpy() == want).all()
     p.close()

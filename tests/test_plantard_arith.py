@@ -109,3 +109,107 @@ def test_gs_bound_closed_form_matches_simulation():
                     b[r] = s if s <= CAP else CAP          # one csub(s, 8q) when the inputs were at the cap
                     b[r2] = 1
             assert max(b) == min(b_in << bits, CAP)
+
+
+# ------------------------------------------------------------------------------------------
+# signed Plantard arithmetic of ntt_small_splant.cuh (five-instruction butterflies)
+def splant_constants(q):
+    """(D, C, Mmax) exactly as csrc/small_plant.cu computes them for the kernel parameters."""
+    mmax = ((1 << 32) - 65536 * (q + 4)) // 2
+    dd = (mmax + 65535 * q + 65535) // 65536
+    cbar = ((1 << 26) + q // 2) // q
+    return dd, cbar, mmax
+
+
+def centred_form(w, q, qinv):
+    W = (q - ((w % q) << 32) % q) % q
+    if W > q // 2:
+        W -= q
+    return (W * qinv) & M32, W
+
+
+def as_i32(x):
+    x = np.asarray(x, dtype=np.int64) & M32
+    return np.where(x >= 1 << 31, x - (1 << 32), x)
+
+
+def splant_mul(y, wt, q, dd):
+    """T = ((Y w~ as int32) >> 16) q + D) >> 16, arithmetic shifts, int64 emulation of the int32 code."""
+    p = as_i32(np.asarray(y, dtype=np.int64) * np.asarray(wt, dtype=np.int64))
+    u = (p >> 16) * q + dd
+    assert (np.abs(u) < 1 << 31).all()
+    return u >> 16
+
+
+@pytest.mark.parametrize("q", [17, 97, 257, 3329, 7681, 12289, 12373, 12385])
+def test_signed_plantard_multiplication_is_exact_and_centred(q):
+    """T == Y w (mod q) and |T| <= (q-1)/2 for every centred W and every |Y| <= 16 q (the largest
+    difference the kernel multiplies; the proof allows 23 q at q = 12289)."""
+    qinv = qinv32(q)
+    dd, _, mmax = splant_constants(q)
+    ylim = 16 * q
+    assert ylim * (q // 2) <= mmax and 2 * mmax + 65536 * (q + 4) <= 1 << 32
+    rng = np.random.default_rng(q + 11)
+    ws = np.arange(q) if q <= 3329 else np.unique(np.concatenate(
+        [rng.integers(0, q, 1500), [0, 1, 2, q - 1, q - 2, q // 2, q // 2 + 1, q // 2 - 1]]))
+    forms = [centred_form(int(w), q, qinv) for w in ws]
+    wt = np.array([f[0] for f in forms], dtype=np.int64)
+    ys = np.unique(np.concatenate([rng.integers(-ylim, ylim + 1, 3000), np.arange(-40, 41), ylim - np.arange(0, 40),
+                                   -ylim + np.arange(0, 40), q * np.arange(-16, 17), q * np.arange(-16, 17) + 1,
+                                   q * np.arange(-16, 17) - 1]))
+    ys = ys[np.abs(ys) <= ylim]
+    Y, WT = np.meshgrid(ys, wt, indexing="ij")
+    _, Wn = np.meshgrid(ys, ws, indexing="ij")
+    T = splant_mul(Y, WT, q, dd)
+    assert (np.abs(T) <= (q - 1) // 2).all()
+    assert ((T - Y * Wn) % q == 0).all()
+
+
+@pytest.mark.parametrize("q", [17, 257, 3329, 7681, 12289, 12385])
+def test_signed_barrett_step_and_pointwise_product(q):
+    """sp_red: x - q ((x C + 2^25) >> 26) lands within q/2 + 20 of zero for |x| <= 16 q; the pointwise
+    Plantard product of a reduced a and any |b| <= 6 q gives -a b 2^-32 mod q, centred."""
+    qinv = qinv32(q)
+    dd, cbar, mmax = splant_constants(q)
+    rng = np.random.default_rng(q + 13)
+    x = np.unique(np.concatenate([rng.integers(-16 * q, 16 * q + 1, 20000), q * np.arange(-16, 17),
+                                  (q * np.arange(-31, 32)) // 2, (q * np.arange(-31, 32)) // 2 + 1]))
+    assert (np.abs(x * cbar) < 1 << 31).all()
+    r = x - q * ((x * cbar + (1 << 25)) >> 26)
+    assert ((r - x) % q == 0).all() and (np.abs(r) <= q // 2 + 20).all()
+    a = r[np.abs(x) <= 6 * q][:4000]
+    b = rng.integers(-6 * q, 6 * q + 1, a.size)
+    assert (np.abs(a * b) <= mmax).all()
+    p = as_i32((as_i32(a * b) * qinv))
+    u = (p >> 16) * q + dd
+    T = u >> 16
+    inv232 = pow(1 << 32, -1, q) if q > 2 else 1
+    assert (np.abs(T) <= (q - 1) // 2).all()
+    assert ((T + a * b * inv232) % q == 0).all()
+
+
+def test_signed_bound_bookkeeping_of_the_inverse():
+    """The compile-time bounds of ntt_small_splant.cuh (units of q/2), restated: no multiplied
+    difference ever passes 32 units (16 q) and no Barrett input passes 32 units."""
+    CAP = 16
+
+    def leg(k, bit, b_in):
+        b = b_in
+        for s in range(bit):
+            if (k >> s) & 1:
+                b = 1
+            else:
+                b *= 2
+                if b > CAP:
+                    b = 1
+        return b
+    for H, R in ((4, 4), (3, 4), (3, 3), (2, 3), (2, 2), (1, 2)):
+        worst = max(leg(k, H, 1) for k in range(1 << H))
+        second = leg(1, H, 1)
+        b_in = max(second, 2) if worst > second else worst
+        for bit in range(H):
+            for k in range(1 << H):
+                assert 2 * leg(k, bit, 1) <= 2 * CAP
+        for kb in range(R):
+            for k in range(1 << R):
+                assert 2 * leg(k, kb, b_in) <= 2 * CAP
