@@ -122,6 +122,77 @@ __attribute__((target("avx2"))) static void copy_stream_avx2(int32_t *dst, const
 }
 #endif
 
+#if defined(__x86_64__)
+/* Variants of the two kernels above, picked by NTTB200_WIRE_SIMD = avx2 | avx2nt | avx512 | avx512nt
+ * (default avx2; "nt" = non-temporal stores into the pinned staging too, sparing the read-for-ownership
+ * of lines that only the DMA engine reads; avx512 = vpmovdw / vpmovzxwd on 512-bit registers where
+ * the host has AVX-512BW).  Measured on the GPU box's host: DESIGN.md section 4. */
+__attribute__((target("avx2"))) static uint32_t narrow_avx2_nt(uint16_t *dst, const int32_t *src, size_t n) {
+  __m256i acc = _mm256_setzero_si256();
+  size_t i = 0;
+  if (((uintptr_t)dst & 31u) == 0) {
+    for (; i + 32 <= n; i += 32) {
+      const __m256i a0 = _mm256_loadu_si256((const __m256i *)(src + i));
+      const __m256i a1 = _mm256_loadu_si256((const __m256i *)(src + i + 8));
+      const __m256i a2 = _mm256_loadu_si256((const __m256i *)(src + i + 16));
+      const __m256i a3 = _mm256_loadu_si256((const __m256i *)(src + i + 24));
+      acc = _mm256_or_si256(acc, _mm256_or_si256(_mm256_or_si256(a0, a1), _mm256_or_si256(a2, a3)));
+      _mm256_stream_si256((__m256i *)(dst + i), _mm256_permute4x64_epi64(_mm256_packus_epi32(a0, a1), 0xD8));
+      _mm256_stream_si256((__m256i *)(dst + i + 16), _mm256_permute4x64_epi64(_mm256_packus_epi32(a2, a3), 0xD8));
+    }
+    _mm_sfence();
+  }
+  uint32_t lanes[8];
+  _mm256_storeu_si256((__m256i *)lanes, acc);
+  uint32_t r = 0;
+  for (int k = 0; k < 8; k++) r |= lanes[k];
+  return r | narrow_avx2(dst + i, src + i, n - i);
+}
+__attribute__((target("avx512f,avx512bw"))) static uint32_t narrow_avx512(uint16_t *dst, const int32_t *src, size_t n, int nt) {
+  __m512i acc = _mm512_setzero_si512();
+  size_t i = 0;
+  nt = nt && (((uintptr_t)dst & 63u) == 0);
+  for (; i + 32 <= n; i += 32) {
+    const __m512i a0 = _mm512_loadu_si512((const void *)(src + i));
+    const __m512i a1 = _mm512_loadu_si512((const void *)(src + i + 16));
+    acc = _mm512_or_si512(acc, _mm512_or_si512(a0, a1));
+    const __m512i p = _mm512_inserti64x4(_mm512_castsi256_si512(_mm512_cvtepi32_epi16(a0)), _mm512_cvtepi32_epi16(a1), 1);
+    if (nt) _mm512_stream_si512((__m512i *)(dst + i), p);
+    else _mm512_storeu_si512((void *)(dst + i), p);
+  }
+  if (nt) _mm_sfence();
+  const uint32_t r = (uint32_t)_mm512_reduce_or_epi32(acc);
+  return r | narrow_scalar(dst + i, src + i, n - i);
+}
+__attribute__((target("avx512f,avx512bw"))) static void widen_avx512(int32_t *dst, const uint16_t *src, size_t n) {
+  size_t i = 0;
+  if (((uintptr_t)dst & 63u) == 0) {
+    for (; i + 32 <= n; i += 32) {
+      const __m512i v = _mm512_loadu_si512((const void *)(src + i));
+      _mm512_stream_si512((__m512i *)(dst + i), _mm512_cvtepu16_epi32(_mm512_castsi512_si256(v)));
+      _mm512_stream_si512((__m512i *)(dst + i + 16), _mm512_cvtepu16_epi32(_mm512_extracti64x4_epi64(v, 1)));
+    }
+    _mm_sfence();
+  }
+  widen_scalar(dst + i, src + i, n - i);
+}
+/* 0 avx2, 1 avx2 + nt, 2 avx512, 3 avx512 + nt */
+static int g_simd = -1;
+static int wire_simd(void) {
+  if (g_simd < 0) {
+    const char *e = getenv("NTTB200_WIRE_SIMD");
+    int v = 0;
+    if (e && !strcmp(e, "avx2nt")) v = 1;
+    else if (e && !strcmp(e, "avx512")) v = 2;
+    else if (e && !strcmp(e, "avx512nt")) v = 3;
+    __builtin_cpu_init();
+    if (v >= 2 && !(__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw"))) v -= 2;
+    g_simd = v;
+  }
+  return g_simd;
+}
+#endif
+
 static int g_have_avx2 = -1;
 static int have_avx2(void) {
   if (g_have_avx2 < 0) {
@@ -137,13 +208,21 @@ static int have_avx2(void) {
 
 uint32_t nttb200_wire_narrow(uint16_t *dst, const int32_t *src, size_t n) {
 #if defined(__x86_64__)
-  if (have_avx2()) return narrow_avx2(dst, src, n);
+  if (have_avx2()) {
+    const int v = wire_simd();
+    if (v >= 2) return narrow_avx512(dst, src, n, v == 3);
+    return v == 1 ? narrow_avx2_nt(dst, src, n) : narrow_avx2(dst, src, n);
+  }
 #endif
   return narrow_scalar(dst, src, n);
 }
 void nttb200_wire_widen(int32_t *dst, const uint16_t *src, size_t n) {
 #if defined(__x86_64__)
-  if (have_avx2()) { widen_avx2(dst, src, n); return; }
+  if (have_avx2()) {
+    if (wire_simd() >= 2) widen_avx512(dst, src, n);
+    else widen_avx2(dst, src, n);
+    return;
+  }
 #endif
   widen_scalar(dst, src, n);
 }
