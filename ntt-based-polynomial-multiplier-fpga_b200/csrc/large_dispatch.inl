@@ -40,6 +40,27 @@ void fill_utw(LargeParams &p, const DevTable *t) {
   for (size_t i = 1; i < lim; i++) p.utw[i] = t->h[i];
 }
 
+/* every kernel of the pipeline is launched with programmatic stream serialization: its CTAs are
+ * scheduled while the previous kernel of the lane drains, and wait (griddepcontrol.wait) where they
+ * first need its results */
+template <typename K>
+int launch_pdl_large(K kernel, unsigned grid, int threads, int smem, cudaStream_t st, const LargeParams &p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NTT_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+  nttb200_count_launch(1);
+  NTT_CUDA(cudaGetLastError());
+  return 0;
+}
+
 /* two columns per lane for the classes with cheap butterflies, when the rows are 8-byte aligned */
 constexpr int LARGE_CPL = (LARGE_ARITH == ARITH_CANON) ? 1 : 2;
 inline bool cols_aligned8(const LargeParams &p) {
@@ -56,10 +77,7 @@ int cols_fwd_cpl(const nttb200_plan *P, LargeParams &p, cudaStream_t st) {
     NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
   const unsigned long long grid = p.batch * p.nops * (1ull << (P->logn - K1 - G::LOG_TILE));
   if (grid > 0x7fffffffull) return nttb200_fail(NTTB200_EPARAM, "batch too large for one launch");
-  kernel<<<(unsigned)grid, G::WARPS * 32, G::SMEM_BYTES, st>>>(p);
-  nttb200_count_launch(1);
-  NTT_CUDA(cudaGetLastError());
-  return 0;
+  return launch_pdl_large(kernel, (unsigned)grid, G::WARPS * 32, G::SMEM_BYTES, st, p);
 }
 template <int K1>
 int cols_fwd(const nttb200_plan *P, LargeParams &p, cudaStream_t st) {
@@ -75,10 +93,7 @@ int cols_inv_cpl(const nttb200_plan *P, LargeParams &p, cudaStream_t st) {
     NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
   const unsigned long long grid = p.batch * (1ull << (P->logn - K1 - G::LOG_TILE));
   if (grid > 0x7fffffffull) return nttb200_fail(NTTB200_EPARAM, "batch too large for one launch");
-  kernel<<<(unsigned)grid, G::WARPS * 32, G::SMEM_BYTES, st>>>(p);
-  nttb200_count_launch(1);
-  NTT_CUDA(cudaGetLastError());
-  return 0;
+  return launch_pdl_large(kernel, (unsigned)grid, G::WARPS * 32, G::SMEM_BYTES, st, p);
 }
 template <int K1>
 int cols_inv(const nttb200_plan *P, LargeParams &p, cudaStream_t st) {
@@ -114,10 +129,7 @@ int rows_polymul(const nttb200_plan *P, LargeParams &p, cudaStream_t st) {
   NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const unsigned long long grid = row_grid(P, p.batch);
   if (grid > 0x7fffffffull) return nttb200_fail(NTTB200_EPARAM, "batch too large for one launch");
-  kernel<<<(unsigned)grid, ROW_WARPS * 32, smem, st>>>(p);
-  nttb200_count_launch(1);
-  NTT_CUDA(cudaGetLastError());
-  return 0;
+  return launch_pdl_large(kernel, (unsigned)grid, ROW_WARPS * 32, smem, st, p);
 }
 
 template <int DIR>
@@ -140,7 +152,7 @@ int rows_ntt(const nttb200_plan *P, LargeParams &p, cudaStream_t st) {
 /* one batch chunk of the product: ta/tb = scratch for a', b' (c' reuses ta) */
 int LARGE_CAT(launch_polymul_large_chunk_, LARGE_NAME)(const nttb200_plan *P, uint32_t *c, const uint32_t *a,
                                                        const uint32_t *b, uint32_t *ta, uint32_t *tb,
-                                                       size_t batch, cudaStream_t st) {
+                                                       size_t batch, cudaStream_t st, int early_loads) {
   const bool cyclic = (P->flags & NTTB200_PLAN_CYCLIC) != 0;
   const DevTable &fwd = cyclic ? P->fwd_plain : P->fwd_mixed;
   const DevTable &inv = cyclic ? P->inv_plain : P->inv_mixed;
@@ -149,7 +161,9 @@ int LARGE_CAT(launch_polymul_large_chunk_, LARGE_NAME)(const nttb200_plan *P, ui
   int rc;
   p.src[0] = a; p.src[1] = b; p.dst[0] = ta; p.dst[1] = tb; p.nops = 2;
   fill_utw(p, &fwd);
+  p.pdl = early_loads ? 1u : 0u;
   if ((rc = cols_fwd_any(P, p, st))) return rc;
+  p.pdl = 0;
   p.src[0] = ta; p.src[1] = tb; p.dst[0] = ta; p.dst[1] = nullptr; p.nops = 1;
   if ((rc = rows_polymul(P, p, st))) return rc;
   /* n^-1 * 2^32: the 2^32 cancels the Montgomery 2^-32 of the pointwise product */

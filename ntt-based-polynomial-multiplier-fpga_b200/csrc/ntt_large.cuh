@@ -48,6 +48,10 @@ struct LargeParams {
   uint2 last_y;               /* K3: multiplier of its diff branch (twiddle p[1] * scale)    */
   uint2 one;                  /* (1, floor(2^32/q)): Shoup pair that only reduces            */
   uint32_t zero;              /* always 0 (modq_regs)                                        */
+  uint32_t pdl;               /* programmatic dependent launch: bit 0 = the forward column pass may READ its
+                                 operands before the previous kernel of its stream has finished (it
+                                 then waits just before its first store into the scratch that kernel
+                                 may still be reading)                                              */
   uint2 utw[32];              /* column passes: entries [1, 32) of the table of this launch's
                                  direction -- the twiddles of the register phase on the high row
                                  bits, whose indices are compile-time numbers (constant bank)   */
@@ -156,6 +160,9 @@ large_cols_fwd_kernel(const __grid_constant__ LargeParams P) {
   uint32_t *dst = P.dst[op] + base;
   uint32_t *sm = smem + lane * CPL;                       /* [row][32 lanes][CPL] */
   const ModQ m = modq_regs(P.m, P.zero);
+  asm volatile("griddepcontrol.launch_dependents;");
+  const bool early = (P.pdl & 1u) != 0;
+  if (!early) asm volatile("griddepcontrol.wait;" ::: "memory");
 
   V x[G::NV];
   /* phase A: row bits K1-1 .. K1-RA are register bits; this warp's fixed low row bits = w */
@@ -172,6 +179,7 @@ large_cols_fwd_kernel(const __grid_constant__ LargeParams P) {
     }
   }
   if (G::RB == 0) {
+    if (early) asm volatile("griddepcontrol.wait;" ::: "memory");
 #pragma unroll
     for (int k = 0; k < G::NV; k++) cv_st<CPL>(dst + ((size_t)k << lr), x[k]);
     return;
@@ -201,6 +209,7 @@ large_cols_fwd_kernel(const __grid_constant__ LargeParams P) {
       }
     }
   }
+  if (early) asm volatile("griddepcontrol.wait;" ::: "memory");
 #pragma unroll
   for (int g = 0; g < G::GB; g++) {
     const int hfix = w * G::GB + g;
@@ -245,6 +254,8 @@ large_cols_inv_kernel(const __grid_constant__ LargeParams P) {
   uint32_t *dst = P.dst[0] + base;
   uint32_t *sm = smem + lane * CPL;
   const ModQ m = modq_regs(P.m, P.zero);
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   V x[G::NV];
   if (G::RB > 0) {
@@ -369,6 +380,8 @@ large_rows_polymul_kernel(const __grid_constant__ LargeParams P) {
   const unsigned long long poly = (bg * WARPS + warp) * Gm::PPW + sub;
   const bool live = poly < P.batch;
   const size_t off = ((size_t)(live ? poly : 0ull) << P.logn) + ((size_t)j << LR);
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   uint32_t xa[Gm::NV], xb[Gm::NV];
   gload_cols<LR>(xa, P.src[0] + off, l);

@@ -58,7 +58,19 @@ struct SmallParams {
 
 enum {
   SMALL_FLAG_SCALE_LAST = 1u,   /* multiply the sum branch of the last inverse stage by last_x */
+  SMALL_FLAG_NOWAIT = 2u,       /* the launch shares no data with the launches still in flight on its stream
+                                   (nttb200_launch_independent): it waits for them at its end, not its start */
 };
+/* programmatic dependent launch: let the next launch of the stream start its CTAs while this grid
+ * drains; a launch whose operands may come from its predecessors waits for them before touching
+ * memory, an independent one only before it ends (so the stream still completes in order) */
+__device__ __forceinline__ void pdl_begin(uint32_t flags) {
+  asm volatile("griddepcontrol.launch_dependents;");
+  if (!(flags & SMALL_FLAG_NOWAIT)) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_end(uint32_t flags) {
+  if (flags & SMALL_FLAG_NOWAIT) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 template <int L>
 struct SmallGeom {
@@ -380,6 +392,7 @@ polymul_small_kernel(const __grid_constant__ SmallParams<SmallGeom<L>::R> P) {
     twf.load(P.tw_fwd, l);
     twi.load(P.tw_inv, l);
   }
+  pdl_begin(P.flags);
 
   const unsigned long long ntiles = (P.batch + Gm::PPW - 1) / Gm::PPW;
   const unsigned long long wstride = (unsigned long long)gridDim.x * WARPS;
@@ -429,6 +442,7 @@ polymul_small_kernel(const __grid_constant__ SmallParams<SmallGeom<L>::R> P) {
     if (live) gstore_cols<L>(xa, P.c + off, l);
     __syncwarp();                                     /* smem reuse by the next tile */
   }
+  pdl_end(P.flags);
 }
 
 /* =====================================================================================
@@ -454,6 +468,7 @@ ntt_small_kernel(const __grid_constant__ SmallParams<SmallGeom<L>::R> P) {
 
   LaneTw<L> tw;
   tw.load(DIR == 0 ? P.tw_fwd : P.tw_inv, l);
+  pdl_begin(P.flags);
 
   const unsigned long long ntiles = (P.batch + Gm::PPW - 1) / Gm::PPW;
   const unsigned long long wstride = (unsigned long long)gridDim.x * WARPS;
@@ -503,6 +518,7 @@ ntt_small_kernel(const __grid_constant__ SmallParams<SmallGeom<L>::R> P) {
       if (live) gstore_cols<L>(x, P.c + off, l);
     }
   }
+  pdl_end(P.flags);
 }
 
 }  // namespace nttb200

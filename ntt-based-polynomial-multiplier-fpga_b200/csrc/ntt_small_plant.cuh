@@ -635,6 +635,8 @@ ntt_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
   LaneTw1<L> tw;
   tw.load(DIR == 0 ? P.tw_fwd : P.tw_inv, l);
   const PlRegs G = pl_regs(P);
+  asm volatile("griddepcontrol.launch_dependents;");
+  if (!P.nowait) asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const unsigned long long ntiles = (P.batch + Gm::PPW - 1) / Gm::PPW;
   const unsigned long long wstride = (unsigned long long)gridDim.x * WARPS;
@@ -689,6 +691,7 @@ ntt_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
       if (live) gstore_cols<L>(x, data + off, l);
     }
   }
+  if (P.nowait) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 }  // namespace nttb200

@@ -478,7 +478,7 @@ static int transform_dev(nttb200_plan *P, int transform, uint32_t *a, size_t bat
 static int env_int(const char *name, int dflt, int lo, int hi);
 #define DECL_LARGE(name)                                                                          \
   int launch_polymul_large_chunk_##name(const nttb200_plan *, uint32_t *, const uint32_t *,       \
-                                        const uint32_t *, uint32_t *, uint32_t *, size_t, cudaStream_t); \
+                                        const uint32_t *, uint32_t *, uint32_t *, size_t, cudaStream_t, int); \
   int launch_ntt_large_##name(const nttb200_plan *, const DevTable &, int, int, uint32_t *, size_t, \
                               cudaStream_t);                                                        \
   int large_fused_clusters_##name(const nttb200_plan *, int *);                                     \
@@ -504,6 +504,11 @@ static size_t large_scratch_budget() {
  * 2: one persistent dataflow kernel (n = 2^16).  Read per call: tests switch it. */
 static int large_mode() { return env_int("NTTB200_LARGE_FUSED", 0, 0, 2); }
 static int large_lanes() { static int v = env_int("NTTB200_LARGE_LANES", 3, 1, 8); return v; }
+
+static bool ranges_overlap(const uint32_t *x, const uint32_t *y, size_t words) {
+  const uintptr_t a = (uintptr_t)x, b = (uintptr_t)y, n = words * sizeof(uint32_t);
+  return a < b + n && b < a + n;
+}
 
 static int ensure_scratch(nttb200_plan *P, size_t polys, int lanes) {
   if (P->scratch_polys >= polys && (int)P->lanes.size() >= lanes) return 0;
@@ -595,10 +600,14 @@ int launch_polymul_large(nttb200_plan *P, uint32_t *c, const uint32_t *a, const 
     const int l = (int)(k % lanes);
     cudaStream_t ls = lanes > 1 ? P->lanes[l].stream : st;
     uint32_t *ta = P->scratch + (size_t)l * chunk * P->n * 2, *tb = ta + chunk * P->n;
+    /* From a lane's second chunk on, the kernel before this chunk's column pass is the same call's
+     * own last pass of an EARLIER chunk: unless the result array overlaps an operand, this chunk's
+     * operands cannot be its output, so they may be read while it still runs */
+    const int early = (k >= (size_t)lanes && !ranges_overlap(c, a, batch * P->n) && !ranges_overlap(c, b, batch * P->n)) ? 1 : 0;
     switch (P->arith) {
-      case ARITH_LAZY: rc = launch_polymul_large_chunk_lazy(P, c + o, a + o, b + o, ta, tb, nb, ls); break;
-      case ARITH_HARVEY: rc = launch_polymul_large_chunk_harvey(P, c + o, a + o, b + o, ta, tb, nb, ls); break;
-      default: rc = launch_polymul_large_chunk_canon(P, c + o, a + o, b + o, ta, tb, nb, ls); break;
+      case ARITH_LAZY: rc = launch_polymul_large_chunk_lazy(P, c + o, a + o, b + o, ta, tb, nb, ls, early); break;
+      case ARITH_HARVEY: rc = launch_polymul_large_chunk_harvey(P, c + o, a + o, b + o, ta, tb, nb, ls, early); break;
+      default: rc = launch_polymul_large_chunk_canon(P, c + o, a + o, b + o, ta, tb, nb, ls, early); break;
     }
     if (rc) return rc;
   }

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "ntt_small.cuh"
 #include "plan.h"
@@ -38,16 +39,51 @@ inline uint2 shoup_pair(uint64_t w, uint32_t q) {
 template <typename K>
 int grid_for(K kernel, int threads, int smem, int sm_count, unsigned long long tiles_per_block_unit,
              int *grid) {
-  int per_sm = 0;
-  NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  NTT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
-  if (per_sm < 1) return nttb200_fail(NTTB200_ECUDA, "kernel does not fit on an SM");
+  /* asked once per kernel and device, not per launch (kernels of one signature share K: key by address) */
+  struct Seen { const void *k; int dev; int v; };
+  static Seen seen[64];
+  static int nseen = 0;
+  static std::mutex mu;
+  int dev = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < nseen; i++)
+      if (seen[i].k == (const void *)kernel && seen[i].dev == dev) per_sm = seen[i].v;
+  }
+  if (!per_sm) {
+    NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    NTT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    if (per_sm < 1) return nttb200_fail(NTTB200_ECUDA, "kernel does not fit on an SM");
+    std::lock_guard<std::mutex> lock(mu);
+    if (nseen < 64) seen[nseen++] = Seen{(const void *)kernel, dev, per_sm};
+  }
   unsigned long long want = tiles_per_block_unit;
   unsigned long long cap = (unsigned long long)sm_count * per_sm;
   /* up to 4 times the resident CTAs while a warp still gets 6 tiles or more: the hardware hands
    * CTAs to the SMs as they free up, which evens out the SM-to-SM spread (small_plant.cu) */
   cap *= std::min<unsigned long long>(4, std::max<unsigned long long>(1, want / (cap * 6)));
   *grid = (int)(want < cap ? (want ? want : 1) : cap);
+  return 0;
+}
+
+/* launch with programmatic stream serialization; `flags` carries SMALL_FLAG_NOWAIT when the launch is
+ * independent of what is in flight on the stream (plan.h: nttb200_launch_independent) */
+template <typename K, typename PT>
+int launch_pdl(K kernel, int grid, int threads, int smem, cudaStream_t st, const PT &p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NTT_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+  nttb200_count_launch(1);
+  NTT_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -72,10 +108,9 @@ int run_polymul(const nttb200_plan *P, uint32_t *c, const uint32_t *a, const uin
   int grid = 0;
   int rc = grid_for(kernel, Cfg::WARPS * 32, smem, P->sm_count, (tiles + Cfg::WARPS - 1) / Cfg::WARPS, &grid);
   if (rc) return rc;
-  kernel<<<grid, Cfg::WARPS * 32, smem, st>>>(p);
-  nttb200_count_launch(1);
-  NTT_CUDA(cudaGetLastError());
-  return 0;
+  const size_t bytes = batch * Gm::N * sizeof(uint32_t);
+  if (nttb200_launch_independent(st, a, bytes, b, bytes, c, bytes)) p.flags |= SMALL_FLAG_NOWAIT;
+  return launch_pdl(kernel, grid, Cfg::WARPS * 32, smem, st, p);
 }
 
 template <int L, int DIR>
@@ -102,10 +137,10 @@ int run_ntt(const nttb200_plan *P, const DevTable &tab, int scale, uint32_t *a, 
   int grid = 0;
   int rc = grid_for(kernel, WARPS * 32, smem, P->sm_count, (tiles + WARPS - 1) / WARPS, &grid);
   if (rc) return rc;
-  kernel<<<grid, WARPS * 32, smem, st>>>(p);
-  nttb200_count_launch(1);
-  NTT_CUDA(cudaGetLastError());
-  return 0;
+  /* in place: the array is both read and written */
+  if (nttb200_launch_independent(st, a, batch * Gm::N * sizeof(uint32_t), nullptr, 0, a, batch * Gm::N * sizeof(uint32_t)))
+    p.flags |= SMALL_FLAG_NOWAIT;
+  return launch_pdl(kernel, grid, WARPS * 32, smem, st, p);
 }
 
 template <int L>

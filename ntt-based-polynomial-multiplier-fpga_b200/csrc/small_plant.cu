@@ -291,7 +291,19 @@ int run_ntt_plant(const nttb200_plan *P, const DevTable &tab, int scale, uint32_
   unsigned long long cap = (unsigned long long)P->sm_count * per_sm;
   cap *= std::min<unsigned long long>(4, std::max<unsigned long long>(1, want / (cap * 6)));   /* as run_plant */
   const int grid = (int)(want < cap ? (want ? want : 1) : cap);
-  kernel<<<grid, WARPS * 32, smem, st>>>(p);
+  p.nowait = (plant_pdl() && nttb200_launch_independent(st, a, batch * Gm::N * sizeof(uint32_t), nullptr, 0, a,
+                                                        batch * Gm::N * sizeof(uint32_t))) ? 1u : 0u;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(WARPS * 32);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = plant_pdl() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NTT_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
   nttb200_count_launch(1);
   NTT_CUDA(cudaGetLastError());
   return 0;
