@@ -227,7 +227,7 @@ def cpu_baseline(n, q, psi, seconds=4.0):
                       f"polymuls for {seconds:.0f} s (operand restore excluded, as time_testing256.c:175-185)"}
 
 
-def run_reference_arm(args, n, q, psi, logb, desc):
+def run_reference_arm(args, n, q, psi, logb, desc, out=sys.stdout):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -258,8 +258,10 @@ def run_reference_arm(args, n, q, psi, logb, desc):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": desc, "n": n, "q": q, "batch_per_step": sample,
-                   "note": "CPU arm: host cores only, no GPU, no host<->device copies"},
+        "config": {"workload": desc, "n": n, "q": q, "batch_per_gpu": full,
+                   "l2": "inputs larger than L2 (CPU arm: each process loops over its own slice)"},
+        "setup": {"batch_per_step": sample, "note": "CPU arm: host cores only, no GPU, no host<->device copies; each "
+                  "step is a bounded sample of the workload (cpu_baseline.sample)"},
         "cpu_baseline": {"value": value, "unit": "polymul/s", "cores": cores, "kind": kind,
                          "sample": f"{what}; each step = {sample} polymuls ({reps} passes over {per} rows "
                                    f"per process, {cores} processes = one per core; the workload has {full}), "
@@ -267,7 +269,7 @@ def run_reference_arm(args, n, q, psi, logb, desc):
         "e2e": {"value": value, "unit": "polymul/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
     return 0
 
 
@@ -442,7 +444,19 @@ def side_workload(mod, sh, torch, name, dev, rank, world, local, peak_gbs, imad_
         w.close()
 
 
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    banner and, at NCCL_DEBUG=INFO, its whole log to the C-level stdout): keep a private copy of the
+    real stdout for the JSON line and point file descriptor 1 at stderr for everybody else, so
+    nothing is lost and NCCL_DEBUG stays as the operator set it."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main() -> int:
+    out = protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
@@ -458,7 +472,7 @@ def main() -> int:
     batch = 1 << logb
 
     if args.impl == "reference":
-        return run_reference_arm(args, n, q, psi, logb, desc)
+        return run_reference_arm(args, n, q, psi, logb, desc, out)
 
     import torch
     mod = importlib.import_module(PKG)
@@ -620,8 +634,10 @@ def main() -> int:
         "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
         "data": "synthetic",
-        "config": {"workload": desc, "n": n, "q": q, "psi": plan_psi, "batch_per_gpu": batch,
-                   "plan": plan_desc,
+        "config": {"workload": desc, "n": n, "q": q, "batch_per_gpu": batch,
+                   "l2": f"inputs larger than L2: {sets} rotating buffer sets ({sets * 3 * batch * row_bytes >> 20} MiB "
+                         f"against 126 MB), no step finds its operands cached"},
+        "setup": { "psi": plan_psi, "plan": plan_desc,
                    "inputs": "SURVEY 8d batch: splitmix64 stream, coefficient = next() % q, edge rows 0..7 "
                              "(0, q-1, delta_0, delta_{n-1}, KATs 1-4), the reference's coefficient files in row 8",
                    "l2": f"inputs rotate over {sets} buffer sets ({sets * 3 * batch * row_bytes >> 20} MiB) "
@@ -670,7 +686,7 @@ def main() -> int:
         except Exception as ex:  # the baseline is a report, never a reason to lose the GPU line
             line["cpu_baseline"] = {"value": None, "error": repr(ex)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
