@@ -276,6 +276,35 @@ def run_reference_arm(args, n, q, psi, logb, desc, out=sys.stdout):
 # --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
+def bind_near_gpu(local: int, world: int):
+    """N > 1, host-buffer calls: every rank narrows, stages and widens its rows with a pool of host
+    threads into pinned memory, and eight ranks share one box.  Keep each rank's threads -- and, by
+    first touch, its pinned pages -- on the CPUs NVML reports as local to its GPU, and split those
+    CPUs between the ranks that share them.  Returns (cpus of this rank, threads for its pool) or None
+    when NVML has nothing to say (then the ranks simply split all cores evenly)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        allowed = os.sched_getaffinity(0)
+        words = (max(allowed) // 64) + 1
+
+        def near(i):
+            h = pynvml.nvmlDeviceGetHandleByIndex(i)
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+            return frozenset(64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1) & allowed
+        mine = near(local)
+        sharers = [i for i in range(world) if near(i) == mine]
+        if len(mine) < 2 * len(sharers):
+            return None                                   # too few local cores to be worth a binding
+        cpus = sorted(mine)
+        k = sharers.index(local)
+        part = cpus[len(cpus) * k // len(sharers): len(cpus) * (k + 1) // len(sharers)]
+        os.sched_setaffinity(0, part)
+        return part, len(part)
+    except Exception:
+        return None
+
+
 def load_fixture():
     """The reference's coefficient files (row 8 of the (256, 12289) batch); the committed
     copy under tests/golden (a fixture file, not the oracle)."""
@@ -351,12 +380,13 @@ class Workload:
                                            row_offset=off + k * (self.full_batch * max(1, world)))
             self.bufs.append((a, b, torch.empty_like(a)))
         self.stream = torch.cuda.current_stream().cuda_stream
+        self.ptrs = [(c.data_ptr(), a.data_ptr(), b.data_ptr()) for a, b, c in self.bufs]
         self.alg_bytes = 12 * self.n * self.batch               # read a, read b, write c (int32 API)
         self.launches_per_step = None
 
     def step(self, i):
-        a, b, c = self.bufs[i % self.sets]
-        self.plan.polymul_dev(c.data_ptr(), a.data_ptr(), b.data_ptr(), self.batch, self.stream)
+        c, a, b = self.ptrs[i % self.sets]
+        self.plan.polymul_dev(c, a, b, self.batch, self.stream)
 
     def timed(self, steps, warmup, local, clocks=True):
         """K steps between two events, barrier + synchronize on both sides, max over ranks."""
@@ -486,8 +516,10 @@ def main() -> int:
     if world > 1:
         sh.init_distributed("nccl")
     # the ranks of one box share its host cores: split them between the per-process pools that
-    # narrow / widen the rows of the host-buffer call (csrc/hostwire.c)
-    os.environ.setdefault("NTTB200_HOST_THREADS", str(max(1, host_cores() // max(1, world))))
+    # narrow / widen the rows of the host-buffer call (csrc/hostwire.c), each rank next to its GPU
+    binding = bind_near_gpu(local, world) if world > 1 and os.environ.get("NTTB200_BENCH_BIND", "1") != "0" else None
+    os.environ.setdefault("NTTB200_HOST_THREADS",
+                          str(binding[1] if binding else max(1, host_cores() // max(1, world))))
     warmup = max(3, args.warmup)
     peak_gbs, peak_src = measured_peaks()
     imad_peak = mod.measure_int_peak(0)
@@ -642,7 +674,8 @@ def main() -> int:
                              "(0, q-1, delta_0, delta_{n-1}, KATs 1-4), the reference's coefficient files in row 8",
                    "l2": f"inputs rotate over {sets} buffer sets ({sets * 3 * batch * row_bytes >> 20} MiB) "
                          f"> 126 MB L2, so no step finds its operands cached",
-                   "parallelism": f"batch-sharded x{world}, no collective"},
+                   "parallelism": f"batch-sharded x{world}, no collective",
+                   "host_binding": (f"rank 0 bound to {len(binding[0])} CPUs local to its GPU" if binding else "none")},
         "e2e": {"value": e2e_value, "unit": "polymul/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
                 "api": "nttb200_polymul_batch (int32 host buffers in and out, pinned; stream ring; rows cross "
                        "PCIe as 16-bit words when the host thread pool narrows them, else as 32-bit words)",

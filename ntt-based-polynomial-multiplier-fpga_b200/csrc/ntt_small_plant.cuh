@@ -392,6 +392,9 @@ __device__ __forceinline__ void cp_async16(uint32_t *smem_dst, const uint32_t *g
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+#ifndef PLANT_SHARE_XCHG
+#define PLANT_SHARE_XCHG 0
+#endif
 template <int L, typename IO = uint32_t>
 struct PlantGeom {
   using Gm = SmallGeom<L>;
@@ -402,8 +405,11 @@ struct PlantGeom {
   static constexpr int CHUNKS = Gm::N / EPC;                    /* 16-byte chunks per polynomial */
   static constexpr int ITERS = (Gm::PPW * CHUNKS + 31) / 32;     /* cp.async per lane per operand */
   static constexpr int PF_WORDS = (Gm::PPW * PSTRIDE * (int)sizeof(IO) + 15) / 16 * 4;   /* per operand */
-  /* per warp: prefetch a, prefetch b, transposition a, transposition b */
-  static constexpr int WARP_WORDS = 2 * PF_WORDS + 2 * Gm::PPW * Gm::STRIDE;
+  /* per warp: prefetch a, prefetch b, transposition a, transposition b.  From n = 512 up the two
+   * operands take turns in ONE transposition buffer (PLANT_SHARE_XCHG): 12 instead of 16 KiB per warp
+   * at n = 1024, which is what lets a fourth CTA (16 warps) fit into the SM's shared memory */
+  static constexpr bool SHARE_XCHG = PLANT_SHARE_XCHG && (L >= 9);
+  static constexpr int WARP_WORDS = 2 * PF_WORDS + (SHARE_XCHG ? 1 : 2) * Gm::PPW * Gm::STRIDE;
 };
 
 template <int L, typename IO>
@@ -433,8 +439,11 @@ __device__ __forceinline__ void plant_prefetch(IO *pa, IO *pb, const IO *ga, con
 #ifndef PLANT_MINB_SCALE
 #define PLANT_MINB_SCALE 1   /* with PLANT_WARPS=4: 2 keeps 16 warps per SM as 4 CTAs (tuning experiment) */
 #endif
+#ifndef PLANT_BIG_MINB
+#define PLANT_BIG_MINB 0     /* tuning experiment: resident CTAs asked for at n >= 512 (0 = MINB) */
+#endif
 template <int L, int WARPS, int MINB, bool TWREG, typename IO = uint32_t, typename OIO = IO>
-__global__ void __launch_bounds__(WARPS * 32, (L <= 8) ? MINB * PLANT_MINB_SCALE : MINB)
+__global__ void __launch_bounds__(WARPS * 32, (L <= 8) ? MINB * PLANT_MINB_SCALE : (PLANT_BIG_MINB ? PLANT_BIG_MINB : MINB))
 polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
   using Gm = SmallGeom<L>;
   using Pg = PlantGeom<L, IO>;
@@ -446,7 +455,7 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
   IO *pf_a = reinterpret_cast<IO *>(smem + warp * Pg::WARP_WORDS);
   IO *pf_b = reinterpret_cast<IO *>(smem + warp * Pg::WARP_WORDS + Pg::PF_WORDS);
   uint32_t *sm_a = smem + warp * Pg::WARP_WORDS + 2 * Pg::PF_WORDS + sub * Gm::STRIDE;
-  uint32_t *sm_b = sm_a + Gm::PPW * Gm::STRIDE;
+  uint32_t *sm_b = Pg::SHARE_XCHG ? sm_a : sm_a + Gm::PPW * Gm::STRIDE;
   const IO *ga = static_cast<const IO *>(P.a), *gb = static_cast<const IO *>(P.b);
   OIO *gc = static_cast<OIO *>(P.c);                  /* result rows may be wider than the operands */
   const PlRegs G = pl_regs(P);
@@ -528,9 +537,14 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
     }
     if (Gm::H > 0) {
       store_cols<L>(xa, sm_a, l);
+      if (Pg::SHARE_XCHG) {                             /* one buffer: a goes through, then b */
+        __syncwarp();
+        load_rows<L>(xa, sm_a, l);
+        __syncwarp();
+      }
       store_cols<L>(xb, sm_b, l);
       __syncwarp();
-      load_rows<L>(xa, sm_a, l);
+      if (!Pg::SHARE_XCHG) load_rows<L>(xa, sm_a, l);
       load_rows<L>(xb, sm_b, l);
       if (!TWREG) twf.load(P.tw_fwd, l);
       pl_fwd_rows<L>(xa, twf, P, G);

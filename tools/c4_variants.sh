@@ -1,5 +1,6 @@
+# c4 (n=1024, q=12289, batch 2^18) with variant builds of the library: bash tools/c4_variants.sh "" _x3 _x4 ...
 L=$PWD/ntt-based-polynomial-multiplier-fpga_b200
-for t in "" _b14 _b12; do
+for t in "$@"; do
   NTTB200_LIB=$L/libnttb200$t.so timeout 300 python bench.py --workload c4 --steps 100 --warmup 10 --no-cpu-baseline --no-side-workloads --e2e-steps 2 > gpurun_out/c4v$t.json 2> gpurun_out/c4v$t.err
   python -c "
 import json
