@@ -54,9 +54,10 @@ WORKLOADS = {
 }
 # DRAM bytes (read + write) per launch of the dominant kernel, from `ncu --set full` captures
 # committed under profiles/ (a profiler run is never a bench value; this is the traffic only)
-TRAFFIC_NCU = {"c2": 134264064 + 35679488}
-TRAFFIC_SRC = {"c2": "profiles/r1_c2_polymul_plant_n256_v5_ncu_full.txt: dram__bytes_read.sum 134.26 MB + "
-                     "dram__bytes_write.sum 35.68 MB per launch (algorithmic 201.3 MB; part of c stays dirty in L2)"}
+TRAFFIC_NCU = {"c2": 134265088 + 37861120, "c4": 2147971000 + 1040125000}
+TRAFFIC_SRC = {"c2": "profiles/r2_c2_plant_nowait_ncu_full.txt: dram__bytes_read.sum 134.27 MB + "
+                     "dram__bytes_write.sum 37.86 MB per launch (algorithmic 201.3 MB; part of c stays dirty in L2)",
+               "c4": "profiles/r2_c4_plant_ncu_full.txt: 2.148 GB read + 1.040 GB written per launch (algorithmic 3.221 GB)"}
 SEED = 0x4E545442323030
 L2_BYTES = 126 * 1000 * 1000
 
