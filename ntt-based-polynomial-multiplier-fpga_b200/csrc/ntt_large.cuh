@@ -84,9 +84,9 @@ template <int CPL>
 __device__ __forceinline__ CVec<CPL> cv_ldg(const uint32_t *p) {
   CVec<CPL> r;
   if (CPL == 1) {
-    r.v[0] = __ldg(p);
+    r.v[0] = __ldcg(p);             /* L2, not the non-coherent path: see gload_cols in ntt_small.cuh */
   } else {
-    const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+    const uint2 t = __ldcg(reinterpret_cast<const uint2 *>(p));
     r.v[0] = t.x;
     r.v[CPL - 1] = t.y;
   }

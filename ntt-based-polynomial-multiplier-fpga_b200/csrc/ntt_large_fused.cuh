@@ -86,7 +86,7 @@ __device__ __forceinline__ void fused_cols_fwd(const uint32_t *src, uint32_t *ds
   constexpr int lr = LARGE_LR;
   uint32_t x[G::NV];
 #pragma unroll
-  for (int k = 0; k < G::NV; k++) x[k] = __ldg(src + ((size_t)((k << G::RB) | w) << lr));
+  for (int k = 0; k < G::NV; k++) x[k] = __ldcg(src + ((size_t)((k << G::RB) | w) << lr));
 #pragma unroll
   for (int s = 0; s < G::RA; s++) {
     const int bit = G::RA - 1 - s;

@@ -159,12 +159,18 @@ __device__ __forceinline__ void store_rows(const uint32_t (&x)[SmallGeom<L>::NV]
   }
 }
 
-/* ---- global memory, layout 1: lane l, register k  <->  coefficient (k << H) | l ------ */
+/* ---- global memory, layout 1: lane l, register k  <->  coefficient (k << H) | l ------
+ * Operands are read with ld.global.cg (L2), NOT through the non-coherent path (__ldg): the kernels
+ * are launched with programmatic stream serialization, so their lifetime overlaps the previous
+ * kernel of the stream -- which may be the one that WRITES these operands.  After
+ * griddepcontrol.wait its stores are visible in L2, but a line it read earlier can still sit in this
+ * SM's non-coherent cache; "read-only for the lifetime of the kernel" does not hold.  (Found by
+ * tests/test_gpu_parity.py::test_random_launch_sequences_...; twiddle tables stay on __ldg.) */
 template <int L>
 __device__ __forceinline__ void gload_cols(uint32_t (&x)[SmallGeom<L>::NV], const uint32_t *g, int l) {
   using Gm = SmallGeom<L>;
 #pragma unroll
-  for (int k = 0; k < Gm::NV; k++) x[k] = __ldg(g + (k << Gm::H) + l);
+  for (int k = 0; k < Gm::NV; k++) x[k] = __ldcg(g + (k << Gm::H) + l);
 }
 template <int L>
 __device__ __forceinline__ void gstore_cols(const uint32_t (&x)[SmallGeom<L>::NV], uint32_t *g, int l) {
@@ -182,7 +188,7 @@ __device__ __forceinline__ void gload_rows(uint32_t (&x)[SmallGeom<L>::NV], cons
     if (Gm::H >= 2) {
 #pragma unroll
       for (int c = 0; c < Gm::CPR; c++) {
-        uint4 v = __ldg(reinterpret_cast<const uint4 *>(rowp) + c);
+        uint4 v = __ldcg(reinterpret_cast<const uint4 *>(rowp) + c);
         x[(g << Gm::H) + 4 * c + 0] = v.x;
         x[(g << Gm::H) + 4 * c + 1] = v.y;
         x[(g << Gm::H) + 4 * c + 2] = v.z;
@@ -190,7 +196,7 @@ __device__ __forceinline__ void gload_rows(uint32_t (&x)[SmallGeom<L>::NV], cons
       }
     } else {
 #pragma unroll
-      for (int r = 0; r < Gm::T; r++) x[(g << Gm::H) + r] = __ldg(rowp + r);
+      for (int r = 0; r < Gm::T; r++) x[(g << Gm::H) + r] = __ldcg(rowp + r);
     }
   }
 }

@@ -303,6 +303,15 @@ bool nttb200_launch_independent(cudaStream_t st, const void *a, size_t abytes, c
   return indep;
 }
 
+/* Kernels of this library that trigger their dependents early but are NOT recorded above (the large-n
+ * pipeline writes its result from several launches and lanes) forget the stream's history instead: the
+ * next recorded launch then waits, whatever it reads. */
+void nttb200_launch_forget(cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(g_hist_mu);
+  for (auto &x : g_hist)
+    if (x.used && x.st == st) x.n = 0;
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* dispatch                                                                              */
 /* ------------------------------------------------------------------------------------ */
@@ -532,6 +541,7 @@ int launch_polymul_large(nttb200_plan *P, uint32_t *c, const uint32_t *a, const 
    * streams are serialised on the device through `scratch_done` (recorded at the end of every
    * call, awaited at the start of the next), and on the host by large_mu. */
   std::lock_guard<std::mutex> lock(P->large_mu);
+  nttb200_launch_forget(st);
   if (!P->scratch_done) NTT_CUDA(cudaEventCreateWithFlags(&P->scratch_done, cudaEventDisableTiming));
   else NTT_CUDA(cudaStreamWaitEvent(st, P->scratch_done, 0));
   /* n = 2^15, 2^16: one persistent cluster kernel for the whole batch (ntt_large_fused.cuh); its
@@ -623,6 +633,7 @@ int launch_polymul_large(nttb200_plan *P, uint32_t *c, const uint32_t *a, const 
 
 int launch_ntt_large(nttb200_plan *P, const DevTable &tab, int dir, int scale, uint32_t *a, size_t batch,
                      cudaStream_t st) {
+  nttb200_launch_forget(st);
   switch (P->arith) {
     case ARITH_LAZY: return launch_ntt_large_lazy(P, tab, dir, scale, a, batch, st);
     case ARITH_HARVEY: return launch_ntt_large_harvey(P, tab, dir, scale, a, batch, st);

@@ -120,6 +120,7 @@ void nttb200_count_launch(int k);
 /* Is a launch on `st` that reads [a, a+abytes), [b, b+bbytes) and writes [c, c+cbytes) independent of
  * every launch of this library that may still be running on that stream?  Records the launch either
  * way (nttb200.cu). */
+void nttb200_launch_forget(cudaStream_t st);
 bool nttb200_launch_independent(cudaStream_t st, const void *a, size_t abytes, const void *b, size_t bbytes,
                                 const void *c, size_t cbytes);
 

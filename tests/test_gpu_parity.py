@@ -981,3 +981,101 @@ def test_independent_launches_skip_the_wait_dependent_ones_do_not(gpu, oracle, n
     want = oracle.product(n, q, ab[rr].cpu().numpy(), bb[rr].cpu().numpy(), 10)
     assert (cb[rr].cpu().numpy() == want).all()
     p.close()
+
+
+@pytest.mark.parametrize("n,q", [(256, 12289), (256, 8380417), (1024, 12289)])
+def test_random_launch_sequences_on_one_stream_equal_their_sequential_meaning(gpu, oracle, nttb200, n, q):
+    """60 products issued back to back on ONE stream over a pool of six buffers, each on a random row
+    range, with operands and results drawn at random (results over operands, results read by the next
+    launch, ranges that overlap partly): whatever the library decides about which launches may start
+    early, every buffer ends up as if the launches had run one after the other (replayed with the
+    oracle on the sampled rows -- rows are independent)."""
+    import torch
+    rows = 1 << 14
+    p = gpu.Plan(n, q)
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(n + q)
+    bufs = [nttb200.inputs.survey_batch(n, q, rows, 2, device="cuda", row_offset=k * rows)[0] for k in range(6)]
+    watch = np.unique(np.r_[0:4, rows - 4:rows, rng.integers(0, rows, 40)])
+    model = [b[torch.from_numpy(watch).cuda()].cpu().numpy() for b in bufs]
+    plan = []
+    for _ in range(60):
+        ia, ib, ic = rng.integers(0, 6, 3)
+        lo = int(rng.integers(0, rows - 1))
+        hi = int(rng.integers(lo + 1, min(rows, lo + rng.choice([64, 2048, rows])) + 1))
+        plan.append((int(ia), int(ib), int(ic), lo, hi))
+    for ia, ib, ic, lo, hi in plan:
+        off = lo * n * 4
+        p.polymul_dev(bufs[ic].data_ptr() + off, bufs[ia].data_ptr() + off, bufs[ib].data_ptr() + off, hi - lo, st)
+    torch.cuda.synchronize()
+    for ia, ib, ic, lo, hi in plan:
+        m = (watch >= lo) & (watch < hi)
+        if m.any():
+            model[ic][m] = oracle.product(n, q, model[ia][m], model[ib][m], 10)
+    for k in range(6):
+        got = bufs[k][torch.from_numpy(watch).cuda()].cpu().numpy()
+        assert (got == model[k]).all(), k
+    p.close()
+
+
+def _friendly_primes(L, n, bits, count):
+    out = []
+    for seed in range(count * 3):
+        q = L.nttb200_gen_prime(bits, n, seed)
+        if q and q not in out:
+            out.append(int(q))
+        if len(out) == count:
+            break
+    return out
+
+
+@pytest.mark.parametrize("logn", [3, 5, 8, 9, 10, 11, 13, 16, 17])
+def test_products_at_generated_primes_of_every_width(gpu, oracle, logn):
+    """NTT-friendly primes from the library's own generator (Generator_Params twin) at 13 .. 31 bits:
+    every arithmetic class (Plantard, LAZY, HARVEY, CANON) at every kernel family, against the oracle."""
+    n = 1 << logn
+    import ctypes
+    L = gpu.lib()
+    L.nttb200_gen_prime.restype = ctypes.c_uint32
+    L.nttb200_gen_prime.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64]
+    seen = set()
+    for bits in (13, 14, 17, 20, 23, 26, 29, 30, 31):
+        if bits < logn + 2:
+            continue
+        for q in _friendly_primes(L, n, bits, 2 if logn <= 10 else 1):
+            if q in seen or (q - 1) % (2 * n):
+                continue
+            seen.add(q)
+            p = gpu.Plan(n, q)
+            batch = 9 if logn <= 10 else 3
+            a, b = oracle.random((batch, n), q, SEED + q), oracle.random((batch, n), q, SEED + q + 1)
+            a[0], b[0] = q - 1, q - 1
+            a[1] = np.where(np.arange(n) % 2 == 0, q - 1, 0)
+            assert (p.polymul(a, b) == oracle.product(n, q, a, b, 10)).all(), p.describe()
+            p.close()
+    assert len(seen) >= 4
+
+
+def test_small_product_right_after_a_large_n_product_on_the_same_stream(gpu, oracle, nttb200):
+    """A large-n product (its last kernel triggers its dependents early) followed at once by an
+    n = 256 product that reads its result viewed as rows of 256: the second one must wait."""
+    import torch
+    nl, q = 4096, 12289
+    pl, ps = gpu.Plan(nl, q), gpu.Plan(256, q)
+    st = torch.cuda.current_stream().cuda_stream
+    a, b = nttb200.inputs.survey_batch(nl, q, 48, 4, device="cuda")
+    warm = nttb200.inputs.survey_batch(256, q, 64, 2, device="cuda")
+    wc = torch.empty_like(warm[0])
+    for rep in range(3):
+        c = torch.zeros_like(a)
+        d = torch.empty_like(a)
+        ps.polymul_dev(wc.data_ptr(), warm[0].data_ptr(), warm[1].data_ptr(), 64, st)     # history on the stream
+        pl.polymul_dev(c.data_ptr(), a.data_ptr(), b.data_ptr(), 48, st)
+        ps.polymul_dev(d.data_ptr(), c.data_ptr(), b.data_ptr(), 48 * nl // 256, st)      # reads c as rows of 256
+        torch.cuda.synchronize()
+        hc = oracle.product(nl, q, a.cpu().numpy(), b.cpu().numpy(), 10)
+        assert (c.cpu().numpy() == hc).all()
+        want = oracle.product(256, q, hc.reshape(-1, 256), b.cpu().numpy().reshape(-1, 256), 10)
+        assert (d.cpu().numpy().reshape(-1, 256) == want).all()
+    pl.close()
+    ps.close()
