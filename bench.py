@@ -384,6 +384,12 @@ class Workload:
         self.ptrs = [(c.data_ptr(), a.data_ptr(), b.data_ptr()) for a, b, c in self.bufs]
         self.alg_bytes = 12 * self.n * self.batch               # read a, read b, write c (int32 API)
         self.launches_per_step = None
+        # setup, not a step: every buffer set goes through the call once, so that no timed step is the
+        # first ever to touch its result buffer (with W = 5 warm-up steps over 8 sets three of them would
+        # be: measured 1 296 vs 1 327 M polymul/s for the K = 20 region, tools/k20_probe.py)
+        for i in range(self.sets):
+            self.step(i)
+        torch.cuda.synchronize()
 
     def step(self, i):
         c, a, b = self.ptrs[i % self.sets]
