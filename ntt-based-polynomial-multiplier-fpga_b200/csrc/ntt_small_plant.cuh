@@ -395,6 +395,9 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 #ifndef PLANT_SHARE_XCHG
 #define PLANT_SHARE_XCHG 0
 #endif
+#ifndef PLANT_SEQ_AB
+#define PLANT_SEQ_AB 0       /* tuning experiment (n >= 512): see polymul_plant_kernel */
+#endif
 template <int L, typename IO = uint32_t>
 struct PlantGeom {
   using Gm = SmallGeom<L>;
@@ -408,7 +411,8 @@ struct PlantGeom {
   /* per warp: prefetch a, prefetch b, transposition a, transposition b.  From n = 512 up the two
    * operands take turns in ONE transposition buffer (PLANT_SHARE_XCHG): 12 instead of 16 KiB per warp
    * at n = 1024, which is what lets a fourth CTA (16 warps) fit into the SM's shared memory */
-  static constexpr bool SHARE_XCHG = PLANT_SHARE_XCHG && (L >= 9);
+  static constexpr bool SEQ_AB = PLANT_SEQ_AB && (L >= 9) && !PLANT_BULK_STORE;
+  static constexpr bool SHARE_XCHG = PLANT_SHARE_XCHG && (L >= 9) && !SEQ_AB;
   static constexpr int WARP_WORDS = 2 * PF_WORDS + (SHARE_XCHG ? 1 : 2) * Gm::PPW * Gm::STRIDE;
 };
 
@@ -512,6 +516,37 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
     uint32_t xa[Gm::NV], xb[Gm::NV];
     cp_async_wait_all();
     __syncwarp();
+    if (Pg::SEQ_AB) {
+      /* n >= 512, PLANT_SEQ_AB: ONE copy of the forward transform's code, run for a and then for b
+       * (a real loop: the operand is picked by a pointer), NTT(a) parked in the warp's second buffer in
+       * the meantime -- a third less code for the instruction cache at the price of the a/b interleaving */
+      uint32_t *park = smem + warp * Pg::WARP_WORDS + 2 * Pg::PF_WORDS + Gm::PPW * Gm::STRIDE + lane;
+#pragma unroll 1
+      for (int op = 0; op < 2; op++) {
+        const IO *pf = op ? pf_b : pf_a;
+#pragma unroll
+        for (int k = 0; k < Gm::NV; k++) xb[k] = pf[sub * Pg::PSTRIDE + (k << Gm::H) + l];
+        if (op == 1) {
+          __syncwarp();                               /* prefetch buffers are free again */
+          if (next < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, next, P.batch, lane);
+        }
+        pl_fwd_cols<L>(xb, P, G);
+        if (Gm::H > 0) {
+          __syncwarp();
+          store_cols<L>(xb, sm_a, l);
+          __syncwarp();
+          load_rows<L>(xb, sm_a, l);
+          if (!TWREG) twf.load(P.tw_fwd, l);
+          pl_fwd_rows<L>(xb, twf, P, G);
+        }
+        if (op == 0) {
+#pragma unroll
+          for (int k = 0; k < Gm::NV; k++) park[k * 32] = xb[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < Gm::NV; k++) xa[k] = park[k * 32];
+    } else {
 #pragma unroll
     for (int k = 0; k < Gm::NV; k++) {
       xa[k] = pf_a[sub * Pg::PSTRIDE + (k << Gm::H) + l];
@@ -519,6 +554,7 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
     }
     __syncwarp();                                     /* prefetch buffers are free again */
     if (next < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, next, P.batch, lane);
+    }
     /* the tile after next: round-robin while static rounds are left, then one grab from the
      * counter, issued here and only looked at when this tile ends */
     const bool grab = dyn && rounds_left == 0;
@@ -529,6 +565,7 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
       if (dyn) rounds_left--;
     }
 
+    if (!Pg::SEQ_AB) {
     pl_fwd_cols<L>(xa, P, G);
     pl_fwd_cols<L>(xb, P, G);
     if (BULK && bulk_pending) {                       /* the previous tile's result row has left sm_a */
@@ -549,6 +586,7 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
       if (!TWREG) twf.load(P.tw_fwd, l);
       pl_fwd_rows<L>(xa, twf, P, G);
       pl_fwd_rows<L>(xb, twf, P, G);
+    }
     }
 
     /* pointwise product (mul_array, R/NTT/ntt.C:131-137) as a Plantard product of two
