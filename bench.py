@@ -54,10 +54,10 @@ WORKLOADS = {
 }
 # DRAM bytes (read + write) per launch of the dominant kernel, from `ncu --set full` captures
 # committed under profiles/ (a profiler run is never a bench value; this is the traffic only)
-TRAFFIC_NCU = {"c2": 134265088 + 37861120, "c4": 2147971000 + 1040125000}
-TRAFFIC_SRC = {"c2": "profiles/r2_c2_plant_nowait_ncu_full.txt: dram__bytes_read.sum 134.27 MB + "
-                     "dram__bytes_write.sum 37.86 MB per launch (algorithmic 201.3 MB; part of c stays dirty in L2)",
-               "c4": "profiles/r2_c4_plant_ncu_full.txt: 2.148 GB read + 1.040 GB written per launch (algorithmic 3.221 GB)"}
+TRAFFIC_NCU = {"c2": 134259456 + 37774592, "c4": 2147583000 + 1039149000}
+TRAFFIC_SRC = {"c2": "profiles/r2_c2_splant_inc_ncu_full.txt: dram__bytes_read.sum 134.26 MB + "
+                     "dram__bytes_write.sum 37.77 MB per launch (algorithmic 201.3 MB; part of c stays dirty in L2)",
+               "c4": "profiles/r2_c4_splant_ncu_full.txt: 2.148 GB read + 1.039 GB written per launch (algorithmic 3.221 GB)"}
 SEED = 0x4E545442323030
 L2_BYTES = 126 * 1000 * 1000
 
@@ -316,12 +316,18 @@ def load_fixture():
         return None
 
 
-def slots_per_polymul(n: int, plantard: bool) -> int:
+def slots_per_polymul(n: int, plantard: bool, signed: bool = False) -> int:
     """fmaheavy issue slots per product as the kernels are written: Shoup butterfly = IMAD.HI (2 slots:
     measured half rate) + 2 IMAD; pointwise Montgomery = 2 IMAD.HI + 2 IMAD; the n^-1 scaling costs one
     extra multiplication on the sum branch of the last stage.  Plantard (q <= 12385): butterfly 3,
-    pointwise 4, scale 3; at n <= 256 butterfly and scale 2 (IMAD, SHF, IMAD, SHF)."""
+    pointwise 4, scale 3; at n <= 256 butterfly and scale 2 (IMAD, SHF, IMAD, SHF).  Signed Plantard
+    kernel (ntt_small_splant.cuh, the default): L - 1 stages per transform with 2 multiplications per
+    butterfly, 4 in the butterflies of the last inverse stage, and per coefficient pair 2 Barrett steps
+    (2 each), 5 raw products and 3 reductions (2 each): n (3 L + 5.5)."""
     bflies = 3 * (n // 2) * (n.bit_length() - 1)
+    L = n.bit_length() - 1
+    if plantard and signed:
+        return 2 * n * (L - 1) + (n // 2) * 15 + n * (L - 2) + 2 * n
     if plantard and n <= 256:
         return 2 * bflies + 4 * n + 2 * (n // 2)
     if plantard:
@@ -363,6 +369,7 @@ class Workload:
         self.cyclic = (self.q - 1) % (2 * self.n) != 0          # q=3329, n=256: no 512-th root of unity
         self.plan = mod.Plan(self.n, self.q, self.psi, cyclic=self.cyclic)
         self.plantard = "plantard" in self.plan.describe()
+        self.signed = "plantard-signed" in self.plan.describe()
         row_bytes = self.n * 4
         # distinct buffer sets so that successive steps never find their inputs in the 126 MB L2; a
         # stream of fresh batches is also what the call is for, so rotate over 8 sets (24 GiB at most):
@@ -445,7 +452,7 @@ class Workload:
     def fractions(self, rate_per_gpu, peak_gbs, imad_peak):
         n = self.n
         modmuls = 3 * (n // 2) * (n.bit_length() - 1) + n      # M
-        slots = slots_per_polymul(n, self.plantard)
+        slots = slots_per_polymul(n, self.plantard, self.signed)
         return {"hbm_frac": rate_per_gpu * 12 * n / 1e9 / peak_gbs,
                 "imad_frac_survey_3_per_modmul": rate_per_gpu * 3 * modmuls / imad_peak if imad_peak else None,
                 "imad_slot_frac_as_written": rate_per_gpu * slots / imad_peak if imad_peak else None}
@@ -633,7 +640,7 @@ def main() -> int:
     bflies = 3 * (n // 2) * logn
     modmuls = bflies + n                            # M
     plantard = W.plantard
-    slots = slots_per_polymul(n, plantard)
+    slots = slots_per_polymul(n, plantard, W.signed)
     rate = batch / (roof_ms * 1e-3)
     int_achieved = rate * 3 * modmuls
     slot_achieved = rate * slots
@@ -695,7 +702,8 @@ def main() -> int:
         "sustained": sustained,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
-                     "kernel": ("polymul_plant_kernel" if plantard else "polymul_small_kernel") if n <= 1024 else
+                     "kernel": (("polymul_splant_kernel" if W.signed else "polymul_plant_kernel") if plantard
+                                else "polymul_small_kernel") if n <= 1024 else
                                "large-n product pipeline (whole step)",
                      "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": roof_ms,
                      "traffic_source": TRAFFIC_SRC.get(args.workload)},
@@ -711,7 +719,7 @@ def main() -> int:
                          "note": "peak = independent IMAD chains on every SM, measured live "
                                  "(nttb200_measure_int_peak); IMAD.HI measured at half that rate so it "
                                  "counts 2 slots (slots_per_polymul in bench.py)",
-                         "arith": "plantard" if plantard else "shoup"},
+                         "arith": ("plantard-signed" if W.signed else "plantard") if plantard else "shoup"},
         "parity_ok": parity_ok, "parity_rows_checked": parity_rows, "parity_checker": parity_checker,
         "two_streams": two,
         "standalone_ntt": ntt_lines,

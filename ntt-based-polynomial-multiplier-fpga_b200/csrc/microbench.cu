@@ -117,6 +117,48 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *sink, uint32_t 
           const int xn = (int)x[i] + (u >> 16);
           y[i] = 2u * x[i] - (uint32_t)xn;
           x[i] = (uint32_t)xn;
+        } else if (WHICH == 18 || (WHICH == 19 && (i & 1)) || (WHICH == 23 && (i % 3) == 0)) {
+          /* 14 with the second leg on the MULTIPLIER pipe: Y' = 2 X - X' as IMAD (X, 2, -X'), so that the
+           * butterfly is 3 multiplier-pipe + 2 ALU instructions (14: 2 + 3); 19 alternates the two forms
+           * (2.5 + 2.5: both pipes level), 23 uses this form in one butterfly of three */
+          const int p = (int)(y[i] * a);
+          const int u = (p >> 16) * (int)m.q + (int)b;
+          const int xn = (int)x[i] + (u >> 16);
+          int yn;
+          asm("{ .reg .s32 t; neg.s32 t, %2; mad.lo.s32 %0, %1, 2, t; }" : "=r"(yn) : "r"((int)x[i]), "r"(xn));
+          y[i] = (uint32_t)yn;
+          x[i] = (uint32_t)xn;
+        } else if (WHICH == 19 || WHICH == 23) {
+          const int p = (int)(y[i] * a);
+          const int u = (p >> 16) * (int)m.q + (int)b;
+          const int xn = (int)x[i] + (u >> 16);
+          y[i] = 2u * x[i] - (uint32_t)xn;
+          x[i] = (uint32_t)xn;
+        } else if (WHICH == 20) {
+          /* signed half-word Gentleman-Sande butterfly: IADD, IADD, IMAD, SHF, IMAD, SHF */
+          const int d = (int)x[i] - (int)y[i];
+          x[i] = x[i] + y[i];
+          const int p = (int)((uint32_t)d * a);
+          const int u = (p >> 16) * (int)m.q + (int)b;
+          y[i] = (uint32_t)(u >> 16);
+        } else if (WHICH == 21) {
+          /* 20 with the sum on the multiplier pipe (IMAD X, 1, Y): 3 + 3 */
+          const int d = (int)x[i] - (int)y[i];
+          int s;
+          asm("mad.lo.s32 %0, %1, 1, %2;" : "=r"(s) : "r"((int)x[i]), "r"((int)y[i]));
+          x[i] = (uint32_t)s;
+          const int p = (int)((uint32_t)d * a);
+          const int u = (p >> 16) * (int)m.q + (int)b;
+          y[i] = (uint32_t)(u >> 16);
+        } else if (WHICH == 22) {
+          /* Gentleman-Sande on a product leg whose last shift is still pending (y holds u, the value is
+           * u >> 16): S = X + (u >> 16) is LEA.HI.SX32, D = 2 X - S; then the product of D, left pending
+           * again: LEA.HI, IADD3, IMAD, SHF, IMAD = 5 */
+          const int s = (int)x[i] + ((int)y[i] >> 16);
+          const int d = 2 * (int)x[i] - s;
+          x[i] = (uint32_t)s;
+          const int p = (int)((uint32_t)d * a);
+          y[i] = (uint32_t)((p >> 16) * (int)m.q + (int)b);
         } else if (WHICH == 15) {
           /* LEA.HI.SX32 alone: x += y >> 16 */
           x[i] = (uint32_t)((int)x[i] + ((int)y[i] >> 16));
@@ -184,6 +226,12 @@ extern "C" int nttb200_measure_int_peak(int which, double *lane_ops_per_s) {
     case 15: return run<15>(1, lane_ops_per_s); /* LEA.HI.SX32                                     */
     case 16: return run<16>(1, lane_ops_per_s); /* signed Plantard butterflies / s: IMAD, IMAD.HI, LEA.HI.SX32, IADD3 */
     case 17: return run<17>(1, lane_ops_per_s); /* 14 and 16 alternating                           */
+    case 18: return run<18>(1, lane_ops_per_s); /* 14 with Y' = 2X - X' as an IMAD (3 multiplier + 2 ALU)         */
+    case 19: return run<19>(1, lane_ops_per_s); /* 14 and 18 alternating (2.5 + 2.5)                              */
+    case 20: return run<20>(1, lane_ops_per_s); /* signed half-word GS butterfly, 6 instructions                  */
+    case 21: return run<21>(1, lane_ops_per_s); /* 20 with the sum as an IMAD (3 + 3)                             */
+    case 22: return run<22>(1, lane_ops_per_s); /* signed GS with the product's last shift left pending, 5        */
+    case 23: return run<23>(1, lane_ops_per_s); /* 14, 14, 18 in turn                                             */
     default: return nttb200_fail(NTTB200_EPARAM, "unknown microbenchmark %d", which);
   }
 }

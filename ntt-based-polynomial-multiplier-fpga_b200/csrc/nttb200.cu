@@ -97,12 +97,23 @@ static int upload_table(DevTable &t, const std::vector<uint32_t> &w, uint32_t q,
     for (size_t i = 0; i < w.size(); i++) t.h2[i] = nttb200_plant_form_centred(w[i], q, plant_qinv);
     NTT_CUDA(cudaMalloc(&t.d2, t.h2.size() * sizeof(uint32_t)));
     NTT_CUDA(cudaMemcpy(t.d2, t.h2.data(), t.h2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    const size_t half = w.size() / 2;
+    t.h3.resize(half ? half : 1);
+    for (size_t j = 0; j < half; j++) {
+      const uint64_t z = (uint64_t)(w[half + j] % q) * (w[half + j] % q) % q;
+      const uint64_t Z = (q - (z << 32) % q) % q;
+      t.h3[j] = Z > q / 2 ? (uint32_t)Z - q : (uint32_t)Z;
+    }
+    NTT_CUDA(cudaMalloc(&t.d3, t.h3.size() * sizeof(uint32_t)));
+    NTT_CUDA(cudaMemcpy(t.d3, t.h3.data(), t.h3.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
   }
   return 0;
 }
 static void free_table(DevTable &t) {
   if (t.d2) cudaFree(t.d2);
   t.d2 = nullptr;
+  if (t.d3) cudaFree(t.d3);
+  t.d3 = nullptr;
   if (t.d) cudaFree(t.d);
   if (t.d1) cudaFree(t.d1);
   t.d = nullptr;
@@ -202,7 +213,7 @@ extern "C" int nttb200_plan_create(nttb200_plan **out, uint32_t n, uint32_t q, u
   snprintf(P->desc, sizeof P->desc, "n=%u q=%u %s=%u kernel=%s arith=%s%s device=%d sms=%d", n, q,
            cyclic ? "omega" : "psi", cyclic ? omega : psi,
            P->kernel == PK_SMALL ? "fused-small(regs+smem)" : "large(multi-pass)", an[P->arith],
-           P->plant ? "+plantard(product)" : "", dev, P->sm_count);
+           P->plant ? (small_plant_signed(P) ? "+plantard-signed(product)" : "+plantard(product)") : "", dev, P->sm_count);
   *out = P;
   return 0;
 }

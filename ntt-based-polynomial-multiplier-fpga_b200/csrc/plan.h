@@ -19,6 +19,9 @@ struct DevTable {
   std::vector<uint32_t> h1;
   uint32_t *d2 = nullptr;        /* device: Plantard form with W centred (signed kernel, ntt_small_splant.cuh) */
   std::vector<uint32_t> h2;
+  uint32_t *d3 = nullptr;        /* device: n/2 entries -(w^2) 2^32 mod q, centred, w = entry n/2 + j: the pair
+                                    multiplication of the incomplete transform (ntt_small_splant.cuh)          */
+  std::vector<uint32_t> h3;
 };
 
 /* Plantard form of a constant: ((-w 2^32) mod q) * q^-1 mod 2^32  (ntt_small_plant.cuh) */
@@ -145,6 +148,7 @@ int small_kernel_info(const nttb200_plan *P, int *regs, int *smem_bytes, int *bl
 int launch_polymul_small_plant(const nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b,
                                size_t batch, cudaStream_t st);
 int small_kernel_info_plant(const nttb200_plan *P, int *regs, int *smem_bytes, int *blocks_per_sm);
+int small_plant_signed(const nttb200_plan *P);      /* 1: products run polymul_splant_kernel (NTTB200_PLANT_SIGNED) */
 int launch_ntt_small_plant(const nttb200_plan *P, const DevTable &tab, int dir, int scale, uint32_t *a,
                            size_t batch, cudaStream_t st);
 int launch_polymul_small_plant_u16(const nttb200_plan *P, uint16_t *c, const uint16_t *a, const uint16_t *b,

@@ -14,8 +14,14 @@ using namespace nttb200;
 #ifndef PLANT_WARPS
 #define PLANT_WARPS 8
 #endif
+#ifndef PLANT_BIG_WARPS
+#define PLANT_BIG_WARPS 4      /* warps per CTA at n >= 512 (tuning knob; with 12, PLANT_BIG_CTAS 1) */
+#endif
+#ifndef PLANT_BIG_CTAS
+#define PLANT_BIG_CTAS 2
+#endif
 template <int L> struct PlantCfg {
-  static constexpr int WARPS = (L >= 9) ? 4 : PLANT_WARPS;
+  static constexpr int WARPS = (L >= 9) ? PLANT_BIG_WARPS : PLANT_WARPS;
   static constexpr bool TWREG = (L <= 8);
 };
 /* resident CTAs per SM the kernel is compiled for (register cap).  Measured on B200 (c2:
@@ -126,29 +132,32 @@ int run_plant(const nttb200_plan *P, void *c, const void *a, const void *b, size
   return 0;
 }
 
-/* NTTB200_PLANT_SIGNED=1 runs the signed five-instruction-butterfly kernel of ntt_small_splant.cuh for
- * n <= 256.  Measured on B200: 5 % fewer instructions per tile and +1.6 % at batch
- * 2^16 for a few milliseconds (1 362 vs 1 340 M polymul/s), but both kernels run into the 1000 W
- * power cap when the load lasts a second, and the signed one, with more of its work on the
- * multiplier pipe, is clocked lower there (1 890 vs 1 965 MHz: 1 321 vs 1 334 M sustained).  The
- * unsigned kernel therefore stays the default; read per call so that the tests cover both. */
-int plant_signed() {
+/* Which of the two Plantard kernels serves a product.  The signed kernel of ntt_small_splant.cuh
+ * (five-instruction butterflies levelled over the two integer pipes, incomplete transform with a pair
+ * multiplication) is the default at every size: measured on B200 c2 1 340 -> 1 473,
+ * c3 1 407 -> 1 484, c4 263 -> 273 M polymul/s, and 1 325 -> 1 392 M at c2 when the load lasts a second
+ * and the chip runs into its power cap.  NTTB200_PLANT_SIGNED=0 brings the unsigned kernel of
+ * ntt_small_plant.cuh back (2: signed for n >= 512 only, 3: for n <= 256 only); read per call so that
+ * the tests cover both. */
+int plant_signed(int logn) {
   const char *e = getenv("NTTB200_PLANT_SIGNED");
-  return e ? atoi(e) != 0 : 0;
+  const int v = e ? atoi(e) : 1;
+  return v == 1 || (v == 2 && logn >= 9) || (v == 3 && logn <= 8);
 }
 
-/* the signed kernel, n <= 256 */
+/* the signed kernel */
 template <int L, typename IO = uint32_t, typename OIO = IO>
 int run_splant(const nttb200_plan *P, void *c, const void *a, const void *b, size_t batch, cudaStream_t st) {
   using Gm = SmallGeom<L>;
   using Pg = PlantGeom<L, IO>;
-  constexpr int WARPS = PLANT_WARPS;
+  using Cfg = PlantCfg<L>;
+  constexpr int WARPS = Cfg::WARPS;
   const bool cyclic = (P->flags & NTTB200_PLAN_CYCLIC) != 0;
   const DevTable &fwd = cyclic ? P->fwd_plain : P->fwd_mixed;
   const DevTable &inv = cyclic ? P->inv_plain : P->inv_mixed;
   SPlantParams<Gm::R> p{};
   p.a = a; p.b = b; p.c = c; p.batch = batch;
-  p.tw_fwd = fwd.d2; p.tw_inv = inv.d2;
+  p.tw_fwd = fwd.d2; p.tw_inv = inv.d2; p.zeta = fwd.d3;
   const uint32_t q = P->q;
   p.q = q; p.qinv = P->m.qinv;
   /* |Y W| <= mmax is what the second product tolerates (ntt_small_splant.cuh); the kernel multiplies
@@ -157,15 +166,17 @@ int run_splant(const nttb200_plan *P, void *c, const void *a, const void *b, siz
   if (8ull * q * q > mmax) return nttb200_fail(NTTB200_EPARAM, "q=%u is too large for the signed Plantard kernel", q);
   p.dd = (uint32_t)((mmax + 65535ull * q + 65535ull) / 65536ull);
   p.cbar = (uint32_t)(((1ull << SP_RED_SHIFT) + q / 2) / q);
-  /* -n^-1 2^32: cancels the -2^-32 of the Plantard pointwise product */
-  const uint64_t fs = (q - (uint64_t)P->n_inv * ((1ull << 32) % q) % q) % q;
+  /* -n^-1 2^32: cancels the -2^-32 of the Plantard pointwise product; (n/2)^-1 when the inverse
+   * network runs without its first stage (SPLANT_INCOMPLETE) */
+  const uint64_t ninv = (uint64_t)P->n_inv * (SP_DROP && Gm::H > 0 ? 2 : 1) % q;
+  const uint64_t fs = (q - ninv * ((1ull << 32) % q) % q) % q;
   p.last_x = nttb200_plant_form_centred((uint32_t)fs, q, p.qinv);
   p.last_y = nttb200_plant_form_centred((uint32_t)(fs * inv.h[1].x % q), q, p.qinv);
   for (int i = 0; i < (1 << Gm::R); i++) {
     p.ufwd[i] = (size_t)i < fwd.h2.size() ? fwd.h2[i] : 0;
     p.uinv[i] = (size_t)i < inv.h2.size() ? inv.h2[i] : 0;
   }
-  auto kernel = polymul_splant_kernel<L, WARPS, 2, IO, OIO>;
+  auto kernel = polymul_splant_kernel<L, WARPS, (L >= 9) ? PLANT_BIG_CTAS : 2, Cfg::TWREG, IO, OIO>;
   const int smem = WARPS * Pg::WARP_WORDS * (int)sizeof(uint32_t);
   static int per_sm_dev[64] = {0};
   int &per_sm = per_sm_dev[P->device & 63];
@@ -179,10 +190,20 @@ int run_splant(const nttb200_plan *P, void *c, const void *a, const void *b, siz
   const unsigned long long tiles = (batch + Gm::PPW - 1) / Gm::PPW;
   const unsigned long long want = (tiles + WARPS - 1) / WARPS;
   static const int gridx_env = [] { const char *e = getenv("NTTB200_PLANT_GRIDX"); int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 64 ? 64 : v); }();
-  unsigned long long gridx = gridx_env > 0 ? (unsigned long long)gridx_env
-      : std::min<unsigned long long>(4, std::max<unsigned long long>(1, tiles / ((unsigned long long)P->sm_count * per_sm * WARPS * 6)));
+  unsigned long long gridx = 1;
+  if (gridx_env > 0) gridx = (unsigned long long)gridx_env;
+  else if (L < PLANT_DYN_MINL)
+    gridx = std::min<unsigned long long>(4, std::max<unsigned long long>(1, tiles / ((unsigned long long)P->sm_count * per_sm * WARPS * 6)));
   const unsigned long long cap = (unsigned long long)P->sm_count * per_sm * gridx;
   const int grid = (int)(want < cap ? (want ? want : 1) : cap);
+  /* tail scheduler, as run_plant */
+  const unsigned long long warps = (unsigned long long)grid * WARPS;
+  p.sched = nullptr;
+  if (L >= PLANT_DYN_MINL && P->sched_ring && plant_dyn_pct() > 0 && tiles > 4 * warps) {
+    const unsigned long long stat = tiles * (100 - plant_dyn_pct()) / 100 / warps;
+    p.static_rounds = (uint32_t)std::min<unsigned long long>(std::max<unsigned long long>(stat, 2), 0x7fffffffull);
+    p.sched = P->sched_ring + 2 * (size_t)(P->sched_seq.fetch_add(1) % NTTB200_SCHED_SLOTS);
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(WARPS * 32);
@@ -201,6 +222,20 @@ int run_splant(const nttb200_plan *P, void *c, const void *a, const void *b, siz
   return 0;
 }
 
+template <int L>
+int info_splant(int *regs, int *smem_bytes, int *blocks_per_sm) {
+  using Pg = PlantGeom<L>;
+  using Cfg = PlantCfg<L>;
+  auto kernel = polymul_splant_kernel<L, Cfg::WARPS, (L >= 9) ? PLANT_BIG_CTAS : 2, Cfg::TWREG>;
+  cudaFuncAttributes at;
+  NTT_CUDA(cudaFuncGetAttributes(&at, kernel));
+  const int smem = Cfg::WARPS * Pg::WARP_WORDS * (int)sizeof(uint32_t);
+  NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int per_sm = 0;
+  NTT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, Cfg::WARPS * 32, smem));
+  *regs = at.numRegs; *smem_bytes = smem; *blocks_per_sm = per_sm;
+  return 0;
+}
 template <int L, int MINB>
 int info_plant(int *regs, int *smem_bytes, int *blocks_per_sm) {
   using Pg = PlantGeom<L>;
@@ -238,26 +273,28 @@ int info_plant(int *regs, int *smem_bytes, int *blocks_per_sm) {
     case 6: { constexpr int L = 6; expr_of_L; }      \
     case 7: { constexpr int L = 7; expr_of_L; }      \
     case 8: { constexpr int L = 8; expr_of_L; }      \
+    case 9: { constexpr int L = 9; expr_of_L; }      \
+    case 10: { constexpr int L = 10; expr_of_L; }    \
     default: break;                                  \
   }
 
 int launch_polymul_small_plant(const nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b,
                                size_t batch, cudaStream_t st) {
-  if (plant_signed() && P->logn <= 8) { SPLANT_SWITCH(return (run_splant<L>(P, c, a, b, batch, st))) }
+  if (plant_signed(P->logn)) { SPLANT_SWITCH(return (run_splant<L>(P, c, a, b, batch, st))) }
   if (plant_minb(P->logn) == 2) { PLANT_SWITCH(return (run_plant<L, 2>(P, c, a, b, batch, st))) }
   PLANT_SWITCH(return (run_plant<L, 3>(P, c, a, b, batch, st)))
 }
 /* packed 16-bit operands and result (extension outside the reference API) */
 int launch_polymul_small_plant_u16(const nttb200_plan *P, uint16_t *c, const uint16_t *a, const uint16_t *b,
                                    size_t batch, cudaStream_t st) {
-  if (plant_signed() && P->logn <= 8) { SPLANT_SWITCH(return (run_splant<L, uint16_t>(P, c, a, b, batch, st))) }
+  if (plant_signed(P->logn)) { SPLANT_SWITCH(return (run_splant<L, uint16_t>(P, c, a, b, batch, st))) }
   PLANT_SWITCH(return (run_plant<L, 2, uint16_t>(P, c, a, b, batch, st)))
 }
 /* 16-bit operands, 32-bit result: the wire pipeline of the host-buffer call narrows a and b on
  * the host and lets the kernel write the caller's int32 rows (nttb200.cu, polymul_batch_wire) */
 int launch_polymul_small_plant_u16in(const nttb200_plan *P, uint32_t *c, const uint16_t *a, const uint16_t *b,
                                      size_t batch, cudaStream_t st) {
-  if (plant_signed() && P->logn <= 8) { SPLANT_SWITCH(return (run_splant<L, uint16_t, uint32_t>(P, c, a, b, batch, st))) }
+  if (plant_signed(P->logn)) { SPLANT_SWITCH(return (run_splant<L, uint16_t, uint32_t>(P, c, a, b, batch, st))) }
   PLANT_SWITCH(return (run_plant<L, 2, uint16_t, uint32_t>(P, c, a, b, batch, st)))
 }
 template <int L, int DIR>
@@ -316,7 +353,10 @@ int launch_ntt_small_plant(const nttb200_plan *P, const DevTable &tab, int dir, 
   PLANT_SWITCH(return (run_ntt_plant<L, 1>(P, tab, scale, a, batch, st)))
 }
 
+int small_plant_signed(const nttb200_plan *P) { return plant_signed((int)P->logn); }
+
 int small_kernel_info_plant(const nttb200_plan *P, int *regs, int *smem_bytes, int *blocks_per_sm) {
+  if (plant_signed(P->logn)) { SPLANT_SWITCH(return (info_splant<L>(regs, smem_bytes, blocks_per_sm))) }
   if (plant_minb(P->logn) == 2) { PLANT_SWITCH(return (info_plant<L, 2>(regs, smem_bytes, blocks_per_sm))) }
   PLANT_SWITCH(return (info_plant<L, 3>(regs, smem_bytes, blocks_per_sm)))
 }

@@ -13,7 +13,13 @@ NAMES = {0: "IMAD", 1: "IMAD.HI", 2: "IADD", 12: "SHF + IADD pairs (x2)", 15: "L
          11: "Plantard half word, 6 instructions (IMAD, SHF, IMAD, SHF, 2 IADD)",
          14: "signed Plantard half word, 5 instructions (IMAD, SHF, IMAD, LEA.HI.SX32, IADD3)",
          16: "signed Plantard full word, 4 instructions (IMAD, IMAD.HI, LEA.HI.SX32, IADD3)",
-         17: "14 and 16 alternating"}
+         17: "14 and 16 alternating",
+         18: "14 with the second leg as mad.lo (X, 2, -X'): ptxas levels IMAD / LEA over the two pipes",
+         19: "14 and 18 alternating",
+         23: "14, 14, 18 in turn",
+         20: "signed Plantard half word, Gentleman-Sande, 6 instructions (2 IADD, IMAD, SHF, IMAD, SHF)",
+         21: "20 with the sum as mad.lo (X, 1, Y)",
+         22: "signed Gentleman-Sande, last shift of the product left pending (LEA.HI.SX32, IADD3, IMAD, SHF, IMAD)"}
 sms, clk = 148, 1.965e9
 for k, name in NAMES.items():
     r = m.measure_int_peak(k)

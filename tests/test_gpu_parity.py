@@ -1060,7 +1060,7 @@ def test_small_product_right_after_a_large_n_product_on_the_same_stream(gpu, ora
     """A large-n product (its last kernel triggers its dependents early) followed at once by an
     n = 256 product that reads its result viewed as rows of 256: the second one must wait."""
     import torch
-    nl, q = 4096, 12289
+    nl, q = 2048, 12289                                  # 2 nl = 4096 divides q - 1 = 2^12 3
     pl, ps = gpu.Plan(nl, q), gpu.Plan(256, q)
     st = torch.cuda.current_stream().cuda_stream
     a, b = nttb200.inputs.survey_batch(nl, q, 48, 4, device="cuda")
