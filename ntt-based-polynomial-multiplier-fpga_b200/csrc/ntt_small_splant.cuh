@@ -56,7 +56,7 @@ struct SPlantParams {
   void *c;
   const uint32_t *tw_fwd;    /* device level table of centred w~, n entries */
   const uint32_t *tw_inv;
-  const uint32_t *zeta;      /* n/2 entries: -(w^2) 2^32 mod q, centred, w = tw_fwd level n/2 (SPLANT_INCOMPLETE) */
+  const uint32_t *zeta;      /* n / 2^V entries: -(w^2) 2^32 mod q, centred, w = forward table entry n / 2^V + j */
   unsigned long long batch;
   uint32_t q, qinv;
   uint32_t dd;               /* D: addend of the second product                             */
@@ -180,33 +180,40 @@ __host__ __device__ constexpr int sp_phase_out_mixed(int bits, int b_in, int fir
   return worst;
 }
 
-/* ---- incomplete transform (SPLANT_INCOMPLETE, the default) ---------------------------------------
- * The last forward stage, the pointwise product and the first inverse stage are replaced by one
- * multiplication of degree-1 polynomials per register pair: before its last stage the Cooley-Tukey
- * network holds a0 + a1 x in Z_q[x]/(x^2 - w^2) in the pair (2j, 2j+1) (the last butterfly would
- * evaluate it at +-w), so
- *        c0 = a0 b0 + w^2 a1 b1,      c1 = a0 b1 + a1 b0
- * is the pair the inverse network holds after ITS first stage, up to the factor 2 that stage would
- * have contributed (the last stage scales by (n/2)^-1 instead of n^-1).  Same ring, same canonical
+/* ---- incomplete transform (SPLANT_INCOMPLETE = number of stages left out, default 2) -------------
+ * The last D forward stages, the pointwise product and the first D inverse stages are replaced by one
+ * multiplication of polynomials of degree 2^D - 1 per group of 2^D registers: before its last D stages
+ * the Cooley-Tukey network holds a_0 + a_1 x + ... in Z_q[x]/(x^(2^D) - w^2) in the group at positions
+ * 2^D j .. 2^D j + 2^D - 1, w being the twiddle of the group's next butterflies (table entry
+ * n / 2^D + j): the remaining stages would only evaluate it at the 2^D roots.  So
+ *        c_k = sum_{i+j=k} a_i b_j  +  w^2 sum_{i+j=k+2^D} a_i b_j
+ * is what the inverse network holds after ITS first D stages, up to the factor 2^D those stages would
+ * have contributed (the last stage scales by (n / 2^D)^-1 instead of n^-1).  Same ring, same canonical
  * result.  Raw 32-bit products are added BEFORE they are reduced:
- *        a0, a1 <- Barrett step (|.| <= q/2 + 20)                       3 + 3
- *        c1 = redc(a0 b1 + a1 b0)                                       2 + 4
- *        m  = redc(a1 b1)                 (= -a1 b1 2^-32, centred)     1 + 4
- *        c0 = redc(a0 b0 + m Z)           Z = -(w^2) 2^32 mod q centred 2 + 4
- * 23 instructions per pair against 2 x 5 (butterflies of a and b) + 2 x 8 (pointwise) + 6 (inverse
- * butterfly) = 32, and the lane phase keeps half as many twiddles.  redc(x) = ((x q^-1 >> 16) q + D)
- * >> 16 = -x 2^-32 mod q for |x| <= M (header); here |b| <= (L + 1) q / 2, so |a0 b1 + a1 b0| <=
- * (L + 1)(q/2 + 20) q <= 5.6 q^2 < M = 11.5 q^2 at n = 1024. */
+ *        a_i <- Barrett step (|.| <= q/2 + 20)                                  3 each
+ *        h_k = redc(sum_{i+j=k+2^D} a_i b_j)   (= -(...) 2^-32, centred)        products + 4
+ *        c_k = redc(sum_{i+j=k} a_i b_j + h_k Z), Z = -(w^2) 2^32 mod q centred products + 1 + 4
+ * D = 1: 23 instructions per pair against 2 x 5 (butterflies of a and b) + 2 x 8 (pointwise) + 6
+ * (inverse butterfly) = 32; D = 2: 59 per group of four against 2 x 23 + 20 + 12 = 78 (measured: c2
+ * 1 371 -> 1 473 M polymul/s with D = 1); and the lane phase keeps a half / a quarter of the twiddles.
+ * D = 3 does not fit: redc(x) = ((x q^-1 >> 16) q + D) >> 16 needs |x| <= M = 11.5 q^2 (header), and
+ * with |b| <= (L + 2 - D) q / 2 a sum of 2^D products reaches 2^D (q/2 + 20)(L + 2 - D) q / 2 + q^2 / 4
+ * = 10.3 q^2 at n = 1024, D = 2 (run_splant checks it), 14 q^2 at D = 3. */
 #ifndef SPLANT_INCOMPLETE
-#define SPLANT_INCOMPLETE 1
+#define SPLANT_INCOMPLETE 2
 #endif
-constexpr int SP_DROP = SPLANT_INCOMPLETE ? 1 : 0;
+template <int L>
+struct SpDrop {
+  static constexpr int H = SmallGeom<L>::H;
+  static constexpr int V = SPLANT_INCOMPLETE < H ? SPLANT_INCOMPLETE : H;    /* stages left out */
+  static constexpr int D = 1 << V;                                           /* registers per group */
+};
 
-/* per-lane twiddles of the lane phase, levels 0 .. H-1-SP_DROP (LaneTw1 holds all H levels) */
+/* per-lane twiddles of the lane phase, levels 0 .. H-1-V (LaneTw1 holds all H levels) */
 template <int L>
 struct LaneTwS {
   using Gm = SmallGeom<L>;
-  static constexpr int LV = Gm::H - SP_DROP;
+  static constexpr int LV = Gm::H - SpDrop<L>::V;
   static constexpr int PER_ROW = (1 << LV) - 1;
   uint32_t w[(1 << Gm::G) * (PER_ROW > 0 ? PER_ROW : 1)];
   __device__ __forceinline__ void load(const uint32_t *tab, int l) {
@@ -239,12 +246,12 @@ struct LaneTwS {
     return w[g * PER_ROW + ((1 << m) - 1) + u];
   }
 };
-/* per-lane Z of the pair multiplication: 2^(H-1) per row, laid out like the last table level */
+/* per-lane Z of the group multiplication: 2^(H-V) per row, laid out like table level R + H - V */
 template <int L>
 struct LaneZeta {
   using Gm = SmallGeom<L>;
-  static constexpr int M = Gm::H - 1;
-  static constexpr int ZPR = 1 << (M > 0 ? M : 0);
+  static constexpr int M = Gm::H - SpDrop<L>::V;
+  static constexpr int ZPR = 1 << M;
   int z[(1 << Gm::G) * ZPR];
   __device__ __forceinline__ void load(const uint32_t *tab, int l) {
 #pragma unroll
@@ -279,25 +286,36 @@ __device__ __forceinline__ int sp_redc_u(int x, const SpRegs &G) {
   return (p >> 16) * G.q + G.dd;
 }
 __device__ __forceinline__ int sp_redc(int x, const SpRegs &G) { return sp_redc_u(x, G) >> 16; }
-/* the pair multiplication, lane-phase layout: pairs are registers (r, r + 1), r even */
+/* the group multiplication, lane-phase layout: group = registers r .. r + 2^V - 1, r a multiple of 2^V */
 template <int L>
-__device__ __forceinline__ void sp_pairmul(uint32_t (&xa)[SmallGeom<L>::NV], const uint32_t (&xb)[SmallGeom<L>::NV],
-                                           const LaneZeta<L> &zt, const SpRegs &G) {
+__device__ __forceinline__ void sp_groupmul(uint32_t (&xa)[SmallGeom<L>::NV], const uint32_t (&xb)[SmallGeom<L>::NV],
+                                            const LaneZeta<L> &zt, const SpRegs &G) {
   using Gm = SmallGeom<L>;
-  static_assert(Gm::H >= 1, "pairs live in the lane-phase layout");
+  constexpr int V = SpDrop<L>::V, D = SpDrop<L>::D;
+  static_assert(Gm::H >= 1 && V >= 1, "groups live in the lane-phase layout");
 #pragma unroll
-  for (int r = 0; r < Gm::NV; r += 2) {
-    const uint32_t a0 = (uint32_t)sp_red((int)xa[r], G), a1 = (uint32_t)sp_red((int)xa[r + 1], G);
-    const uint32_t b0 = xb[r], b1 = xb[r + 1];
-    const int zeta = zt.get(r >> Gm::H, (r & (Gm::T - 1)) >> 1);
-    const uint32_t m = (uint32_t)sp_redc((int)(a1 * b1), G);
-    const uint32_t c1 = a0 * b1 + a1 * b0;
-    const uint32_t c0 = a0 * b0 + m * (uint32_t)zeta;
-    xa[r] = (uint32_t)(SPLANT_PENDING ? sp_redc_u((int)c0, G) : sp_redc((int)c0, G));
-    xa[r + 1] = (uint32_t)(SPLANT_PENDING ? sp_redc_u((int)c1, G) : sp_redc((int)c1, G));
+  for (int r = 0; r < Gm::NV; r += D) {
+    uint32_t a[D], lo[D], hi[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) a[i] = (uint32_t)sp_red((int)xa[r + i], G);
+    const uint32_t zeta = (uint32_t)zt.get(r >> Gm::H, (r & (Gm::T - 1)) >> V);
+#pragma unroll
+    for (int k = 0; k < D; k++) { lo[k] = 0; hi[k] = 0; }
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+      for (int j = 0; j < D; j++) {
+        if (i + j < D) lo[i + j] += a[i] * xb[r + j];
+        else hi[i + j - D] += a[i] * xb[r + j];
+      }
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+      uint32_t c = lo[k];
+      if (k < D - 1) c += (uint32_t)sp_redc((int)hi[k], G) * zeta;
+      xa[r + k] = (uint32_t)(SPLANT_PENDING ? sp_redc_u((int)c, G) : sp_redc((int)c, G));
+    }
   }
 }
-
 template <int L>
 __device__ __forceinline__ void sp_fwd_cols(uint32_t (&x)[SmallGeom<L>::NV], const SPlantParams<SmallGeom<L>::R> &P,
                                             const SpRegs &G) {
@@ -316,7 +334,7 @@ template <int L>
 __device__ __forceinline__ void sp_fwd_rows(uint32_t (&x)[SmallGeom<L>::NV], const LaneTwS<L> &tw, const SpRegs &G) {
   using Gm = SmallGeom<L>;
 #pragma unroll
-  for (int lv = 0; lv < Gm::H - SP_DROP; lv++) {
+  for (int lv = 0; lv < Gm::H - SpDrop<L>::V; lv++) {
     const int bit = Gm::H - 1 - lv;
 #pragma unroll
     for (int r = 0; r < Gm::NV; r++) {
@@ -326,13 +344,14 @@ __device__ __forceinline__ void sp_fwd_rows(uint32_t (&x)[SmallGeom<L>::NV], con
     }
   }
 }
-/* inverse, layout 2: register bits SP_DROP .. H-1; inputs are products (bound 1), pending when
+/* inverse, layout 2: register bits V .. H-1; inputs are products (bound 1), pending when
  * SPLANT_PENDING; the outputs are values (the products of the last stage are shifted here, and so are
  * the inputs when the phase has no stage at all) */
 template <int L>
 __device__ __forceinline__ void sp_inv_rows(uint32_t (&x)[SmallGeom<L>::NV], const LaneTwS<L> &tw, const SpRegs &G) {
   using Gm = SmallGeom<L>;
   constexpr bool PD = SPLANT_PENDING != 0;
+  constexpr int SP_DROP = SpDrop<L>::V;
 #pragma unroll
   for (int bit = SP_DROP; bit < Gm::H; bit++) {
     const int lv = Gm::H - 1 - bit;
@@ -404,6 +423,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 polymul_splant_kernel(const __grid_constant__ SPlantParams<SmallGeom<L>::R> P) {
   using Gm = SmallGeom<L>;
   using Pg = PlantGeom<L, IO>;
+  constexpr int SP_DROP = SpDrop<L>::V;
   static_assert(TWREG ? L <= 8 : L <= 10, "twiddles of the lane phase live in registers up to n = 256");
   static_assert(L + 2 <= 2 * SP_CAP, "forward values are never reduced");
   static_assert(Gm::H >= 1, "n >= 8: there is a lane phase (the pair multiplication and the pending products rely on it)");
@@ -520,7 +540,7 @@ polymul_splant_kernel(const __grid_constant__ SPlantParams<SmallGeom<L>::R> P) {
      * With SPLANT_INCOMPLETE it is the pair multiplication above (same constant). */
     if (SP_DROP && Gm::H > 0) {
       if (!TWREG) zt.load(P.zeta, l);
-      sp_pairmul<L>(xa, xb, zt, G);
+      sp_groupmul<L>(xa, xb, zt, G);
     } else {
 #pragma unroll
       for (int k = 0; k < Gm::NV; k++) {

@@ -97,10 +97,11 @@ static int upload_table(DevTable &t, const std::vector<uint32_t> &w, uint32_t q,
     for (size_t i = 0; i < w.size(); i++) t.h2[i] = nttb200_plant_form_centred(w[i], q, plant_qinv);
     NTT_CUDA(cudaMalloc(&t.d2, t.h2.size() * sizeof(uint32_t)));
     NTT_CUDA(cudaMemcpy(t.d2, t.h2.data(), t.h2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    const size_t half = w.size() / 2;
-    t.h3.resize(half ? half : 1);
-    for (size_t j = 0; j < half; j++) {
-      const uint64_t z = (uint64_t)(w[half + j] % q) * (w[half + j] % q) % q;
+    /* -(w^2) 2^32 mod q, centred, entry by entry in the table's own layout: the group multiplication of
+     * the incomplete transform reads the level it stops at (ntt_small_splant.cuh) */
+    t.h3.resize(w.size() ? w.size() : 1);
+    for (size_t j = 0; j < w.size(); j++) {
+      const uint64_t z = (uint64_t)(w[j] % q) * (w[j] % q) % q;
       const uint64_t Z = (q - (z << 32) % q) % q;
       t.h3[j] = Z > q / 2 ? (uint32_t)Z - q : (uint32_t)Z;
     }

@@ -19,8 +19,8 @@ struct DevTable {
   std::vector<uint32_t> h1;
   uint32_t *d2 = nullptr;        /* device: Plantard form with W centred (signed kernel, ntt_small_splant.cuh) */
   std::vector<uint32_t> h2;
-  uint32_t *d3 = nullptr;        /* device: n/2 entries -(w^2) 2^32 mod q, centred, w = entry n/2 + j: the pair
-                                    multiplication of the incomplete transform (ntt_small_splant.cuh)          */
+  uint32_t *d3 = nullptr;        /* device: entry by entry -(w^2) 2^32 mod q, centred: the group multiplication
+                                    of the incomplete transform (ntt_small_splant.cuh)                         */
   std::vector<uint32_t> h3;
 };
 

@@ -20,6 +20,9 @@ using namespace nttb200;
 #ifndef PLANT_BIG_CTAS
 #define PLANT_BIG_CTAS 2
 #endif
+#ifndef SPLANT_SMALL_CTAS
+#define SPLANT_SMALL_CTAS 2    /* resident CTAs the signed kernel is compiled for at n <= 256 (register cap) */
+#endif
 template <int L> struct PlantCfg {
   static constexpr int WARPS = (L >= 9) ? PLANT_BIG_WARPS : PLANT_WARPS;
   static constexpr bool TWREG = (L <= 8);
@@ -157,18 +160,23 @@ int run_splant(const nttb200_plan *P, void *c, const void *a, const void *b, siz
   const DevTable &inv = cyclic ? P->inv_plain : P->inv_mixed;
   SPlantParams<Gm::R> p{};
   p.a = a; p.b = b; p.c = c; p.batch = batch;
-  p.tw_fwd = fwd.d2; p.tw_inv = inv.d2; p.zeta = fwd.d3;
+  constexpr int V = SpDrop<L>::V;                   /* stages the transforms leave to the group multiplication */
+  p.tw_fwd = fwd.d2; p.tw_inv = inv.d2; p.zeta = fwd.d3 + (Gm::N >> V);
   const uint32_t q = P->q;
   p.q = q; p.qinv = P->m.qinv;
   /* |Y W| <= mmax is what the second product tolerates (ntt_small_splant.cuh); the kernel multiplies
    * differences up to 16 q by |W| <= q/2 */
   const uint64_t mmax = ((1ull << 32) - 65536ull * (q + 4)) / 2;
   if (8ull * q * q > mmax) return nttb200_fail(NTTB200_EPARAM, "q=%u is too large for the signed Plantard kernel", q);
+  /* the group multiplication reduces sums of 2^V raw products a b with |a| <= q/2 + 20 (Barrett step),
+   * |b| <= (L + 2 - V) q / 2 (forward values after L - V stages), plus one product of two centred values */
+  if (V > 0 && (uint64_t)(1 << V) * (q / 2 + 21) * ((uint64_t)(L + 2 - V) * q / 2 + 1) + (uint64_t)q * q / 4 > mmax)
+    return nttb200_fail(NTTB200_EPARAM, "q=%u is too large for the signed Plantard kernel at n=%u", q, Gm::N);
   p.dd = (uint32_t)((mmax + 65535ull * q + 65535ull) / 65536ull);
   p.cbar = (uint32_t)(((1ull << SP_RED_SHIFT) + q / 2) / q);
-  /* -n^-1 2^32: cancels the -2^-32 of the Plantard pointwise product; (n/2)^-1 when the inverse
-   * network runs without its first stage (SPLANT_INCOMPLETE) */
-  const uint64_t ninv = (uint64_t)P->n_inv * (SP_DROP && Gm::H > 0 ? 2 : 1) % q;
+  /* -n^-1 2^32: cancels the -2^-32 of the Plantard pointwise product; (n / 2^V)^-1 when the inverse
+   * network runs without its first V stages (SPLANT_INCOMPLETE) */
+  const uint64_t ninv = (uint64_t)P->n_inv * (1u << V) % q;
   const uint64_t fs = (q - ninv * ((1ull << 32) % q) % q) % q;
   p.last_x = nttb200_plant_form_centred((uint32_t)fs, q, p.qinv);
   p.last_y = nttb200_plant_form_centred((uint32_t)(fs * inv.h[1].x % q), q, p.qinv);
@@ -176,7 +184,7 @@ int run_splant(const nttb200_plan *P, void *c, const void *a, const void *b, siz
     p.ufwd[i] = (size_t)i < fwd.h2.size() ? fwd.h2[i] : 0;
     p.uinv[i] = (size_t)i < inv.h2.size() ? inv.h2[i] : 0;
   }
-  auto kernel = polymul_splant_kernel<L, WARPS, (L >= 9) ? PLANT_BIG_CTAS : 2, Cfg::TWREG, IO, OIO>;
+  auto kernel = polymul_splant_kernel<L, WARPS, (L >= 9) ? PLANT_BIG_CTAS : SPLANT_SMALL_CTAS, Cfg::TWREG, IO, OIO>;
   const int smem = WARPS * Pg::WARP_WORDS * (int)sizeof(uint32_t);
   static int per_sm_dev[64] = {0};
   int &per_sm = per_sm_dev[P->device & 63];
@@ -226,7 +234,7 @@ template <int L>
 int info_splant(int *regs, int *smem_bytes, int *blocks_per_sm) {
   using Pg = PlantGeom<L>;
   using Cfg = PlantCfg<L>;
-  auto kernel = polymul_splant_kernel<L, Cfg::WARPS, (L >= 9) ? PLANT_BIG_CTAS : 2, Cfg::TWREG>;
+  auto kernel = polymul_splant_kernel<L, Cfg::WARPS, (L >= 9) ? PLANT_BIG_CTAS : SPLANT_SMALL_CTAS, Cfg::TWREG>;
   cudaFuncAttributes at;
   NTT_CUDA(cudaFuncGetAttributes(&at, kernel));
   const int smem = Cfg::WARPS * Pg::WARP_WORDS * (int)sizeof(uint32_t);
