@@ -1,0 +1,235 @@
+/*
+ * ntt_splant_n1024.cuh -- fused product kernel for n = 1024, half-word moduli: the arithmetic of
+ * ntt_small_splant.cuh (signed Plantard, five-instruction butterflies, two stages left to a group
+ * multiplication) in a geometry whose code FITS THE INSTRUCTION CACHE.
+ *
+ * Why: one warp per polynomial with 32 coefficients per lane (polymul_splant_kernel<10>) unrolls to
+ * 3 036 instructions per tile = 48 KB, the SM's instruction cache holds 32 KB, and twelve resident warps
+ * run through the loop each at its own place: ncu shows `no_instruction` as the top stall (1.45 warps per
+ * issue cycle, issue slots 69 % busy against 82 % for the 20 KB loop of n = 256;
+ * profiles/r2_c4_splant_ncu_full.txt).
+ *
+ * Geometry: still one warp per polynomial, but 16 registers per "virtual lane" and 64 virtual lanes: the
+ * warp runs every phase twice (a rolled loop over the two halves of the virtual lanes, same code) and the
+ * two operands of the forward transform through ONE copy of the code (a rolled loop over a, b).  With 4
+ * index bits in registers per layout it takes three layouts of the 10 index bits i9 .. i0:
+ *
+ *      layout A   registers i9 i8 i7 i6   half i5          lane i4 .. i0        stages on bits 9 .. 6
+ *      layout B   registers i5 i4 i3 i2   half i1          lane i9 .. i6, i0    stages on bits 5 .. 2
+ *      layout C   registers i3 i2 i1 i0   half i9          lane i8 .. i4        group multiplication
+ *
+ * (forward A -> B -> C, inverse C -> B -> A; dataflow of R/NTT/ntt.C:342-371 and 428-451 as in
+ * ntt_small_splant.cuh).  The polynomial lives in the warp's shared memory between the phases, every
+ * phase reads the 16 words it owns and writes the same 16 words back, so the only synchronisation is
+ * __syncwarp between phases.  Word i sits at  i + (i >> 5)  (one word of padding per 32): every access of
+ * every layout is then conflict-free (A: 32 consecutive words; B: bank = 2 (i9 i8 i7 i6) + i0 + const;
+ * C: bank = 16 i4 + 2 (i8 i7 i6) + i5 + const) and the address of register k is the lane's base plus a
+ * compile-time constant (A: 66 k, B: 4 k + (k >> 3), C: k), so no access costs address arithmetic.  Layout A reads the
+ * operands straight from the cp.async prefetch buffer and writes the result straight to global memory, 128
+ * contiguous bytes per register.  The twiddles of layout A are constant-bank operands (table entries 1 ..
+ * 15), those of layout B depend on i9 .. i6 only, i.e. on the lane and not on the half: 15 + 15 words per
+ * lane held in registers for the whole kernel; the four Z of layout C are one 16-byte load per half.
+ *
+ * Price: five more trips through shared memory per coefficient (14 against 9 scalar-equivalent accesses):
+ * 3 382 instead of 3 087 warp instructions per polynomial (+9.6 %).  The loop is 1 426 instructions =
+ * 23 KB, 80 registers.  Measured on B200 (profiles/r2_c4_splant_n1024_ncu_full.txt): `no_instruction`
+ * drops from 1.45 to 0.11 warps per issue cycle, issue slots 69.5 % -> 83.2 % busy (3.33 instructions per
+ * clock and SM, what the n = 256 kernel reaches), c4 279.5 -> 286 M polymul/s.
+ */
+#pragma once
+#include <stdint.h>
+#include "ntt_small_splant.cuh"
+
+namespace nttb200 {
+
+constexpr int N1024_WK = 1024 + 32;      /* words per padded polynomial */
+
+/* four Cooley-Tukey stages on register bits 3 .. 0 with the lane's twiddles (levels 0 .. 3 of LaneTw1<8>:
+ * level m holds table entries (16 << m) + (row << m) + u, u < 2^m) */
+__device__ __forceinline__ void n1024_fwd_lane(uint32_t (&x)[16], const LaneTw1<8> &tw, const SpRegs &G) {
+#pragma unroll
+  for (int lv = 0; lv < 4; lv++) {
+    const int bit = 3 - lv;
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+      if (r & (1 << bit)) continue;
+      sp_ct(x[r], x[r | (1 << bit)], tw.get(0, lv, r >> (bit + 1)), G, sp_use_mad(pl_ord(r, bit) + lv + 1));
+    }
+  }
+}
+/* four Gentleman-Sande stages on register bits 0 .. 3; inputs are products (bound 1) */
+__device__ __forceinline__ void n1024_inv_lane(uint32_t (&x)[16], const LaneTw1<8> &tw, const SpRegs &G) {
+#pragma unroll
+  for (int bit = 0; bit < 4; bit++) {
+    const int lv = 3 - bit;
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+      if (r & (1 << bit)) continue;
+      const bool red = 2 * sp_leg_bound(r, bit, 1) > SP_CAP;
+      sp_gs_r<false, false>(red, x[r], x[r | (1 << bit)], tw.get(0, lv, r >> (bit + 1)), G);
+    }
+  }
+}
+/* group multiplication of layout C: four groups of four registers, Z of group g in z[g] */
+__device__ __forceinline__ void n1024_groupmul(uint32_t (&xa)[16], const uint32_t (&xb)[16], const int (&z)[4],
+                                               const SpRegs &G) {
+#pragma unroll
+  for (int r = 0; r < 16; r += 4) {
+    uint32_t a[4], lo[4], hi[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) a[i] = (uint32_t)sp_red((int)xa[r + i], G);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { lo[k] = 0; hi[k] = 0; }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (i + j < 4) lo[i + j] += a[i] * xb[r + j];
+        else hi[i + j - 4] += a[i] * xb[r + j];
+      }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint32_t c = lo[k];
+      if (k < 3) c += (uint32_t)sp_redc((int)hi[k], G) * (uint32_t)z[r >> 2];
+      xa[r + k] = (uint32_t)sp_redc((int)c, G);
+    }
+  }
+}
+
+template <int WARPS, int MINB, typename IO = uint32_t, typename OIO = IO>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+polymul_splant_n1024_kernel(const __grid_constant__ SPlantParams<4> P) {
+  constexpr int L = 10, N = 1 << L;
+  using Pg = PlantGeom<L, IO>;
+  static_assert(Pg::PSTRIDE == N && SmallGeom<L>::PPW == 1, "one polynomial per warp, rows unpadded");
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  constexpr int WARP_WORDS = 2 * Pg::PF_WORDS + 2 * N1024_WK;
+  IO *pf_a = reinterpret_cast<IO *>(smem + warp * WARP_WORDS);
+  IO *pf_b = reinterpret_cast<IO *>(smem + warp * WARP_WORDS + Pg::PF_WORDS);
+  uint32_t *wk_a = smem + warp * WARP_WORDS + 2 * Pg::PF_WORDS;
+  uint32_t *wk_b = wk_a + N1024_WK;
+  const IO *ga = static_cast<const IO *>(P.a), *gb = static_cast<const IO *>(P.b);
+  OIO *gc = static_cast<OIO *>(P.c);
+  SpRegs G;
+  G.q = (int)(P.q + P.zero);
+  G.qinv = P.qinv;
+  G.dd = (int)(P.dd + P.zero);
+  G.cbar = (int)P.cbar;
+
+  const unsigned long long ntiles = P.batch;
+  const unsigned long long wstride = (unsigned long long)gridDim.x * WARPS;
+  const bool dyn = P.sched != nullptr;
+  uint32_t rounds_left = dyn ? P.static_rounds : 0xffffffffu;
+  const unsigned long long dyn_base = (unsigned long long)P.static_rounds * wstride;
+  unsigned long long tile = (unsigned long long)blockIdx.x * WARPS + warp;
+  unsigned long long next = tile + wstride;
+  unsigned long long pend = 0;
+  if (dyn) rounds_left -= 2;
+
+  asm volatile("griddepcontrol.launch_dependents;");
+  const bool nowait = P.nowait != 0;
+  if (nowait && tile < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile, P.batch, lane);
+  /* layout B: the lane is (i9 i8 i7 i6, i0) */
+  const int hi4 = lane >> 1, b0 = lane & 1;
+  LaneTw1<8> twf, twi;
+  twf.load(P.tw_fwd, hi4);
+  twi.load(P.tw_inv, hi4);
+  if (!nowait) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tile < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile, P.batch, lane);
+  }
+
+  unsigned long long next2 = 0;
+  for (; tile < ntiles; tile = next, next = next2) {
+    cp_async_wait_all();
+    __syncwarp();
+    /* forward transforms: a, then b, through one copy of the code */
+#pragma unroll 1
+    for (int op = 0; op < 2; op++) {
+      const IO *pf = op ? pf_b : pf_a;
+      uint32_t *wk = op ? wk_b : wk_a;
+#pragma unroll 1
+      for (int half = 0; half < 2; half++) {               /* layout A, stages on bits 9 .. 6 */
+        uint32_t x[16];
+        const int base = (half << 5) | lane;
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = (uint32_t)pf[(k << 6) | base];
+        sp_fwd_cols<8>(x, P, G);
+#pragma unroll
+        for (int k = 0; k < 16; k++) wk[base + half + 66 * k] = x[k];
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int half = 0; half < 2; half++) {               /* layout B, stages on bits 5 .. 2 */
+        uint32_t x[16];
+        const int base = 66 * hi4 + (half << 1) + b0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = wk[base + 4 * k + (k >> 3)];
+        n1024_fwd_lane(x, twf, G);
+#pragma unroll
+        for (int k = 0; k < 16; k++) wk[base + 4 * k + (k >> 3)] = x[k];
+      }
+    }
+    __syncwarp();                                          /* prefetch buffers are free again */
+    if (next < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, next, P.batch, lane);
+    const bool grab = dyn && rounds_left == 0;
+    if (grab) {
+      if (lane == 0) pend = atomicAdd(P.sched, 1ULL);
+    } else {
+      next2 = next + wstride;
+      if (dyn) rounds_left--;
+    }
+
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {                 /* layout C: group multiplication */
+      uint32_t xa[16], xb[16];
+      const int vl = (half << 5) | lane;                   /* i9 .. i4 */
+      const int base = (vl << 4) + (vl >> 1);
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        xa[k] = wk_a[base + k];
+        xb[k] = wk_b[base + k];
+      }
+      const uint4 zv = __ldg(reinterpret_cast<const uint4 *>(P.zeta) + vl);
+      const int z[4] = {(int)zv.x, (int)zv.y, (int)zv.z, (int)zv.w};
+      n1024_groupmul(xa, xb, z, G);
+#pragma unroll
+      for (int k = 0; k < 16; k++) wk_a[base + k] = xa[k];
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {                 /* layout B, inverse stages on bits 2 .. 5 */
+      uint32_t x[16];
+      const int base = 66 * hi4 + (half << 1) + b0;
+#pragma unroll
+      for (int k = 0; k < 16; k++) x[k] = wk_a[base + 4 * k + (k >> 3)];
+      n1024_inv_lane(x, twi, G);
+      /* the register that only ever took sums goes back to the centre (polymul_splant_kernel) */
+      static_assert(sp_phase_out(4, 1) > sp_phase_out_mixed(4, 1), "register 0 is the one above the others");
+      x[0] = (uint32_t)sp_red((int)x[0], G);
+#pragma unroll
+      for (int k = 0; k < 16; k++) wk_a[base + 4 * k + (k >> 3)] = x[k];
+    }
+    __syncwarp();
+    OIO *cp = gc + (tile << L);
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {                 /* layout A, inverse stages on bits 6 .. 9 */
+      uint32_t x[16];
+      const int base = (half << 5) | lane;
+#pragma unroll
+      for (int k = 0; k < 16; k++) x[k] = wk_a[base + half + 66 * k];
+      constexpr int b_in = sp_phase_out_mixed(4, 1) > 2 ? sp_phase_out_mixed(4, 1) : 2;
+      sp_inv_cols<8, b_in>(x, P, G);
+#pragma unroll
+      for (int k = 0; k < 16; k++) cp[(k << 6) | base] = (OIO)x[k];
+    }
+    __syncwarp();                                          /* shared memory reuse by the next tile */
+    if (grab) next2 = dyn_base + __shfl_sync(0xffffffffu, pend, 0);
+  }
+  if (dyn) plant_sched_done(P.sched, lane, wstride);
+  if (nowait) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+}  // namespace nttb200

@@ -6,6 +6,7 @@
 
 #include "ntt_small_plant.cuh"
 #include "ntt_small_splant.cuh"
+#include "ntt_splant_n1024.cuh"
 #include "plan.h"
 
 namespace {
@@ -230,6 +231,85 @@ int run_splant(const nttb200_plan *P, void *c, const void *a, const void *b, siz
   return 0;
 }
 
+/* n = 1024: the three-layout kernel of ntt_splant_n1024.cuh (NTTB200_PLANT_N1024=0 keeps the one-layout-
+ * per-phase kernel polymul_splant_kernel<10>) */
+#ifndef SPLANT_N1024_WARPS
+#define SPLANT_N1024_WARPS 4
+#endif
+#ifndef SPLANT_N1024_CTAS
+#define SPLANT_N1024_CTAS 3
+#endif
+int plant_n1024() {
+  const char *e = getenv("NTTB200_PLANT_N1024");
+  return e ? atoi(e) != 0 : 1;
+}
+template <typename IO = uint32_t, typename OIO = IO>
+int run_splant_n1024(const nttb200_plan *P, void *c, const void *a, const void *b, size_t batch, cudaStream_t st) {
+  constexpr int L = 10, N = 1 << L, V = 2;
+  using Pg = PlantGeom<L, IO>;
+  constexpr int WARPS = SPLANT_N1024_WARPS;
+  const bool cyclic = (P->flags & NTTB200_PLAN_CYCLIC) != 0;
+  const DevTable &fwd = cyclic ? P->fwd_plain : P->fwd_mixed;
+  const DevTable &inv = cyclic ? P->inv_plain : P->inv_mixed;
+  SPlantParams<4> p{};
+  p.a = a; p.b = b; p.c = c; p.batch = batch;
+  p.tw_fwd = fwd.d2; p.tw_inv = inv.d2; p.zeta = fwd.d3 + (N >> V);
+  const uint32_t q = P->q;
+  p.q = q; p.qinv = P->m.qinv;
+  const uint64_t mmax = ((1ull << 32) - 65536ull * (q + 4)) / 2;       /* as run_splant */
+  if (8ull * q * q > mmax ||
+      (uint64_t)(1 << V) * (q / 2 + 21) * ((uint64_t)(L + 2 - V) * q / 2 + 1) + (uint64_t)q * q / 4 > mmax)
+    return nttb200_fail(NTTB200_EPARAM, "q=%u is too large for the signed Plantard kernel at n=%d", q, N);
+  p.dd = (uint32_t)((mmax + 65535ull * q + 65535ull) / 65536ull);
+  p.cbar = (uint32_t)(((1ull << SP_RED_SHIFT) + q / 2) / q);
+  const uint64_t ninv = (uint64_t)P->n_inv * (1u << V) % q;
+  const uint64_t fs = (q - ninv * ((1ull << 32) % q) % q) % q;
+  p.last_x = nttb200_plant_form_centred((uint32_t)fs, q, p.qinv);
+  p.last_y = nttb200_plant_form_centred((uint32_t)(fs * inv.h[1].x % q), q, p.qinv);
+  for (int i = 0; i < 16; i++) {
+    p.ufwd[i] = (size_t)i < fwd.h2.size() ? fwd.h2[i] : 0;
+    p.uinv[i] = (size_t)i < inv.h2.size() ? inv.h2[i] : 0;
+  }
+  auto kernel = polymul_splant_n1024_kernel<WARPS, SPLANT_N1024_CTAS, IO, OIO>;
+  const int smem = WARPS * (2 * Pg::PF_WORDS + 2 * N1024_WK) * (int)sizeof(uint32_t);
+  static int per_sm_dev[64] = {0};
+  int &per_sm = per_sm_dev[P->device & 63];
+  if (!per_sm) {
+    int v = 0;
+    NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    NTT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, WARPS * 32, smem));
+    if (v < 1) return nttb200_fail(NTTB200_ECUDA, "n = 1024 plant kernel does not fit on an SM");
+    per_sm = v;
+  }
+  const unsigned long long tiles = batch;
+  const unsigned long long want = (tiles + WARPS - 1) / WARPS;
+  const unsigned long long cap = (unsigned long long)P->sm_count * per_sm;
+  const int grid = (int)(want < cap ? (want ? want : 1) : cap);
+  const unsigned long long warps = (unsigned long long)grid * WARPS;
+  p.sched = nullptr;
+  if (P->sched_ring && plant_dyn_pct() > 0 && tiles > 4 * warps) {
+    const unsigned long long stat = tiles * (100 - plant_dyn_pct()) / 100 / warps;
+    p.static_rounds = (uint32_t)std::min<unsigned long long>(std::max<unsigned long long>(stat, 2), 0x7fffffffull);
+    p.sched = P->sched_ring + 2 * (size_t)(P->sched_seq.fetch_add(1) % NTTB200_SCHED_SLOTS);
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(WARPS * 32);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = plant_pdl() ? 1 : 0;
+  p.nowait = (plant_pdl() && nttb200_launch_independent(st, a, batch * N * sizeof(IO), b, batch * N * sizeof(IO),
+                                                        c, batch * N * sizeof(OIO))) ? 1u : 0u;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NTT_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+  nttb200_count_launch(1);
+  NTT_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int L>
 int info_splant(int *regs, int *smem_bytes, int *blocks_per_sm) {
   using Pg = PlantGeom<L>;
@@ -288,6 +368,7 @@ int info_plant(int *regs, int *smem_bytes, int *blocks_per_sm) {
 
 int launch_polymul_small_plant(const nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b,
                                size_t batch, cudaStream_t st) {
+  if (plant_signed(P->logn) && P->logn == 10 && plant_n1024()) return run_splant_n1024<>(P, c, a, b, batch, st);
   if (plant_signed(P->logn)) { SPLANT_SWITCH(return (run_splant<L>(P, c, a, b, batch, st))) }
   if (plant_minb(P->logn) == 2) { PLANT_SWITCH(return (run_plant<L, 2>(P, c, a, b, batch, st))) }
   PLANT_SWITCH(return (run_plant<L, 3>(P, c, a, b, batch, st)))
@@ -295,6 +376,7 @@ int launch_polymul_small_plant(const nttb200_plan *P, uint32_t *c, const uint32_
 /* packed 16-bit operands and result (extension outside the reference API) */
 int launch_polymul_small_plant_u16(const nttb200_plan *P, uint16_t *c, const uint16_t *a, const uint16_t *b,
                                    size_t batch, cudaStream_t st) {
+  if (plant_signed(P->logn) && P->logn == 10 && plant_n1024()) return run_splant_n1024<uint16_t>(P, c, a, b, batch, st);
   if (plant_signed(P->logn)) { SPLANT_SWITCH(return (run_splant<L, uint16_t>(P, c, a, b, batch, st))) }
   PLANT_SWITCH(return (run_plant<L, 2, uint16_t>(P, c, a, b, batch, st)))
 }
@@ -302,6 +384,7 @@ int launch_polymul_small_plant_u16(const nttb200_plan *P, uint16_t *c, const uin
  * the host and lets the kernel write the caller's int32 rows (nttb200.cu, polymul_batch_wire) */
 int launch_polymul_small_plant_u16in(const nttb200_plan *P, uint32_t *c, const uint16_t *a, const uint16_t *b,
                                      size_t batch, cudaStream_t st) {
+  if (plant_signed(P->logn) && P->logn == 10 && plant_n1024()) return run_splant_n1024<uint16_t, uint32_t>(P, c, a, b, batch, st);
   if (plant_signed(P->logn)) { SPLANT_SWITCH(return (run_splant<L, uint16_t, uint32_t>(P, c, a, b, batch, st))) }
   PLANT_SWITCH(return (run_plant<L, 2, uint16_t, uint32_t>(P, c, a, b, batch, st)))
 }
