@@ -63,10 +63,15 @@ enum {
 };
 /* programmatic dependent launch: let the next launch of the stream start its CTAs while this grid
  * drains; a launch whose operands may come from its predecessors waits for them before touching
- * memory, an independent one only before it ends (so the stream still completes in order) */
+ * memory, an independent one only before it ends (so the stream still completes in order).
+ * A launch that waits triggers its dependents only AFTER its wait: the host checks a new launch against
+ * the launches since the last one that waited (nttb200_launch_independent), which is only enough if
+ * nothing older can still be running when the new launch starts -- a waiting launch that triggered
+ * first would let its successor run next to ITS predecessors, unchecked (found by
+ * test_random_launch_sequences_on_one_stream_equal_their_sequential_meaning). */
 __device__ __forceinline__ void pdl_begin(uint32_t flags) {
-  asm volatile("griddepcontrol.launch_dependents;");
   if (!(flags & SMALL_FLAG_NOWAIT)) asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");
 }
 __device__ __forceinline__ void pdl_end(uint32_t flags) {
   if (flags & SMALL_FLAG_NOWAIT) asm volatile("griddepcontrol.wait;" ::: "memory");

@@ -481,20 +481,24 @@ polymul_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
   /* programmatic dependent launch: let the next launch on the stream start its CTAs (and
    * their twiddle loads, which depend on nothing) while this grid drains; operands may be the
    * previous kernel's output, so they are only touched after griddepcontrol.wait */
-  asm volatile("griddepcontrol.launch_dependents;");
+  const bool nowait = P.nowait != 0;
+  if (nowait) asm volatile("griddepcontrol.launch_dependents;");
   /* A launch whose operands have nothing to do with the launches still running on the stream (the
    * host compares address ranges, nttb200.cu:launch_independent) starts its first prefetch right
    * away: its CTAs fill the SMs that the previous grid's tail leaves idle -- what a caller with two
    * streams gets (+8 % at batch 2^16), for a single-stream caller.  Such a launch waits for its
-   * predecessors at its END instead, so completion on the stream stays in order. */
-  const bool nowait = P.nowait != 0;
+   * predecessors at its END instead, so completion on the stream stays in order.  A launch that waits
+   * triggers its dependents only after its wait (ntt_small.cuh, pdl_begin). */
   if (nowait && tile < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile, P.batch, lane);
   LaneTw1<L> twf, twi;
   if (TWREG) {
     twf.load(P.tw_fwd, l);
     twi.load(P.tw_inv, l);
   }
-  if (!nowait) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (!nowait) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
+  }
 #if PLANT_STAGGER_NS > 0
   /* The warps of a launch start together and stay in step from tile to tile, so the four that
    * share a scheduler want the same pipes at the same time.  Starting them a fraction of a tile
@@ -687,8 +691,8 @@ ntt_plant_kernel(const __grid_constant__ PlantParams<SmallGeom<L>::R> P) {
   LaneTw1<L> tw;
   tw.load(DIR == 0 ? P.tw_fwd : P.tw_inv, l);
   const PlRegs G = pl_regs(P);
+  if (!P.nowait) asm volatile("griddepcontrol.wait;" ::: "memory");     /* wait, then trigger: pdl_begin */
   asm volatile("griddepcontrol.launch_dependents;");
-  if (!P.nowait) asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const unsigned long long ntiles = (P.batch + Gm::PPW - 1) / Gm::PPW;
   const unsigned long long wstride = (unsigned long long)gridDim.x * WARPS;

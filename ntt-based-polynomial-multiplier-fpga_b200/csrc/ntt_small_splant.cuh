@@ -456,8 +456,8 @@ polymul_splant_kernel(const __grid_constant__ SPlantParams<SmallGeom<L>::R> P) {
   unsigned long long pend = 0;
   if (dyn) rounds_left -= 2;
 
-  asm volatile("griddepcontrol.launch_dependents;");
   const bool nowait = P.nowait != 0;
+  if (nowait) asm volatile("griddepcontrol.launch_dependents;");    /* a launch that waits triggers after its wait */
   if (nowait && tile < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile, P.batch, lane);
   LaneTwS<L> twf, twi;
   LaneZeta<L> zt;
@@ -468,6 +468,7 @@ polymul_splant_kernel(const __grid_constant__ SPlantParams<SmallGeom<L>::R> P) {
   }
   if (!nowait) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     if (tile < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile, P.batch, lane);
   }
 

@@ -128,8 +128,8 @@ polymul_splant_n1024_kernel(const __grid_constant__ SPlantParams<4> P) {
   unsigned long long pend = 0;
   if (dyn) rounds_left -= 2;
 
-  asm volatile("griddepcontrol.launch_dependents;");
   const bool nowait = P.nowait != 0;
+  if (nowait) asm volatile("griddepcontrol.launch_dependents;");    /* a launch that waits triggers after its wait */
   if (nowait && tile < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile, P.batch, lane);
   /* layout B: the lane is (i9 i8 i7 i6, i0) */
   const int hi4 = lane >> 1, b0 = lane & 1;
@@ -138,6 +138,7 @@ polymul_splant_n1024_kernel(const __grid_constant__ SPlantParams<4> P) {
   twi.load(P.tw_inv, hi4);
   if (!nowait) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     if (tile < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile, P.batch, lane);
   }
 

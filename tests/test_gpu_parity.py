@@ -1018,6 +1018,40 @@ def test_random_launch_sequences_on_one_stream_equal_their_sequential_meaning(gp
     p.close()
 
 
+@pytest.mark.parametrize("n,q", [(256, 12289), (256, 8380417), (1024, 12289)])
+def test_launch_after_a_waiting_launch_does_not_overtake_older_launches(gpu, oracle, nttb200, n, q):
+    """L1 writes X (long), L2 is tiny, reads one row of X (so it waits for L1) and writes elsewhere, L3
+    reads a window of X and shares nothing with L2.  The library checks L3 only against the launches since
+    the last one that waited (L2), so L2 must not let its dependents go before its own wait is over: L3
+    would run next to L1 and read rows of X that L1 has not written yet.  (With the trigger ahead of the
+    wait this fails on the windows that L1 writes last.)"""
+    import torch
+    rows = (1 << 16) if n == 256 else (1 << 14)
+    p = gpu.Plan(n, q)
+    st = torch.cuda.current_stream().cuda_stream
+    a, b = nttb200.inputs.survey_batch(n, q, rows, 2, device="cuda")
+    windows = [(rows * 3 // 4, rows), (rows * 27 // 32, rows * 28 // 32), (rows - 2048, rows), (rows // 2, rows * 5 // 8),
+               (rows * 13 // 16, rows * 14 // 16), (rows - 256, rows), (0, rows)]
+    for rep, (lo, hi) in enumerate(windows * 2):
+        watch = np.unique(np.r_[lo:lo + 8, hi - 64:hi, np.random.default_rng(rep).integers(lo, hi, 64)])
+        tw = torch.from_numpy(watch).cuda()
+        hb = b[tw].cpu().numpy()
+        hx = oracle.product(n, q, a[tw].cpu().numpy(), hb, 10)
+        want = oracle.product(n, q, hx, hb, 10)
+        x = torch.full_like(a, q - 1)                # what a too-early L3 would read
+        z = torch.empty((1, n), dtype=a.dtype, device="cuda")
+        d = torch.zeros_like(a)
+        torch.cuda.synchronize()
+        off = lo * n * 4
+        p.polymul_dev(x.data_ptr(), a.data_ptr(), b.data_ptr(), rows, st)                               # L1
+        p.polymul_dev(z.data_ptr(), x.data_ptr(), b.data_ptr(), 1, st)                                  # L2: waits for L1
+        p.polymul_dev(d.data_ptr() + off, x.data_ptr() + off, b.data_ptr() + off, hi - lo, st)          # L3
+        torch.cuda.synchronize()
+        assert (x[tw].cpu().numpy() == hx).all()
+        assert (d[tw].cpu().numpy() == want).all(), (rep, lo, hi)
+    p.close()
+
+
 def _friendly_primes(L, n, bits, count):
     out = []
     for seed in range(count * 3):
