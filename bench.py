@@ -54,10 +54,10 @@ WORKLOADS = {
 }
 # DRAM bytes (read + write) per launch of the dominant kernel, from `ncu --set full` captures
 # committed under profiles/ (a profiler run is never a bench value; this is the traffic only)
-TRAFFIC_NCU = {"c2": 134259456 + 37774592, "c4": 2147583000 + 1039149000}
+TRAFFIC_NCU = {"c2": 134259456 + 37774592, "c4": 2147519000 + 1041052000}
 TRAFFIC_SRC = {"c2": "profiles/r2_c2_splant_inc_ncu_full.txt: dram__bytes_read.sum 134.26 MB + "
                      "dram__bytes_write.sum 37.77 MB per launch (algorithmic 201.3 MB; part of c stays dirty in L2)",
-               "c4": "profiles/r2_c4_splant_ncu_full.txt: 2.148 GB read + 1.039 GB written per launch (algorithmic 3.221 GB)"}
+               "c4": "profiles/r2_c4_splant_n1024_ncu_full.txt: 2.148 GB read + 1.041 GB written per launch (algorithmic 3.221 GB)"}
 SEED = 0x4E545442323030
 L2_BYTES = 126 * 1000 * 1000
 
@@ -321,13 +321,13 @@ def slots_per_polymul(n: int, plantard: bool, signed: bool = False) -> int:
     measured half rate) + 2 IMAD; pointwise Montgomery = 2 IMAD.HI + 2 IMAD; the n^-1 scaling costs one
     extra multiplication on the sum branch of the last stage.  Plantard (q <= 12385): butterfly 3,
     pointwise 4, scale 3; at n <= 256 butterfly and scale 2 (IMAD, SHF, IMAD, SHF).  Signed Plantard
-    kernel (ntt_small_splant.cuh, the default): L - 1 stages per transform with 2 multiplications per
-    butterfly, 4 in the butterflies of the last inverse stage, and per coefficient pair 2 Barrett steps
-    (2 each), 5 raw products and 3 reductions (2 each): n (3 L + 5.5)."""
+    kernels (ntt_small_splant.cuh, ntt_splant_n1024.cuh: the default): L - 2 stages per transform with 2
+    multiplications per butterfly, 4 in the butterflies of the last inverse stage, and per group of four
+    coefficients 4 Barrett steps (2 each), 16 + 3 raw products and 7 reductions (2 each): n (3 L + 5.25)."""
     bflies = 3 * (n // 2) * (n.bit_length() - 1)
     L = n.bit_length() - 1
     if plantard and signed:
-        return 2 * n * (L - 1) + (n // 2) * 15 + n * (L - 2) + 2 * n
+        return 2 * n * (L - 2) + (n // 4) * 41 + n * (L - 3) + 2 * n
     if plantard and n <= 256:
         return 2 * bflies + 4 * n + 2 * (n // 2)
     if plantard:
@@ -702,7 +702,8 @@ def main() -> int:
         "sustained": sustained,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
-                     "kernel": (("polymul_splant_kernel" if W.signed else "polymul_plant_kernel") if plantard
+                     "kernel": ((("polymul_splant_n1024_kernel" if n == 1024 else "polymul_splant_kernel") if W.signed
+                                 else "polymul_plant_kernel") if plantard
                                 else "polymul_small_kernel") if n <= 1024 else
                                "large-n product pipeline (whole step)",
                      "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": roof_ms,
