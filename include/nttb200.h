@@ -96,6 +96,16 @@ const char *nttb200_plan_describe(const nttb200_plan *plan);
  * returns when c is complete. */
 int nttb200_polymul_batch(nttb200_plan *plan, int32_t *c, const int32_t *a, const int32_t *b,
                           size_t batch);
+/* The same product, asynchronous: the call queues the job and returns a ticket; a worker thread of
+ * the plan runs the queue through the SAME pipeline as the synchronous call, as one stream of jobs --
+ * so the first chunks of a product are narrowed and sent while the last chunks of the one before it
+ * drain (consecutive synchronous calls leave their fill and drain bare: about 9 % of a 2^16-row call).
+ * a, b must stay valid and unchanged, and c untouched, until nttb200_polymul_wait(plan, ticket) has
+ * returned (its return value is the product's status; ticket 0 waits for every product queued so far).
+ * Products complete in the order they were queued.  nttb200_plan_destroy runs the queue to its end. */
+int nttb200_polymul_batch_async(nttb200_plan *plan, int32_t *c, const int32_t *a, const int32_t *b,
+                                size_t batch, unsigned long long *ticket);
+int nttb200_polymul_wait(nttb200_plan *plan, unsigned long long ticket);
 /* Wire format of the host-buffer call above, half-word moduli (q <= 12385, n <= 1024), calls of
  * 2^19 words per operand or more: the call is bound by the PCIe link, so chunks of the batch
  * cross it as 16-bit words -- narrowed from / widened into the caller's int32_t rows by a pool of

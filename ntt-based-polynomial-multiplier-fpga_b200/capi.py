@@ -69,6 +69,8 @@ def lib() -> C.CDLL:
     L.nttb200_plan_describe.argtypes = [vp]
     L.nttb200_plan_describe.restype = C.c_char_p
     L.nttb200_polymul_batch.argtypes = [vp, i32p, i32p, i32p, sz]
+    L.nttb200_polymul_batch_async.argtypes = [vp, i32p, i32p, i32p, sz, C.POINTER(C.c_ulonglong)]
+    L.nttb200_polymul_wait.argtypes = [vp, C.c_ulonglong]
     L.nttb200_polymul_batch_dev.argtypes = [vp, i32p, i32p, i32p, sz, vp]
     L.nttb200_plan_wire_stats.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong),
                                           C.POINTER(C.c_ulonglong), C.POINTER(C.c_int)]
@@ -321,6 +323,17 @@ class Plan:
 
     def polymul_host_ptr(self, c_ptr: int, a_ptr: int, b_ptr: int, batch: int) -> None:
         _check(lib().nttb200_polymul_batch(self._h, c_ptr, a_ptr, b_ptr, batch))
+
+    def polymul_async_ptr(self, c_ptr: int, a_ptr: int, b_ptr: int, batch: int) -> int:
+        """Queue a host-buffer product (nttb200_polymul_batch_async); returns its ticket.  The buffers
+        must stay alive and untouched until wait(ticket) has returned."""
+        t = C.c_ulonglong(0)
+        _check(lib().nttb200_polymul_batch_async(self._h, c_ptr, a_ptr, b_ptr, batch, C.byref(t)))
+        return int(t.value)
+
+    def wait(self, ticket: int = 0) -> None:
+        """Block until the product with this ticket is complete (0: every product queued so far)."""
+        _check(lib().nttb200_polymul_wait(self._h, ticket))
 
 
 def ntt_table_batch(n: int, q: int, dataflow: str, table: np.ndarray, a: np.ndarray,

@@ -15,7 +15,10 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
+#include <unordered_map>
 #include <new>
 #include <string>
 #include <thread>
@@ -219,8 +222,10 @@ extern "C" int nttb200_plan_create(nttb200_plan **out, uint32_t n, uint32_t q, u
   return 0;
 }
 
+static void async_shutdown(nttb200_plan *P);
 extern "C" void nttb200_plan_destroy(nttb200_plan *P) {
   if (!P) return;
+  async_shutdown(P);                                   /* runs queued asynchronous products to their end */
   int cur = -1;
   cudaGetDevice(&cur);
   cudaSetDevice(P->device);
@@ -824,8 +829,10 @@ enum { WK_16 = 0,        /* narrowed by the pool, 16-bit words both ways (or int
        WK_32_STAGED = 2  /* 32-bit words copied by the pool through pinned staging (pageable callers)   */ };
 
 /* 32-bit words: from the caller's pinned buffers, or from staging the pool has filled */
-static int wire_send32(nttb200_plan *P, WireSlot &s, int32_t *c, const int32_t *a, const int32_t *b, bool staged) {
+static int wire_send32(nttb200_plan *P, WireSlot &s, bool staged) {
   const size_t n = P->n, bytes = s.rows * n * sizeof(uint32_t);
+  int32_t *c = s.job->c;
+  const int32_t *a = s.job->a, *b = s.job->b;
   const void *sa = staged ? (const void *)s.h_a : (const void *)(a + s.row0 * n);
   const void *sb = staged ? (const void *)s.h_b : (const void *)(b + s.row0 * n);
   void *dc = staged ? (void *)s.h_c : (void *)(c + s.row0 * n);
@@ -844,8 +851,10 @@ static int wire_send32(nttb200_plan *P, WireSlot &s, int32_t *c, const int32_t *
 /* 16-bit operands; the result comes back as 16-bit rows into pinned staging that the pool widens,
  * or (c_direct) as the caller's int32 rows written by the kernel's own 32-bit stores and copied
  * straight into a pinned c */
-static int wire_send16(nttb200_plan *P, WireSlot &s, int32_t *c, bool c_direct) {
+static int wire_send16(nttb200_plan *P, WireSlot &s) {
   const size_t n = P->n, bytes = s.rows * n * sizeof(uint16_t);
+  int32_t *c = s.job->c;
+  const bool c_direct = s.job->c_direct;
   NTT_CUDA(cudaMemcpyAsync(s.d_a, s.h_a, bytes, cudaMemcpyHostToDevice, s.stream));
   NTT_CUDA(cudaMemcpyAsync(s.d_b, s.h_b, bytes, cudaMemcpyHostToDevice, s.stream));
   int rc;
@@ -869,8 +878,9 @@ static int wire_send16(nttb200_plan *P, WireSlot &s, int32_t *c, bool c_direct) 
   return 0;
 }
 /* queue the pool jobs that fill the slot's staging with the chunk's operands */
-static void wire_stage_in(nttb200_plan *P, WireSlot &s, const int32_t *a, const int32_t *b, int kind, uint32_t *mask) {
+static void wire_stage_in(nttb200_plan *P, WireSlot &s, int kind, uint32_t *mask) {
   const size_t n = P->n, words = s.rows * n;
+  const int32_t *a = s.job->a, *b = s.job->b;
   if (kind == WK_16) {
     *mask = 0;
     s.job_a = nttb200_wire_post_narrow((uint16_t *)s.h_a, a + s.row0 * n, words, mask);
@@ -883,15 +893,18 @@ static void wire_stage_in(nttb200_plan *P, WireSlot &s, const int32_t *a, const 
   s.state = WS_STAGING;
 }
 
-static int polymul_batch_wire(nttb200_plan *P, int32_t *c, const int32_t *a, const int32_t *b, size_t batch) {
+/* The pipeline runs over a STREAM of jobs: `feed(peek)` hands out the next job (nullptr: none right
+ * now; peek = true only asks whether one is waiting), `done(job)` is told when the last row of a job has
+ * reached its c.  While the last chunks of one job drain, the first chunks of the next one are already
+ * being narrowed and sent -- what consecutive synchronous calls cannot do (their fill and drain, about 9 %
+ * of a 2^16-row call, lie bare).  The synchronous call is the stream of one job. */
+template <typename Feed, typename Done>
+static int wire_stream(nttb200_plan *P, Feed &&feed, Done &&done) {
   int rc = ensure_wire_slots(P);
   if (rc) return rc;
   const size_t n = P->n;
-  const bool c_pinned = is_pinned(c);
-  const bool pinned = is_pinned(a) && is_pinned(b) && c_pinned;
   const int mode = wire_mode();
   const bool narrow_ok = P->plant && mode != 32;
-  const bool c_direct = c_pinned && env_int("NTTB200_WIRE_C32", 0, 0, 1) == 1;
   /* How much the pool can take.  A dozen threads or more keep up with the link (1 GPU, 16 host
    * cores: 29.5 M polymul/s all-narrowed against 27.4 M mixed and 22.3 M all-32-bit).  Eight ranks
    * sharing the 32 cores of one box get 4 threads each, and the box's memory system is what binds
@@ -903,21 +916,29 @@ static int polymul_batch_wire(nttb200_plan *P, int32_t *c, const int32_t *a, con
   P->wire16_chunks = P->wire32_chunks = P->wire_c32_rows = 0;
   uint32_t mask[16] = {0};                             /* per slot: OR of the words with high bits */
   const size_t nsl = P->wslots.size();
-  size_t next = 0, busy = 0, chunk_no = 0;
+  size_t busy = 0, chunk_no = 0;
+  WireJob *cur = nullptr;
   const bool ramp = env_int("NTTB200_WIRE_RAMP", 1, 0, 1) != 0;
+  auto retire = [&](WireSlot &s) {                     /* the slot's rows are in c */
+    WireJob *jb = s.job;
+    s.state = WS_FREE;
+    s.job = nullptr;
+    busy--;
+    if (--jb->busy == 0 && jb->next >= jb->batch) { jb->finished = true; done(jb); }
+  };
   rc = 0;
   nttb200_wire_begin();
-  while (next < batch || busy > 0) {
+  for (;;) {
     bool progress = false;
     int staging = 0;
     for (size_t i = 0; i < nsl && !rc; i++) {
       WireSlot &s = P->wslots[i];
       if (s.state == WS_STAGING) {
         if (nttb200_wire_done(s.job_a) && nttb200_wire_done(s.job_b)) {
-          if (s.kind == WK_32_STAGED) rc = wire_send32(P, s, c, a, b, true);
-          else if (!(mask[i] & 0xffff0000u)) rc = wire_send16(P, s, c, c_direct);
-          else if (pinned) rc = wire_send32(P, s, c, a, b, false);       /* a word does not fit 16 bits */
-          else wire_stage_in(P, s, a, b, WK_32_STAGED, &mask[i]);
+          if (s.kind == WK_32_STAGED) rc = wire_send32(P, s, true);
+          else if (!(mask[i] & 0xffff0000u)) rc = wire_send16(P, s);
+          else if (s.job->pinned) rc = wire_send32(P, s, false);         /* a word does not fit 16 bits */
+          else wire_stage_in(P, s, WK_32_STAGED, &mask[i]);
           progress = true;
         } else {
           staging++;
@@ -926,9 +947,9 @@ static int polymul_batch_wire(nttb200_plan *P, int32_t *c, const int32_t *a, con
         const cudaError_t e = cudaEventQuery(s.done);
         if (e == cudaSuccess) {
           if (!s.host_out) {
-            s.state = WS_FREE;
-            busy--;
+            retire(s);
           } else {
+            int32_t *c = s.job->c;
             s.job_c = (s.kind == WK_16)
                           ? nttb200_wire_post_widen(c + s.row0 * n, (const uint16_t *)s.h_c, s.rows * n)
                           : nttb200_wire_post_copy(c + s.row0 * n, (const int32_t *)s.h_c, s.rows * n, 1);
@@ -940,35 +961,44 @@ static int polymul_batch_wire(nttb200_plan *P, int32_t *c, const int32_t *a, con
         }
       } else if (s.state == WS_WIDENING) {
         if (nttb200_wire_done(s.job_c)) {
-          s.state = WS_FREE;
-          busy--;
+          retire(s);
           progress = true;
         }
       }
     }
     if (rc) break;
-    if (next < batch) {
+    if (!cur) {
+      if (busy == 0) chunk_no = 0;                     /* the pipeline ran dry: ramp up again */
+      cur = feed(false);
+      if (cur && cur->batch == 0) { cur->finished = true; done(cur); cur = nullptr; progress = true; }
+    }
+    if (cur) {
       for (size_t i = 0; i < nsl; i++) {
         WireSlot &s = P->wslots[i];
         if (s.state != WS_FREE) continue;
-        /* taper the last chunks so that the drain (one kernel + D2H + widen) is short */
-        const size_t left = batch - next;
+        /* taper the last chunks so that the drain (one kernel + D2H + widen) is short -- unless another
+         * job is waiting, whose first chunks will cover it */
+        const size_t left = cur->batch - cur->next;
         size_t nb = std::min(P->wire_polys, left);
         /* ... and ramp the first ones up (1/8, 1/4, 1/2 of a slot) so that the link starts early */
         if (ramp && chunk_no < 3) nb = std::min(nb, std::max<size_t>(P->wire_polys >> (3 - chunk_no), 64));
-        if (left <= P->wire_polys && left > 64) nb = std::min(nb, std::max<size_t>(left / 2, 64));
+        if (left <= P->wire_polys && left > 64 && !feed(true)) nb = std::min(nb, std::max<size_t>(left / 2, 64));
         chunk_no++;
-        s.row0 = next;
+        s.job = cur;
+        s.row0 = cur->next;
         s.rows = nb;
-        next += nb;
+        cur->next += nb;
+        cur->busy++;
         busy++;
-        if (pinned && (!narrow_ok || (mode == 0 && staging >= ahead))) rc = wire_send32(P, s, c, a, b, false);
-        else wire_stage_in(P, s, a, b, narrow_ok ? WK_16 : WK_32_STAGED, &mask[i]);
+        if (cur->pinned && (!narrow_ok || (mode == 0 && staging >= ahead))) rc = wire_send32(P, s, false);
+        else wire_stage_in(P, s, narrow_ok ? WK_16 : WK_32_STAGED, &mask[i]);
+        if (cur->next >= cur->batch) cur = nullptr;    /* all its rows are on their way */
         progress = true;
         break;
       }
       if (rc) break;
     }
+    if (!cur && busy == 0 && !feed(true)) break;       /* nothing in flight, nothing waiting */
     if (!progress) nttb200_wire_help();
   }
   if (rc) {                                            /* leave no job or copy behind */
@@ -976,11 +1006,34 @@ static int polymul_batch_wire(nttb200_plan *P, int32_t *c, const int32_t *a, con
       if (s.state == WS_STAGING) { nttb200_wire_wait(s.job_a); nttb200_wire_wait(s.job_b); }
       if (s.state == WS_WIDENING) nttb200_wire_wait(s.job_c);
       cudaStreamSynchronize(s.stream);
+      if (s.state != WS_FREE && s.job) {
+        s.job->rc = rc;
+        if (--s.job->busy == 0 && !s.job->finished && s.job != cur) { s.job->finished = true; done(s.job); }
+      }
       s.state = WS_FREE;
+      s.job = nullptr;
     }
+    if (cur) { cur->rc = rc; cur->finished = true; done(cur); }
   }
   nttb200_wire_end();
   return rc;
+}
+
+static void wire_job_init(WireJob &jb, int32_t *c, const int32_t *a, const int32_t *b, size_t batch) {
+  jb.c = c; jb.a = a; jb.b = b; jb.batch = batch;
+  const bool c_pinned = is_pinned(c);
+  jb.pinned = is_pinned(a) && is_pinned(b) && c_pinned;
+  jb.c_direct = c_pinned && env_int("NTTB200_WIRE_C32", 0, 0, 1) == 1;
+}
+
+static int polymul_batch_wire(nttb200_plan *P, int32_t *c, const int32_t *a, const int32_t *b, size_t batch) {
+  WireJob jb;
+  wire_job_init(jb, c, a, b, batch);
+  bool handed = false;
+  int rc = wire_stream(P,
+                       [&](bool peek) -> WireJob * { if (handed) return nullptr; if (!peek) handed = true; return &jb; },
+                       [](WireJob *) {});
+  return rc ? rc : jb.rc;
 }
 
 extern "C" int nttb200_plan_wire_stats(const nttb200_plan *P, unsigned long long *rows16,
@@ -994,17 +1047,16 @@ extern "C" int nttb200_plan_wire_stats(const nttb200_plan *P, unsigned long long
   return 0;
 }
 
-extern "C" int nttb200_polymul_batch(nttb200_plan *P, int32_t *c, const int32_t *a, const int32_t *b,
-                                     size_t batch) {
-  if (!P || !c || !a || !b) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
-  g_launches = 0;
-  if (P->flags & NTTB200_PLAN_CHECK_RANGE) {
-    int rcr = check_range_host(P, a, batch * P->n, "a");
-    if (!rcr) rcr = check_range_host(P, b, batch * P->n, "b");
-    if (rcr) return rcr;
-  }
-  std::lock_guard<std::mutex> lock(P->mu);
-  DeviceGuard guard(P->device);
+static bool wire_eligible(const nttb200_plan *P, const int32_t *c, const int32_t *a, const int32_t *b, size_t batch) {
+  /* large batches: half-word moduli cross the link as 16-bit words; pageable buffers of any small-n
+   * plan are staged by the host pool instead of the driver (wire_stream) */
+  return P->kernel == PK_SMALL && batch * P->n >= WIRE_MIN_WORDS &&
+         ((P->plant && wire_mode() != 32) ||
+          (env_int("NTTB200_STAGE_PAGEABLE", 1, 0, 1) && !(is_pinned(a) && is_pinned(b) && is_pinned(c))));
+}
+
+/* the host-buffer product with the plan's mutex held and its device current */
+static int polymul_batch_locked(nttb200_plan *P, int32_t *c, const int32_t *a, const int32_t *b, size_t batch) {
   int rc = ensure_slots(P, true);
   if (rc) return rc;
   const size_t n = P->n;
@@ -1024,12 +1076,7 @@ extern "C" int nttb200_polymul_batch(nttb200_plan *P, int32_t *c, const int32_t 
     memcpy(c, hc, bytes);
     return 0;
   }
-  /* large batches: half-word moduli cross the link as 16-bit words; pageable buffers of any small-n
-   * plan are staged by the host pool instead of the driver (polymul_batch_wire) */
-  if (P->kernel == PK_SMALL && batch * n >= WIRE_MIN_WORDS &&
-      ((P->plant && wire_mode() != 32) ||
-       (env_int("NTTB200_STAGE_PAGEABLE", 1, 0, 1) && !(is_pinned(a) && is_pinned(b) && is_pinned(c)))))
-    return polymul_batch_wire(P, c, a, b, batch);
+  if (wire_eligible(P, c, a, b, batch)) return polymul_batch_wire(P, c, a, b, batch);
   size_t k = 0;
   for (size_t done = 0, nb = 0; done < batch; done += nb, k++) {
     HostSlot &s = P->slots[k % NSLOT];
@@ -1047,6 +1094,165 @@ extern "C" int nttb200_polymul_batch(nttb200_plan *P, int32_t *c, const int32_t 
   }
   for (auto &s : P->slots) NTT_CUDA(cudaStreamSynchronize(s.stream));
   return 0;
+}
+
+extern "C" int nttb200_polymul_batch(nttb200_plan *P, int32_t *c, const int32_t *a, const int32_t *b,
+                                     size_t batch) {
+  if (!P || !c || !a || !b) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
+  g_launches = 0;
+  if (P->flags & NTTB200_PLAN_CHECK_RANGE) {
+    int rcr = check_range_host(P, a, batch * P->n, "a");
+    if (!rcr) rcr = check_range_host(P, b, batch * P->n, "b");
+    if (rcr) return rcr;
+  }
+  std::lock_guard<std::mutex> lock(P->mu);
+  DeviceGuard guard(P->device);
+  return polymul_batch_locked(P, c, a, b, batch);
+}
+
+/* ---- asynchronous host-buffer products ------------------------------------------------------
+ * nttb200_polymul_batch_async queues the product and returns a ticket; a worker thread of the plan
+ * runs the queue through the SAME pipeline as the synchronous call -- as one stream of jobs, so the
+ * first chunks of a product are narrowed and sent while the last chunks of the one before it drain.
+ * nttb200_polymul_wait blocks until the ticket's c is complete (ticket 0: everything queued so far). */
+struct AsyncJob {
+  WireJob w;                  /* first member: the pipeline hands WireJob pointers back */
+  bool done = false;
+};
+struct AsyncCtx {
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv_work, cv_done;
+  std::deque<AsyncJob *> queue;                                  /* submitted, not yet taken */
+  std::unordered_map<unsigned long long, AsyncJob *> jobs;       /* until waited for         */
+  unsigned long long next_ticket = 1;
+  bool stop = false;
+};
+
+static void async_worker(nttb200_plan *P) {
+  AsyncCtx *A = P->async.load();
+  cudaSetDevice(P->device);
+  auto finish = [A](WireJob *w) {
+    std::lock_guard<std::mutex> lk(A->mu);
+    reinterpret_cast<AsyncJob *>(w)->done = true;
+    A->cv_done.notify_all();
+  };
+  for (;;) {
+    AsyncJob *head = nullptr;
+    {
+      std::unique_lock<std::mutex> lk(A->mu);
+      A->cv_work.wait(lk, [&] { return A->stop || !A->queue.empty(); });
+      if (A->queue.empty()) return;                              /* stop, and nothing left to do */
+      head = A->queue.front();
+    }
+    std::lock_guard<std::mutex> plan_lock(P->mu);
+    if (wire_eligible(P, head->w.c, head->w.a, head->w.b, head->w.batch)) {
+      auto feed = [&](bool peek) -> WireJob * {
+        std::lock_guard<std::mutex> lk(A->mu);
+        if (A->queue.empty()) return nullptr;
+        AsyncJob *j = A->queue.front();
+        if (!wire_eligible(P, j->w.c, j->w.a, j->w.b, j->w.batch)) return nullptr;
+        if (!peek) A->queue.pop_front();
+        return &j->w;
+      };
+      int rc = wire_stream(P, feed, finish);
+      if (rc) {                                                  /* could not even start: fail the head */
+        std::unique_lock<std::mutex> lk(A->mu);
+        if (!A->queue.empty() && A->queue.front() == head && !head->done) {
+          A->queue.pop_front();
+          head->w.rc = rc;
+          head->done = true;
+          A->cv_done.notify_all();
+        }
+      }
+    } else {
+      {
+        std::lock_guard<std::mutex> lk(A->mu);
+        A->queue.pop_front();
+      }
+      head->w.rc = polymul_batch_locked(P, head->w.c, head->w.a, head->w.b, head->w.batch);
+      finish(&head->w);
+    }
+  }
+}
+
+extern "C" int nttb200_polymul_batch_async(nttb200_plan *P, int32_t *c, const int32_t *a, const int32_t *b,
+                                           size_t batch, unsigned long long *ticket) {
+  if (!P || !c || !a || !b || !ticket) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
+  if (P->flags & NTTB200_PLAN_CHECK_RANGE) {
+    int rcr = check_range_host(P, a, batch * P->n, "a");
+    if (!rcr) rcr = check_range_host(P, b, batch * P->n, "b");
+    if (rcr) return rcr;
+  }
+  /* (the plan's own mutex is the worker's while it streams: submitting must not wait for it) */
+  AsyncCtx *A = P->async.load();
+  if (!A) {
+    std::lock_guard<std::mutex> init(P->async_init_mu);
+    if (!(A = P->async.load())) {
+      {
+        std::lock_guard<std::mutex> lock(P->mu);
+        DeviceGuard guard(P->device);
+        int rc = ensure_slots(P, true);
+        if (rc) return rc;
+      }
+      A = new AsyncCtx();
+      P->async.store(A);
+      A->th = std::thread(async_worker, P);
+    }
+  }
+  AsyncJob *j = new AsyncJob();
+  {
+    DeviceGuard guard(P->device);
+    wire_job_init(j->w, c, a, b, batch);
+  }
+  std::lock_guard<std::mutex> lk(A->mu);
+  j->w.ticket = *ticket = A->next_ticket++;
+  A->jobs[j->w.ticket] = j;
+  A->queue.push_back(j);
+  A->cv_work.notify_one();
+  return 0;
+}
+
+extern "C" int nttb200_polymul_wait(nttb200_plan *P, unsigned long long ticket) {
+  if (!P) return nttb200_fail(NTTB200_EPARAM, "NULL argument");
+  AsyncCtx *A = P->async.load();
+  if (!A) return ticket ? nttb200_fail(NTTB200_EPARAM, "unknown ticket %llu", ticket) : 0;
+  std::unique_lock<std::mutex> lk(A->mu);
+  int rc = 0;
+  if (ticket == 0) {                                             /* everything submitted so far */
+    std::vector<unsigned long long> all;
+    for (auto &kv : A->jobs) all.push_back(kv.first);
+    for (unsigned long long t : all) {
+      AsyncJob *j = A->jobs[t];
+      A->cv_done.wait(lk, [&] { return j->done; });
+      if (j->w.rc && !rc) rc = j->w.rc;
+      A->jobs.erase(t);
+      delete j;
+    }
+    return rc ? nttb200_fail(rc, "an asynchronous product failed (%d)", rc) : 0;
+  }
+  auto it = A->jobs.find(ticket);
+  if (it == A->jobs.end()) return nttb200_fail(NTTB200_EPARAM, "unknown ticket %llu (already waited for?)", ticket);
+  AsyncJob *j = it->second;
+  A->cv_done.wait(lk, [&] { return j->done; });
+  rc = j->w.rc;
+  A->jobs.erase(ticket);
+  delete j;
+  return rc ? nttb200_fail(rc, "asynchronous product %llu failed (%d)", ticket, rc) : 0;
+}
+
+static void async_shutdown(nttb200_plan *P) {
+  AsyncCtx *A = P->async.load();
+  if (!A) return;
+  {
+    std::lock_guard<std::mutex> lk(A->mu);
+    A->stop = true;
+    A->cv_work.notify_all();
+  }
+  if (A->th.joinable()) A->th.join();                            /* runs the queue dry first */
+  for (auto &kv : A->jobs) delete kv.second;
+  delete A;
+  P->async.store(nullptr);
 }
 
 /* ---- packed 16-bit extension (outside the reference API; half-word moduli only) ---------- */

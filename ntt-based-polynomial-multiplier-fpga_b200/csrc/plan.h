@@ -54,9 +54,24 @@ struct WireSlot {
   uint32_t *h_a = nullptr, *h_b = nullptr, *h_c = nullptr;      /* pinned staging, words of either width */
   int state = 0, kind = 0;
   bool host_out = false;                                        /* the result passes through h_c   */
+  struct WireJob *job = nullptr;                                /* whose rows the slot holds       */
   size_t row0 = 0, rows = 0;
   unsigned long long job_a = 0, job_b = 0, job_c = 0;
 };
+
+/* one host-buffer product on its way through the wire pipeline (nttb200.cu: wire_stream) */
+struct WireJob {
+  int32_t *c = nullptr;
+  const int32_t *a = nullptr, *b = nullptr;
+  size_t batch = 0;
+  size_t next = 0;          /* rows handed to slots so far              */
+  size_t busy = 0;          /* slots that hold rows of this job         */
+  bool pinned = false, c_direct = false;
+  unsigned long long ticket = 0;
+  int rc = 0;
+  bool finished = false;
+};
+struct AsyncCtx;            /* worker thread + queue of nttb200_polymul_batch_async (nttb200.cu) */
 
 struct LargeLane {
   cudaStream_t stream = nullptr;
@@ -91,6 +106,8 @@ struct nttb200_plan {
   std::vector<WireSlot> wslots;
   size_t wire_polys = 0;           /* rows per wire chunk */
   unsigned long long wire16_chunks = 0, wire32_chunks = 0, wire_c32_rows = 0;      /* rows sent on each wire by the last call */
+  std::atomic<AsyncCtx *> async{nullptr};    /* created by the first nttb200_polymul_batch_async */
+  std::mutex async_init_mu;
 
   /* tail scheduler of the Plantard product kernel: ring of (next chunk, warps finished) pairs,
    * zero between launches; every launch that uses it is handed the next pair */

@@ -1113,3 +1113,46 @@ def test_small_product_right_after_a_large_n_product_on_the_same_stream(gpu, ora
         assert (d.cpu().numpy().reshape(-1, 256) == want).all()
     pl.close()
     ps.close()
+
+
+@pytest.mark.parametrize("n,q", [(256, 12289), (1024, 12289), (256, 8380417)])
+def test_asynchronous_host_buffer_products_equal_the_synchronous_call(gpu, oracle, nttb200, n, q):
+    """nttb200_polymul_batch_async: a queue of host-buffer products of mixed sizes (wire-eligible and
+    not, pinned and pageable, an empty one) run by the plan's worker as ONE stream of jobs through the
+    pipeline of the synchronous call; every result equals the synchronous call's and the oracle's on
+    sampled rows, tickets can be waited for in any order, and a synchronous call may come in between."""
+    p = gpu.Plan(n, q)
+    sizes = [(1 << 19) // n * 4, 3, (1 << 19) // n * 2 + 17, 0, (1 << 19) // n * 8, 70, (1 << 19) // n * 3]
+    jobs = []
+    for k, rows in enumerate(sizes):
+        a, b = oracle.random((max(rows, 1), n), q, 100 + k)[:rows], oracle.random((max(rows, 1), n), q, 200 + k)[:rows]
+        if k % 2 == 0 and rows:                      # pinned buffers for every other job
+            ha, hb, hc = nttb200.host_alloc((rows, n)), nttb200.host_alloc((rows, n)), nttb200.host_alloc((rows, n))
+            ha.array[:], hb.array[:] = a, b
+            jobs.append((ha.array, hb.array, hc.array, (ha, hb, hc)))
+        else:
+            jobs.append((np.ascontiguousarray(a), np.ascontiguousarray(b), np.empty((rows, n), np.int32), None))
+    for rep in range(2):
+        for _, _, c, _ in jobs:
+            c[...] = -1
+        tickets = [p.polymul_async_ptr(c.ctypes.data, a.ctypes.data, b.ctypes.data, a.shape[0]) for a, b, c, _ in jobs]
+        if rep == 1:
+            mid = p.polymul(jobs[1][0], jobs[1][1])   # a synchronous call queues behind the stream
+            assert (mid == oracle.product(n, q, jobs[1][0], jobs[1][1], 10)).all()
+        for t in (reversed(tickets) if rep == 0 else tickets[::2]):
+            p.wait(t)
+        p.wait(0)
+        for a, b, c, _ in jobs:
+            rows = a.shape[0]
+            if rows == 0:
+                continue
+            pick = np.unique(np.r_[0:min(rows, 3), max(0, rows - 3):rows, np.random.default_rng(rows).integers(0, rows, 16)])
+            assert (c[pick] == oracle.product(n, q, a[pick], b[pick], 10)).all()
+            assert c.min() >= 0 and c.max() < q
+    with pytest.raises(nttb200.NttError):
+        p.wait(tickets[0])                           # already waited for
+    for *_, keep in jobs:
+        if keep:
+            for h in keep:
+                h.free()
+    p.close()
