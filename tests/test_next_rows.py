@@ -97,6 +97,36 @@ def test_generator_number_theory(L, gen_golden):
     assert _params(L, 256, 13, 8, 12291)[0] != 0           # not prime
 
 
+def test_generate_coeff_command_line_twin(L, tmp_path):
+    """tools/nttb200_generate_coeff.c: the reference's generate_coeff.c:12-59 with N, Q and the seed as
+    optional arguments -- same messages, same two files, 10 decimals per line, every value in [0, Q); the
+    files are what the library's reader (and time_testing256.c:17-44) reads back."""
+    import subprocess
+    exe = os.path.join(PKG_DIR, "nttb200_generate_coeff")
+    assert os.path.exists(exe), "build() makes it (csrc/Makefile)"
+    for args, n, q in (([], 256, 12289), (["1024", "7681", "5"], 1024, 7681)):
+        r = subprocess.run([exe] + args, cwd=tmp_path, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert r.stdout.splitlines() == [f"Gerando coeficientes aleatorios com Q={q} e N={n}.",
+                                         "Arquivos 'coeficientes_a.txt' e 'coeficientes_b.txt' gerados com sucesso!"]
+        got = []
+        for name in ("coeficientes_a.txt", "coeficientes_b.txt"):
+            text = open(tmp_path / name).read()
+            lines = text.split("\n")
+            assert all(len(ln.split()) == 10 and ln.endswith(" ") for ln in lines[:n // 10])
+            back = np.full(n + 1, -1, np.int32)
+            assert L.nttb200_read_coeff_file(str(tmp_path / name).encode(), back.ctypes.data, n + 1) == n
+            assert back[:n].min() >= 0 and back[:n].max() < q
+            got.append(back[:n].copy())
+        assert not (got[0] == got[1]).all()
+    again = subprocess.run([exe, "1024", "7681", "5"], cwd=tmp_path, capture_output=True, text=True)
+    assert again.returncode == 0
+    back = np.zeros(1024, np.int32)
+    L.nttb200_read_coeff_file(str(tmp_path / "coeficientes_b.txt").encode(), back.ctypes.data, 1024)
+    assert (back == got[1]).all()                    # a given seed reproduces the files
+    assert subprocess.run([exe, "0"], cwd=tmp_path, capture_output=True).returncode == 2
+
+
 def test_text_formats(L, golden, tmp_path):
     a = golden["fixture_a"].astype(np.int32)
     p = str(tmp_path / "coef.txt").encode()
