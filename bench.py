@@ -483,9 +483,31 @@ def side_workload(mod, sh, torch, name, dev, rank, world, local, peak_gbs, imad_
                "parity_ok": ok, "parity_rows_checked": nchecked, "parity_checker": checker,
                "l2": f"{w.sets} rotating buffer sets ({w.sets * 3 * w.batch * w.n * 4 >> 20} MiB)"}
         rec.update(w.fractions(w.batch * steps / (ms_local * 1e-3), peak_gbs, imad_peak))
+        if "arith=canon" in rec["plan"]:
+            rec["butterfly_roof"] = butterfly_roof_canon(mod, w.n, w.batch * steps / (ms_local * 1e-3))
         return rec
     finally:
         w.close()
+
+
+def butterfly_roof_canon(mod, n, rate_per_gpu):
+    """31-bit moduli (CANON class): what the integer pipes allow BEFORE a byte moves.  The three butterflies of
+    the large-n kernels are timed in isolation on every SM (nttb200_measure_int_peak 24 / 25 / 26: independent
+    chains, no memory instruction), and a product is counted as they occur in it: per transform log2(n) stages
+    of n/2 butterflies; forward, half the butterflies of three stages in four leave their results in [0, 2q),
+    and so does the whole last stage of operand a (modarith.cuh: LAZYOUT) -- 13 of the 32 forward stages'
+    worth; the 16 inverse stages are Gentleman-Sande.  The pointwise products (two IMAD.HI and two IMAD each)
+    are counted at the measured IMAD.HI rate."""
+    L = n.bit_length() - 1
+    ct, ct_lazy, gs = (mod.measure_int_peak(k) for k in (24, 25, 26))
+    hi = mod.measure_int_peak(1)
+    lazy_stages = 2 * (L - L // 4) * 0.5 + 1          # three stages in four of both operands, half of each; + a's last
+    canon_stages = 2 * L - lazy_stages
+    sec = (n // 2) * (lazy_stages / ct_lazy + canon_stages / ct + L / gs) + n * 3 / hi
+    return {"ct_canonical_per_s": ct, "ct_lazy_out_per_s": ct_lazy, "gs_per_s": gs,
+            "polymul_per_s": 1.0 / sec, "frac": rate_per_gpu * sec,
+            "note": "isolated butterfly rates x the product's butterfly counts: the roof of this arithmetic on the "
+                    "integer pipes, memory instructions and launches not counted"}
 
 
 def protect_stdout():
@@ -756,6 +778,8 @@ def main() -> int:
         "workloads": side,
         "strong_scaling": strong,
     }
+    if "arith=canon" in plan_desc:
+        line["butterfly_roof"] = butterfly_roof_canon(mod, n, rate)
     if two:
         two["hbm_frac"] = two["value"] / world * 12 * n / 1e9 / peak_gbs
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

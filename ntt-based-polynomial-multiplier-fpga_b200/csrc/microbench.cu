@@ -159,6 +159,15 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *sink, uint32_t 
           x[i] = (uint32_t)s;
           const int p = (int)((uint32_t)d * a);
           y[i] = (uint32_t)((p >> 16) * (int)m.q + (int)b);
+        } else if (WHICH == 24 || WHICH == 25 || WHICH == 26) {
+          /* the butterflies of the 31-bit class (q = 2013265921 > 2^30: CANON, modarith.cuh) as the large-n
+           * kernels run them: 24 Cooley-Tukey with canonical results (8 instructions), 25 the same with both
+           * results left in [0, 2q) for the next stage's multiplication (6), 26 Gentleman-Sande (7) */
+          ModQ c;
+          c.q = 2013265921u; c.nq = 0u - 2013265921u; c.q2 = 0; c.qinv = 0;
+          if (WHICH == 24) ct_bfly<ARITH_CANON, false>(x[i], y[i], a, b, c);
+          else if (WHICH == 25) ct_bfly<ARITH_CANON, true>(x[i], y[i], a, b, c);
+          else gs_bfly<ARITH_CANON>(x[i], y[i], a, b, c, 0);
         } else if (WHICH == 15) {
           /* LEA.HI.SX32 alone: x += y >> 16 */
           x[i] = (uint32_t)((int)x[i] + ((int)y[i] >> 16));
@@ -232,6 +241,9 @@ extern "C" int nttb200_measure_int_peak(int which, double *lane_ops_per_s) {
     case 21: return run<21>(1, lane_ops_per_s); /* 20 with the sum as an IMAD (3 + 3)                             */
     case 22: return run<22>(1, lane_ops_per_s); /* signed GS with the product's last shift left pending, 5        */
     case 23: return run<23>(1, lane_ops_per_s); /* 14, 14, 18 in turn                                             */
+    case 24: return run<24>(1, lane_ops_per_s); /* 31-bit class: Cooley-Tukey butterflies / s, canonical results  */
+    case 25: return run<25>(1, lane_ops_per_s); /* 31-bit class: Cooley-Tukey, results left in [0, 2q)            */
+    case 26: return run<26>(1, lane_ops_per_s); /* 31-bit class: Gentleman-Sande butterflies / s                  */
     default: return nttb200_fail(NTTB200_EPARAM, "unknown microbenchmark %d", which);
   }
 }

@@ -19,6 +19,9 @@ NAMES = {0: "IMAD", 1: "IMAD.HI", 2: "IADD", 12: "SHF + IADD pairs (x2)", 15: "L
          23: "14, 14, 18 in turn",
          20: "signed Plantard half word, Gentleman-Sande, 6 instructions (2 IADD, IMAD, SHF, IMAD, SHF)",
          21: "20 with the sum as mad.lo (X, 1, Y)",
+         24: "31-bit class (q = 2013265921), Cooley-Tukey, canonical results, 8 instructions",
+         25: "31-bit class, Cooley-Tukey, results left in [0, 2q) for the next multiplication, 6 instructions",
+         26: "31-bit class, Gentleman-Sande, 7 instructions",
          22: "signed Gentleman-Sande, last shift of the product left pending (LEA.HI.SX32, IADD3, IMAD, SHF, IMAD)"}
 sms, clk = 148, 1.965e9
 for k, name in NAMES.items():
