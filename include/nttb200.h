@@ -102,7 +102,8 @@ int nttb200_polymul_batch(nttb200_plan *plan, int32_t *c, const int32_t *a, cons
  * drain (consecutive synchronous calls leave their fill and drain bare: about 9 % of a 2^16-row call).
  * a, b must stay valid and unchanged, and c untouched, until nttb200_polymul_wait(plan, ticket) has
  * returned (its return value is the product's status; ticket 0 waits for every product queued so far).
- * Products complete in the order they were queued.  nttb200_plan_destroy runs the queue to its end. */
+ * Products complete in the order they were queued; a ticket is waited for once, by one thread.
+ * nttb200_plan_destroy runs the queue to its end. */
 int nttb200_polymul_batch_async(nttb200_plan *plan, int32_t *c, const int32_t *a, const int32_t *b,
                                 size_t batch, unsigned long long *ticket);
 int nttb200_polymul_wait(nttb200_plan *plan, unsigned long long ticket);

@@ -1146,12 +1146,12 @@ static void async_worker(nttb200_plan *P) {
       head = A->queue.front();
     }
     std::lock_guard<std::mutex> plan_lock(P->mu);
-    if (wire_eligible(P, head->w.c, head->w.a, head->w.b, head->w.batch)) {
+    if (head->w.wire) {
       auto feed = [&](bool peek) -> WireJob * {
         std::lock_guard<std::mutex> lk(A->mu);
         if (A->queue.empty()) return nullptr;
         AsyncJob *j = A->queue.front();
-        if (!wire_eligible(P, j->w.c, j->w.a, j->w.b, j->w.batch)) return nullptr;
+        if (!j->w.wire) return nullptr;                          /* a small product: after the stream has drained */
         if (!peek) A->queue.pop_front();
         return &j->w;
       };
@@ -1204,6 +1204,7 @@ extern "C" int nttb200_polymul_batch_async(nttb200_plan *P, int32_t *c, const in
   {
     DeviceGuard guard(P->device);
     wire_job_init(j->w, c, a, b, batch);
+    j->w.wire = wire_eligible(P, c, a, b, batch);
   }
   std::lock_guard<std::mutex> lk(A->mu);
   j->w.ticket = *ticket = A->next_ticket++;

@@ -67,6 +67,7 @@ struct WireJob {
   size_t next = 0;          /* rows handed to slots so far              */
   size_t busy = 0;          /* slots that hold rows of this job         */
   bool pinned = false, c_direct = false;
+  bool wire = false;        /* goes through the wire pipeline (decided when the job is queued) */
   unsigned long long ticket = 0;
   int rc = 0;
   bool finished = false;
