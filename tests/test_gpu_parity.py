@@ -204,9 +204,9 @@ FUSED_N = (32768, 65536)      # one persistent cluster kernel (ntt_large_fused.c
 def test_large_n_multipass_products(gpu, oracle, monkeypatch, n, q, fused):
     """n > 1024: column pass / row pass / column pass (ntt_large.cuh) against the oracle's
     merged CT-fwd/GS-inv pipeline; ragged batch (odd, not a multiple of the CTA's 16 rows).
-    n = 2^15, 2^16 run the three passes inside ONE persistent kernel (1 launch): the ticket
-    dataflow kernel (NTTB200_LARGE_FUSED=2, the default; n = 2^16) or the cluster kernel (=1);
-    NTTB200_LARGE_FUSED=0 asks for the three-launch pipeline."""
+    n = 2^15, 2^16 can also run the three passes inside ONE persistent kernel (1 launch): the ticket
+    dataflow kernel (NTTB200_LARGE_FUSED=2) or the cluster kernel (=1) -- both measured slower than the
+    three-launch pipeline, which is the default (NTTB200_LARGE_FUSED=0)."""
     if fused != 2 and n not in FUSED_N:
         pytest.skip("only n = 2^15, 2^16 have the fused kernels")
     monkeypatch.setenv("NTTB200_LARGE_FUSED", str(fused))
