@@ -753,7 +753,7 @@ def main() -> int:
         "sustained": sustained,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
-                     "kernel": ((("polymul_splant_n1024_kernel" if n == 1024 else "polymul_splant_kernel") if W.signed
+                     "kernel": ((("polymul_splant_wide_kernel" if n in (512, 1024) else "polymul_splant_kernel") if W.signed
                                  else "polymul_plant_kernel") if plantard
                                 else "polymul_small_kernel") if n <= 1024 else
                                "large-n product pipeline (whole step)",

@@ -1,5 +1,5 @@
 /*
- * ntt_splant_n1024.cuh -- fused product kernel for n = 1024, half-word moduli: the arithmetic of
+ * ntt_splant_n1024.cuh -- fused product kernel for n = 1024 (and n = 512), half-word moduli: the arithmetic of
  * ntt_small_splant.cuh (signed Plantard, five-instruction butterflies, two stages left to a group
  * multiplication) in a geometry whose code FITS THE INSTRUCTION CACHE.
  *
@@ -35,6 +35,14 @@
  * 23 KB, 80 registers.  Measured on B200 (profiles/r2_c4_splant_n1024_ncu_full.txt): `no_instruction`
  * drops from 1.45 to 0.11 warps per issue cycle, issue slots 69.5 % -> 83.2 % busy (3.33 instructions per
  * clock and SM, what the n = 256 kernel reaches), c4 279.5 -> 286 M polymul/s.
+ *
+ * n = 512 can run the same kernel (NTTB200_PLANT_N1024=2; measured 1.5 % slower than the one-layout-per-phase
+ * kernel there, so it is not the default) with 32 virtual lanes (no halves) and three stages in layout B:
+ *      layout A   registers i8 i7 i6 i5   lane i4 .. i0          stages on bits 8 .. 5
+ *      layout B   registers i4 i3 i2 i1   lane i8 .. i5, i0      stages on bits 4 .. 2 (i1 rides along)
+ *      layout C   registers i3 i2 i1 i0   lane i8 .. i4          group multiplication
+ * word i at i + 2 (i >> 5): A and B are conflict-free, C has two-way conflicts (no padding of this
+ * additive family serves all three layouts of the 9 index bits; searched exhaustively).
  */
 #pragma once
 #include <stdint.h>
@@ -42,13 +50,34 @@
 
 namespace nttb200 {
 
-constexpr int N1024_WK = 1024 + 32;      /* words per padded polynomial */
+/* geometry of the two sizes */
+template <int L>
+struct WideGeom {
+  static_assert(L == 9 || L == 10, "n = 512 or 1024");
+  static constexpr int N = 1 << L;
+  static constexpr int HALVES = 1 << (L - 9);
+  static constexpr int NB = L - 6;                  /* stages of layout B (on its upper register bits) */
+  static constexpr int FIRST = 4 - NB;              /* lowest register bit of layout B that is a stage */
+  static constexpr int PADMUL = (L == 10) ? 1 : 2;  /* word i sits at i + PADMUL (i >> 5)               */
+  static constexpr int WK = N + PADMUL * (N >> 5);  /* words per padded polynomial                      */
+  /* natural index of register k of layout A for virtual lane v = (half << 5) | lane */
+  __device__ static __forceinline__ int a_index(int k, int v) { return (k << (L - 4)) | v; }
+  /* padded addresses: the lane's base plus a compile-time constant per register */
+  __device__ static __forceinline__ int a_base(int half, int lane) { return (half << 5) + lane + PADMUL * half * (L == 10); }
+  static constexpr int a_off(int k) { return (L == 10) ? 66 * k : 34 * k; }
+  __device__ static __forceinline__ int b_base(int half, int hi4, int b0) {
+    return (L == 10) ? 66 * hi4 + (half << 1) + b0 : 34 * hi4 + b0;
+  }
+  static constexpr int b_off(int k) { return (L == 10) ? 4 * k + (k >> 3) : 2 * k; }
+  __device__ static __forceinline__ int c_base(int v) { return (v << 4) + PADMUL * (v >> 1); }
+};
 
-/* four Cooley-Tukey stages on register bits 3 .. 0 with the lane's twiddles (levels 0 .. 3 of LaneTw1<8>:
- * level m holds table entries (16 << m) + (row << m) + u, u < 2^m) */
-__device__ __forceinline__ void n1024_fwd_lane(uint32_t (&x)[16], const LaneTw1<8> &tw, const SpRegs &G) {
+/* NB Cooley-Tukey stages on register bits 3 .. 4-NB with the lane's twiddles (levels 0 .. NB-1 of
+ * LaneTw1<8>: level m holds table entries (16 << m) + (row << m) + u, u < 2^m) */
+template <int NB>
+__device__ __forceinline__ void wide_fwd_lane(uint32_t (&x)[16], const LaneTw1<8> &tw, const SpRegs &G) {
 #pragma unroll
-  for (int lv = 0; lv < 4; lv++) {
+  for (int lv = 0; lv < NB; lv++) {
     const int bit = 3 - lv;
 #pragma unroll
     for (int r = 0; r < 16; r++) {
@@ -57,22 +86,23 @@ __device__ __forceinline__ void n1024_fwd_lane(uint32_t (&x)[16], const LaneTw1<
     }
   }
 }
-/* four Gentleman-Sande stages on register bits 0 .. 3; inputs are products (bound 1) */
-__device__ __forceinline__ void n1024_inv_lane(uint32_t (&x)[16], const LaneTw1<8> &tw, const SpRegs &G) {
+/* NB Gentleman-Sande stages on register bits 4-NB .. 3; inputs are products (bound 1) */
+template <int NB>
+__device__ __forceinline__ void wide_inv_lane(uint32_t (&x)[16], const LaneTw1<8> &tw, const SpRegs &G) {
 #pragma unroll
-  for (int bit = 0; bit < 4; bit++) {
+  for (int bit = 4 - NB; bit < 4; bit++) {
     const int lv = 3 - bit;
 #pragma unroll
     for (int r = 0; r < 16; r++) {
       if (r & (1 << bit)) continue;
-      const bool red = 2 * sp_leg_bound(r, bit, 1) > SP_CAP;
+      const bool red = 2 * sp_leg_bound(r, bit, 1, 4 - NB) > SP_CAP;
       sp_gs_r<false, false>(red, x[r], x[r | (1 << bit)], tw.get(0, lv, r >> (bit + 1)), G);
     }
   }
 }
 /* group multiplication of layout C: four groups of four registers, Z of group g in z[g] */
-__device__ __forceinline__ void n1024_groupmul(uint32_t (&xa)[16], const uint32_t (&xb)[16], const int (&z)[4],
-                                               const SpRegs &G) {
+__device__ __forceinline__ void wide_groupmul(uint32_t (&xa)[16], const uint32_t (&xb)[16], const int (&z)[4],
+                                              const SpRegs &G) {
 #pragma unroll
   for (int r = 0; r < 16; r += 4) {
     uint32_t a[4], lo[4], hi[4];
@@ -96,20 +126,35 @@ __device__ __forceinline__ void n1024_groupmul(uint32_t (&xa)[16], const uint32_
   }
 }
 
-template <int WARPS, int MINB, typename IO = uint32_t, typename OIO = IO>
+/* one polynomial per warp: 16-byte cp.async copies of both operands into the warp's prefetch buffers */
+template <int L, typename IO>
+__device__ __forceinline__ void wide_prefetch(IO *pa, IO *pb, const IO *ga, const IO *gb, unsigned long long poly,
+                                              int lane) {
+  constexpr int EPC = 16 / (int)sizeof(IO);
+  constexpr int CHUNKS = (1 << L) / EPC;
+  const size_t go = (size_t)poly << L;
+#pragma unroll
+  for (int c = 0; c < CHUNKS / 32; c++) {
+    const int e = (c * 32 + lane) * EPC;
+    cp_async16(reinterpret_cast<uint32_t *>(pa + e), reinterpret_cast<const uint32_t *>(ga + go + e));
+    cp_async16(reinterpret_cast<uint32_t *>(pb + e), reinterpret_cast<const uint32_t *>(gb + go + e));
+  }
+}
+
+template <int L, int WARPS, int MINB, typename IO = uint32_t, typename OIO = IO>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
-polymul_splant_n1024_kernel(const __grid_constant__ SPlantParams<4> P) {
-  constexpr int L = 10, N = 1 << L;
-  using Pg = PlantGeom<L, IO>;
-  static_assert(Pg::PSTRIDE == N && SmallGeom<L>::PPW == 1, "one polynomial per warp, rows unpadded");
+polymul_splant_wide_kernel(const __grid_constant__ SPlantParams<4> P) {
+  using W = WideGeom<L>;
+  constexpr int N = W::N;
+  constexpr int PF_WORDS = N * (int)sizeof(IO) / 4;
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  constexpr int WARP_WORDS = 2 * Pg::PF_WORDS + 2 * N1024_WK;
+  constexpr int WARP_WORDS = 2 * PF_WORDS + 2 * W::WK;
   IO *pf_a = reinterpret_cast<IO *>(smem + warp * WARP_WORDS);
-  IO *pf_b = reinterpret_cast<IO *>(smem + warp * WARP_WORDS + Pg::PF_WORDS);
-  uint32_t *wk_a = smem + warp * WARP_WORDS + 2 * Pg::PF_WORDS;
-  uint32_t *wk_b = wk_a + N1024_WK;
+  IO *pf_b = reinterpret_cast<IO *>(smem + warp * WARP_WORDS + PF_WORDS);
+  uint32_t *wk_a = smem + warp * WARP_WORDS + 2 * PF_WORDS;
+  uint32_t *wk_b = wk_a + W::WK;
   const IO *ga = static_cast<const IO *>(P.a), *gb = static_cast<const IO *>(P.b);
   OIO *gc = static_cast<OIO *>(P.c);
   SpRegs G;
@@ -130,8 +175,8 @@ polymul_splant_n1024_kernel(const __grid_constant__ SPlantParams<4> P) {
 
   const bool nowait = P.nowait != 0;
   if (nowait) asm volatile("griddepcontrol.launch_dependents;");    /* a launch that waits triggers after its wait */
-  if (nowait && tile < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile, P.batch, lane);
-  /* layout B: the lane is (i9 i8 i7 i6, i0) */
+  if (nowait && tile < ntiles) wide_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile, lane);
+  /* layout B: the lane is (the four highest index bits, i0) */
   const int hi4 = lane >> 1, b0 = lane & 1;
   LaneTw1<8> twf, twi;
   twf.load(P.tw_fwd, hi4);
@@ -139,7 +184,7 @@ polymul_splant_n1024_kernel(const __grid_constant__ SPlantParams<4> P) {
   if (!nowait) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;");
-    if (tile < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile, P.batch, lane);
+    if (tile < ntiles) wide_prefetch<L, IO>(pf_a, pf_b, ga, gb, tile, lane);
   }
 
   unsigned long long next2 = 0;
@@ -152,29 +197,30 @@ polymul_splant_n1024_kernel(const __grid_constant__ SPlantParams<4> P) {
       const IO *pf = op ? pf_b : pf_a;
       uint32_t *wk = op ? wk_b : wk_a;
 #pragma unroll 1
-      for (int half = 0; half < 2; half++) {               /* layout A, stages on bits 9 .. 6 */
+      for (int half = 0; half < W::HALVES; half++) {       /* layout A: the four highest stages */
         uint32_t x[16];
-        const int base = (half << 5) | lane;
+        const int v = (half << 5) | lane;
+        const int base = W::a_base(half, lane);
 #pragma unroll
-        for (int k = 0; k < 16; k++) x[k] = (uint32_t)pf[(k << 6) | base];
+        for (int k = 0; k < 16; k++) x[k] = (uint32_t)pf[W::a_index(k, v)];
         sp_fwd_cols<8>(x, P, G);
 #pragma unroll
-        for (int k = 0; k < 16; k++) wk[base + half + 66 * k] = x[k];
+        for (int k = 0; k < 16; k++) wk[base + W::a_off(k)] = x[k];
       }
       __syncwarp();
 #pragma unroll 1
-      for (int half = 0; half < 2; half++) {               /* layout B, stages on bits 5 .. 2 */
+      for (int half = 0; half < W::HALVES; half++) {       /* layout B: the next NB stages */
         uint32_t x[16];
-        const int base = 66 * hi4 + (half << 1) + b0;
+        const int base = W::b_base(half, hi4, b0);
 #pragma unroll
-        for (int k = 0; k < 16; k++) x[k] = wk[base + 4 * k + (k >> 3)];
-        n1024_fwd_lane(x, twf, G);
+        for (int k = 0; k < 16; k++) x[k] = wk[base + W::b_off(k)];
+        wide_fwd_lane<W::NB>(x, twf, G);
 #pragma unroll
-        for (int k = 0; k < 16; k++) wk[base + 4 * k + (k >> 3)] = x[k];
+        for (int k = 0; k < 16; k++) wk[base + W::b_off(k)] = x[k];
       }
     }
     __syncwarp();                                          /* prefetch buffers are free again */
-    if (next < ntiles) plant_prefetch<L, IO>(pf_a, pf_b, ga, gb, next, P.batch, lane);
+    if (next < ntiles) wide_prefetch<L, IO>(pf_a, pf_b, ga, gb, next, lane);
     const bool grab = dyn && rounds_left == 0;
     if (grab) {
       if (lane == 0) pend = atomicAdd(P.sched, 1ULL);
@@ -184,47 +230,51 @@ polymul_splant_n1024_kernel(const __grid_constant__ SPlantParams<4> P) {
     }
 
 #pragma unroll 1
-    for (int half = 0; half < 2; half++) {                 /* layout C: group multiplication */
+    for (int half = 0; half < W::HALVES; half++) {         /* layout C: group multiplication */
       uint32_t xa[16], xb[16];
-      const int vl = (half << 5) | lane;                   /* i9 .. i4 */
-      const int base = (vl << 4) + (vl >> 1);
+      const int v = (half << 5) | lane;                    /* index bits L-1 .. 4 */
+      const int base = W::c_base(v);
 #pragma unroll
       for (int k = 0; k < 16; k++) {
         xa[k] = wk_a[base + k];
         xb[k] = wk_b[base + k];
       }
-      const uint4 zv = __ldg(reinterpret_cast<const uint4 *>(P.zeta) + vl);
+      const uint4 zv = __ldg(reinterpret_cast<const uint4 *>(P.zeta) + v);
       const int z[4] = {(int)zv.x, (int)zv.y, (int)zv.z, (int)zv.w};
-      n1024_groupmul(xa, xb, z, G);
+      wide_groupmul(xa, xb, z, G);
 #pragma unroll
       for (int k = 0; k < 16; k++) wk_a[base + k] = xa[k];
     }
     __syncwarp();
+    constexpr int worst = sp_phase_out(4, 1, W::FIRST), mixed = sp_phase_out_mixed(4, 1, W::FIRST);
 #pragma unroll 1
-    for (int half = 0; half < 2; half++) {                 /* layout B, inverse stages on bits 2 .. 5 */
+    for (int half = 0; half < W::HALVES; half++) {         /* layout B, inverse stages */
       uint32_t x[16];
-      const int base = 66 * hi4 + (half << 1) + b0;
+      const int base = W::b_base(half, hi4, b0);
 #pragma unroll
-      for (int k = 0; k < 16; k++) x[k] = wk_a[base + 4 * k + (k >> 3)];
-      n1024_inv_lane(x, twi, G);
-      /* the register that only ever took sums goes back to the centre (polymul_splant_kernel) */
-      static_assert(sp_phase_out(4, 1) > sp_phase_out_mixed(4, 1), "register 0 is the one above the others");
-      x[0] = (uint32_t)sp_red((int)x[0], G);
+      for (int k = 0; k < 16; k++) x[k] = wk_a[base + W::b_off(k)];
+      wide_inv_lane<W::NB>(x, twi, G);
+      /* the registers that only ever took sums go back to the centre (polymul_splant_kernel) */
+      if (worst > mixed) {
 #pragma unroll
-      for (int k = 0; k < 16; k++) wk_a[base + 4 * k + (k >> 3)] = x[k];
+        for (int e = 0; e < (1 << W::FIRST); e++) x[e] = (uint32_t)sp_red((int)x[e], G);
+      }
+#pragma unroll
+      for (int k = 0; k < 16; k++) wk_a[base + W::b_off(k)] = x[k];
     }
     __syncwarp();
     OIO *cp = gc + (tile << L);
 #pragma unroll 1
-    for (int half = 0; half < 2; half++) {                 /* layout A, inverse stages on bits 6 .. 9 */
+    for (int half = 0; half < W::HALVES; half++) {         /* layout A, the last four inverse stages */
       uint32_t x[16];
-      const int base = (half << 5) | lane;
+      const int v = (half << 5) | lane;
+      const int base = W::a_base(half, lane);
 #pragma unroll
-      for (int k = 0; k < 16; k++) x[k] = wk_a[base + half + 66 * k];
-      constexpr int b_in = sp_phase_out_mixed(4, 1) > 2 ? sp_phase_out_mixed(4, 1) : 2;
+      for (int k = 0; k < 16; k++) x[k] = wk_a[base + W::a_off(k)];
+      constexpr int b_in = (worst > mixed) ? (mixed > 2 ? mixed : 2) : worst;
       sp_inv_cols<8, b_in>(x, P, G);
 #pragma unroll
-      for (int k = 0; k < 16; k++) cp[(k << 6) | base] = (OIO)x[k];
+      for (int k = 0; k < 16; k++) cp[W::a_index(k, v)] = (OIO)x[k];
     }
     __syncwarp();                                          /* shared memory reuse by the next tile */
     if (grab) next2 = dyn_base + __shfl_sync(0xffffffffu, pend, 0);

@@ -232,21 +232,27 @@ int run_splant(const nttb200_plan *P, void *c, const void *a, const void *b, siz
 }
 
 /* n = 1024: the three-layout kernel of ntt_splant_n1024.cuh (NTTB200_PLANT_N1024=0 keeps the one-layout-
- * per-phase kernel polymul_splant_kernel<10>) */
+ * per-phase kernel polymul_splant_kernel<10>).  The same kernel is instantiated for n = 512 and measured
+ * there 1.5 % SLOWER than polymul_splant_kernel<9> (654 against 665 M polymul/s; two polynomials per warp
+ * keep that loop's stalls lower, and layout C of the 9 index bits has two-way bank conflicts), so n = 512
+ * takes it only with NTTB200_PLANT_N1024=2 (the tests do). */
 #ifndef SPLANT_N1024_WARPS
 #define SPLANT_N1024_WARPS 4
 #endif
 #ifndef SPLANT_N1024_CTAS
 #define SPLANT_N1024_CTAS 3
 #endif
+#ifndef SPLANT_N512_CTAS
+#define SPLANT_N512_CTAS 6
+#endif
 int plant_n1024() {
   const char *e = getenv("NTTB200_PLANT_N1024");
-  return e ? atoi(e) != 0 : 1;
+  return e ? atoi(e) : 1;
 }
-template <typename IO = uint32_t, typename OIO = IO>
-int run_splant_n1024(const nttb200_plan *P, void *c, const void *a, const void *b, size_t batch, cudaStream_t st) {
-  constexpr int L = 10, N = 1 << L, V = 2;
-  using Pg = PlantGeom<L, IO>;
+template <int L, typename IO = uint32_t, typename OIO = IO>
+int run_splant_wide(const nttb200_plan *P, void *c, const void *a, const void *b, size_t batch, cudaStream_t st) {
+  constexpr int N = 1 << L, V = 2;
+  using W = WideGeom<L>;
   constexpr int WARPS = SPLANT_N1024_WARPS;
   const bool cyclic = (P->flags & NTTB200_PLAN_CYCLIC) != 0;
   const DevTable &fwd = cyclic ? P->fwd_plain : P->fwd_mixed;
@@ -270,15 +276,15 @@ int run_splant_n1024(const nttb200_plan *P, void *c, const void *a, const void *
     p.ufwd[i] = (size_t)i < fwd.h2.size() ? fwd.h2[i] : 0;
     p.uinv[i] = (size_t)i < inv.h2.size() ? inv.h2[i] : 0;
   }
-  auto kernel = polymul_splant_n1024_kernel<WARPS, SPLANT_N1024_CTAS, IO, OIO>;
-  const int smem = WARPS * (2 * Pg::PF_WORDS + 2 * N1024_WK) * (int)sizeof(uint32_t);
+  auto kernel = polymul_splant_wide_kernel<L, WARPS, (L == 10) ? SPLANT_N1024_CTAS : SPLANT_N512_CTAS, IO, OIO>;
+  const int smem = WARPS * (2 * (N * (int)sizeof(IO) / 4) + 2 * W::WK) * (int)sizeof(uint32_t);
   static int per_sm_dev[64] = {0};
   int &per_sm = per_sm_dev[P->device & 63];
   if (!per_sm) {
     int v = 0;
     NTT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     NTT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, WARPS * 32, smem));
-    if (v < 1) return nttb200_fail(NTTB200_ECUDA, "n = 1024 plant kernel does not fit on an SM");
+    if (v < 1) return nttb200_fail(NTTB200_ECUDA, "n = %d plant kernel does not fit on an SM", N);
     per_sm = v;
   }
   const unsigned long long tiles = batch;
@@ -368,7 +374,8 @@ int info_plant(int *regs, int *smem_bytes, int *blocks_per_sm) {
 
 int launch_polymul_small_plant(const nttb200_plan *P, uint32_t *c, const uint32_t *a, const uint32_t *b,
                                size_t batch, cudaStream_t st) {
-  if (plant_signed(P->logn) && P->logn == 10 && plant_n1024()) return run_splant_n1024<>(P, c, a, b, batch, st);
+  if (plant_signed(P->logn) && P->logn == 10 && plant_n1024()) return run_splant_wide<10>(P, c, a, b, batch, st);
+  if (plant_signed(P->logn) && P->logn == 9 && plant_n1024() >= 2) return run_splant_wide<9>(P, c, a, b, batch, st);
   if (plant_signed(P->logn)) { SPLANT_SWITCH(return (run_splant<L>(P, c, a, b, batch, st))) }
   if (plant_minb(P->logn) == 2) { PLANT_SWITCH(return (run_plant<L, 2>(P, c, a, b, batch, st))) }
   PLANT_SWITCH(return (run_plant<L, 3>(P, c, a, b, batch, st)))
@@ -376,7 +383,8 @@ int launch_polymul_small_plant(const nttb200_plan *P, uint32_t *c, const uint32_
 /* packed 16-bit operands and result (extension outside the reference API) */
 int launch_polymul_small_plant_u16(const nttb200_plan *P, uint16_t *c, const uint16_t *a, const uint16_t *b,
                                    size_t batch, cudaStream_t st) {
-  if (plant_signed(P->logn) && P->logn == 10 && plant_n1024()) return run_splant_n1024<uint16_t>(P, c, a, b, batch, st);
+  if (plant_signed(P->logn) && P->logn == 10 && plant_n1024()) return run_splant_wide<10, uint16_t>(P, c, a, b, batch, st);
+  if (plant_signed(P->logn) && P->logn == 9 && plant_n1024() >= 2) return run_splant_wide<9, uint16_t>(P, c, a, b, batch, st);
   if (plant_signed(P->logn)) { SPLANT_SWITCH(return (run_splant<L, uint16_t>(P, c, a, b, batch, st))) }
   PLANT_SWITCH(return (run_plant<L, 2, uint16_t>(P, c, a, b, batch, st)))
 }
@@ -384,7 +392,8 @@ int launch_polymul_small_plant_u16(const nttb200_plan *P, uint16_t *c, const uin
  * the host and lets the kernel write the caller's int32 rows (nttb200.cu, polymul_batch_wire) */
 int launch_polymul_small_plant_u16in(const nttb200_plan *P, uint32_t *c, const uint16_t *a, const uint16_t *b,
                                      size_t batch, cudaStream_t st) {
-  if (plant_signed(P->logn) && P->logn == 10 && plant_n1024()) return run_splant_n1024<uint16_t, uint32_t>(P, c, a, b, batch, st);
+  if (plant_signed(P->logn) && P->logn == 10 && plant_n1024()) return run_splant_wide<10, uint16_t, uint32_t>(P, c, a, b, batch, st);
+  if (plant_signed(P->logn) && P->logn == 9 && plant_n1024() >= 2) return run_splant_wide<9, uint16_t, uint32_t>(P, c, a, b, batch, st);
   if (plant_signed(P->logn)) { SPLANT_SWITCH(return (run_splant<L, uint16_t, uint32_t>(P, c, a, b, batch, st))) }
   PLANT_SWITCH(return (run_plant<L, 2, uint16_t, uint32_t>(P, c, a, b, batch, st)))
 }

@@ -119,14 +119,18 @@ def test_config2_batch_2e16_vs_all_four_reference_variants(plan256, oracle, load
 
 @pytest.mark.parametrize("n,q", [(8, 17), (16, 97), (32, 193), (64, 257), (128, 3329), (256, 12289),
                                  (256, 7681), (512, 12289), (1024, 12289), (256, 10753), (128, 12289)])
-@pytest.mark.parametrize("signed", [0, 1])
+@pytest.mark.parametrize("signed", [0, 1, 2])
 def test_half_word_moduli_plantard_vs_shoup_kernels(gpu, oracle, monkeypatch, n, q, signed):
-    """q <= 12385: the product runs the Plantard kernel (ntt_small_plant.cuh; with
-    NTTB200_PLANT_SIGNED=1 and n <= 256 the signed five-instruction-butterfly kernel of
-    ntt_small_splant.cuh); the same plan with NTTB200_PLAN_NO_PLANTARD runs the Shoup/Montgomery
-    kernel.  All against the oracle, with worst-case rows (all q-1 and alternating 0 / q-1: every
+    """q <= 12385: the product runs a Plantard kernel -- signed = 1: the default signed kernels
+    (ntt_small_splant.cuh, ntt_splant_n1024.cuh at n = 1024); 0: the unsigned kernel of
+    ntt_small_plant.cuh (NTTB200_PLANT_SIGNED=0); 2: at n >= 512 the OTHER signed kernel of the size --
+    the same plan with NTTB200_PLAN_NO_PLANTARD runs the Shoup/Montgomery kernel.  All against the oracle, with worst-case rows (all q-1 and alternating 0 / q-1: every
     lazy bound is attained) and ragged batch sizes."""
-    monkeypatch.setenv("NTTB200_PLANT_SIGNED", str(signed))
+    if signed == 2:          # n >= 512: the other signed kernel of each size (one layout per phase at n = 1024,
+        if n < 512:          # three layouts at n = 512)
+            pytest.skip("one signed kernel below n = 512")
+        monkeypatch.setenv("NTTB200_PLANT_N1024", "0" if n == 1024 else "2")
+    monkeypatch.setenv("NTTB200_PLANT_SIGNED", "1" if signed else "0")
     pl, sh = gpu.Plan(n, q), gpu.Plan(n, q, no_plantard=True)
     assert "plantard" in pl.describe() and "plantard" not in sh.describe()
     for batch in (1, 2, 31, 32, 33, 257, 1031):
