@@ -15,34 +15,35 @@
  * index bits in registers per layout it takes three layouts of the 10 index bits i9 .. i0:
  *
  *      layout A   registers i9 i8 i7 i6   half i5          lane i4 .. i0        stages on bits 9 .. 6
- *      layout B   registers i5 i4 i3 i2   half i1          lane i9 .. i6, i0    stages on bits 5 .. 2
+ *      layout B   registers i5 i4 i3 i2   half i0          lane i9 .. i6, i1    stages on bits 5 .. 2
  *      layout C   registers i3 i2 i1 i0   half i9          lane i8 .. i4        group multiplication
  *
  * (forward A -> B -> C, inverse C -> B -> A; dataflow of R/NTT/ntt.C:342-371 and 428-451 as in
  * ntt_small_splant.cuh).  The polynomial lives in the warp's shared memory between the phases, every
  * phase reads the 16 words it owns and writes the same 16 words back, so the only synchronisation is
- * __syncwarp between phases.  Word i sits at  i + (i >> 5)  (one word of padding per 32): every access of
- * every layout is then conflict-free (A: 32 consecutive words; B: bank = 2 (i9 i8 i7 i6) + i0 + const;
- * C: bank = 16 i4 + 2 (i8 i7 i6) + i5 + const) and the address of register k is the lane's base plus a
- * compile-time constant (A: 66 k, B: 4 k + (k >> 3), C: k), so no access costs address arithmetic.  Layout A reads the
+ * __syncwarp between phases.  Word i sits at  i + 2 (i >> 5)  (two words of padding per 32, so even words stay
+ * even): layout A reads 32 consecutive words per register; layout B reads the pair i0 = 0, 1 -- its two
+ * halves -- as ONE 64-bit word per register (per half-warp: banks 4 (i8 i7 i6) + 2 i1 + const, conflict-free);
+ * layout C reads its 16 consecutive words as eight 64-bit words (per half-warp: banks 16 i4 + 2 (i7 i6 i5) +
+ * const, conflict-free); and the address of register k is the lane's base plus a compile-time constant
+ * (A: 68 k, B: 4 k + 2 (k >> 3), C: k), so no access costs address arithmetic.  Layout A reads the
  * operands straight from the cp.async prefetch buffer and writes the result straight to global memory, 128
  * contiguous bytes per register.  The twiddles of layout A are constant-bank operands (table entries 1 ..
  * 15), those of layout B depend on i9 .. i6 only, i.e. on the lane and not on the half: 15 + 15 words per
  * lane held in registers for the whole kernel; the four Z of layout C are one 16-byte load per half.
  *
- * Price: five more trips through shared memory per coefficient (14 against 9 scalar-equivalent accesses):
- * 3 382 instead of 3 087 warp instructions per polynomial (+9.6 %).  The loop is 1 426 instructions =
- * 23 KB, 80 registers.  Measured on B200 (profiles/r2_c4_splant_n1024_ncu_full.txt): `no_instruction`
- * drops from 1.45 to 0.11 warps per issue cycle, issue slots 69.5 % -> 83.2 % busy (3.33 instructions per
- * clock and SM, what the n = 256 kernel reaches), c4 279.5 -> 286 M polymul/s.
+ * Price: three more trips through shared memory per coefficient: 3 194 instead of 3 087 warp instructions
+ * per polynomial (3 382 with 32-bit accesses everywhere).  The loop is 1 727 instructions = 28 KB, 95
+ * registers.  Measured on B200 (profiles/r2_c4_splant_wide_v2_ncu_full.txt): `no_instruction` drops from 1.45
+ * to 0.10 warps per issue cycle, issue slots 69.5 % -> 83.1 % busy (3.32 instructions per clock and SM, what
+ * the n = 256 kernel reaches), c4 279.5 -> 302 M polymul/s.
  *
  * n = 512 can run the same kernel (NTTB200_PLANT_N1024=2; measured 1.5 % slower than the one-layout-per-phase
  * kernel there, so it is not the default) with 32 virtual lanes (no halves) and three stages in layout B:
  *      layout A   registers i8 i7 i6 i5   lane i4 .. i0          stages on bits 8 .. 5
  *      layout B   registers i4 i3 i2 i1   lane i8 .. i5, i0      stages on bits 4 .. 2 (i1 rides along)
  *      layout C   registers i3 i2 i1 i0   lane i8 .. i4          group multiplication
- * word i at i + 2 (i >> 5): A and B are conflict-free, C has two-way conflicts (no padding of this
- * additive family serves all three layouts of the 9 index bits; searched exhaustively).
+ * (32-bit accesses in B: its register pairs are not adjacent words).
  */
 #pragma once
 #include <stdint.h>
@@ -58,17 +59,18 @@ struct WideGeom {
   static constexpr int HALVES = 1 << (L - 9);
   static constexpr int NB = L - 6;                  /* stages of layout B (on its upper register bits) */
   static constexpr int FIRST = 4 - NB;              /* lowest register bit of layout B that is a stage */
-  static constexpr int PADMUL = (L == 10) ? 1 : 2;  /* word i sits at i + PADMUL (i >> 5)               */
-  static constexpr int WK = N + PADMUL * (N >> 5);  /* words per padded polynomial                      */
+  static constexpr int PADMUL = 2;                  /* word i sits at i + 2 (i >> 5): even words stay even  */
+  static constexpr int WK = N + PADMUL * (N >> 5);  /* words per padded polynomial                          */
   /* natural index of register k of layout A for virtual lane v = (half << 5) | lane */
   __device__ static __forceinline__ int a_index(int k, int v) { return (k << (L - 4)) | v; }
   /* padded addresses: the lane's base plus a compile-time constant per register */
-  __device__ static __forceinline__ int a_base(int half, int lane) { return (half << 5) + lane + PADMUL * half * (L == 10); }
-  static constexpr int a_off(int k) { return (L == 10) ? 66 * k : 34 * k; }
-  __device__ static __forceinline__ int b_base(int half, int hi4, int b0) {
-    return (L == 10) ? 66 * hi4 + (half << 1) + b0 : 34 * hi4 + b0;
-  }
-  static constexpr int b_off(int k) { return (L == 10) ? 4 * k + (k >> 3) : 2 * k; }
+  __device__ static __forceinline__ int a_base(int half, int lane) { return 34 * half + lane; }
+  static constexpr int a_off(int k) { return (L == 10) ? 68 * k : 34 * k; }
+  /* layout B.  n = 1024: the lane is (i9 .. i6, i1) and reads the PAIR i0 = 0, 1 -- the two halves -- as one
+   * 64-bit word; n = 512: the lane is (i8 .. i5, i0), 32-bit accesses */
+  __device__ static __forceinline__ int b_base(int hi4, int low) { return (L == 10) ? 68 * hi4 + 2 * low : 34 * hi4 + low; }
+  static constexpr int b_off(int k) { return (L == 10) ? 4 * k + 2 * (k >> 3) : 2 * k; }
+  /* layout C: 16 consecutive words from an even address, read and written as 64-bit words */
   __device__ static __forceinline__ int c_base(int v) { return (v << 4) + PADMUL * (v >> 1); }
 };
 
@@ -208,10 +210,22 @@ polymul_splant_wide_kernel(const __grid_constant__ SPlantParams<4> P) {
         for (int k = 0; k < 16; k++) wk[base + W::a_off(k)] = x[k];
       }
       __syncwarp();
-#pragma unroll 1
-      for (int half = 0; half < W::HALVES; half++) {       /* layout B: the next NB stages */
+      if (L == 10) {                                       /* layout B: both halves from 64-bit words */
+        uint32_t x0[16], x1[16];
+        const int base = W::b_base(hi4, b0);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          const uint2 v = *reinterpret_cast<const uint2 *>(wk + base + W::b_off(k));
+          x0[k] = v.x;
+          x1[k] = v.y;
+        }
+        wide_fwd_lane<W::NB>(x0, twf, G);
+        wide_fwd_lane<W::NB>(x1, twf, G);
+#pragma unroll
+        for (int k = 0; k < 16; k++) *reinterpret_cast<uint2 *>(wk + base + W::b_off(k)) = make_uint2(x0[k], x1[k]);
+      } else {                                             /* layout B: the next NB stages */
         uint32_t x[16];
-        const int base = W::b_base(half, hi4, b0);
+        const int base = W::b_base(hi4, b0);
 #pragma unroll
         for (int k = 0; k < 16; k++) x[k] = wk[base + W::b_off(k)];
         wide_fwd_lane<W::NB>(x, twf, G);
@@ -235,26 +249,47 @@ polymul_splant_wide_kernel(const __grid_constant__ SPlantParams<4> P) {
       const int v = (half << 5) | lane;                    /* index bits L-1 .. 4 */
       const int base = W::c_base(v);
 #pragma unroll
-      for (int k = 0; k < 16; k++) {
-        xa[k] = wk_a[base + k];
-        xb[k] = wk_b[base + k];
+      for (int k = 0; k < 16; k += 2) {
+        const uint2 va = *reinterpret_cast<const uint2 *>(wk_a + base + k);
+        const uint2 vb = *reinterpret_cast<const uint2 *>(wk_b + base + k);
+        xa[k] = va.x; xa[k + 1] = va.y;
+        xb[k] = vb.x; xb[k + 1] = vb.y;
       }
       const uint4 zv = __ldg(reinterpret_cast<const uint4 *>(P.zeta) + v);
       const int z[4] = {(int)zv.x, (int)zv.y, (int)zv.z, (int)zv.w};
       wide_groupmul(xa, xb, z, G);
 #pragma unroll
-      for (int k = 0; k < 16; k++) wk_a[base + k] = xa[k];
+      for (int k = 0; k < 16; k += 2) *reinterpret_cast<uint2 *>(wk_a + base + k) = make_uint2(xa[k], xa[k + 1]);
     }
     __syncwarp();
     constexpr int worst = sp_phase_out(4, 1, W::FIRST), mixed = sp_phase_out_mixed(4, 1, W::FIRST);
-#pragma unroll 1
-    for (int half = 0; half < W::HALVES; half++) {         /* layout B, inverse stages */
+    if (L == 10) {                                         /* layout B, inverse stages, both halves */
+      uint32_t x0[16], x1[16];
+      const int base = W::b_base(hi4, b0);
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(wk_a + base + W::b_off(k));
+        x0[k] = v.x;
+        x1[k] = v.y;
+      }
+      wide_inv_lane<W::NB>(x0, twi, G);
+      wide_inv_lane<W::NB>(x1, twi, G);
+      /* the registers that only ever took sums go back to the centre (polymul_splant_kernel) */
+      if (worst > mixed) {
+#pragma unroll
+        for (int e = 0; e < (1 << W::FIRST); e++) {
+          x0[e] = (uint32_t)sp_red((int)x0[e], G);
+          x1[e] = (uint32_t)sp_red((int)x1[e], G);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 16; k++) *reinterpret_cast<uint2 *>(wk_a + base + W::b_off(k)) = make_uint2(x0[k], x1[k]);
+    } else {                                               /* layout B, inverse stages */
       uint32_t x[16];
-      const int base = W::b_base(half, hi4, b0);
+      const int base = W::b_base(hi4, b0);
 #pragma unroll
       for (int k = 0; k < 16; k++) x[k] = wk_a[base + W::b_off(k)];
       wide_inv_lane<W::NB>(x, twi, G);
-      /* the registers that only ever took sums go back to the centre (polymul_splant_kernel) */
       if (worst > mixed) {
 #pragma unroll
         for (int e = 0; e < (1 << W::FIRST); e++) x[e] = (uint32_t)sp_red((int)x[e], G);

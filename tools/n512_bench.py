@@ -8,7 +8,8 @@ m = importlib.import_module("ntt-based-polynomial-multiplier-fpga_b200")
 n, q, rows, sets = 512, 12289, 1 << 19, 6
 st = torch.cuda.current_stream().cuda_stream
 bufs = [tuple(torch.randint(0, q, (rows, n), dtype=torch.int32, device="cuda") for _ in range(3)) for _ in range(sets)]
-for tag, env in (("wide", {}), ("one-layout", {"NTTB200_PLANT_N1024": "0"}), ("unsigned", {"NTTB200_PLANT_SIGNED": "0"})):
+for tag, env in (("three-layout", {"NTTB200_PLANT_N1024": "2"}), ("one-layout", {"NTTB200_PLANT_N1024": "1"}),
+                 ("unsigned", {"NTTB200_PLANT_SIGNED": "0"})):
     for k in ("NTTB200_PLANT_N1024", "NTTB200_PLANT_SIGNED"):
         os.environ.pop(k, None)
     os.environ.update(env)
@@ -26,5 +27,5 @@ for tag, env in (("wide", {}), ("one-layout", {"NTTB200_PLANT_N1024": "0"}), ("u
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print(f"n=512 {tag:11s} {rows * steps / ms / 1e3:8.1f} M polymul/s   hbm frac {rows * steps / (ms * 1e-3) * 12 * n / 6537.3e9:.3f}  {p.describe()}")
+    print(f"n=512 {tag:13s} {rows * steps / ms / 1e3:8.1f} M polymul/s   hbm frac {rows * steps / (ms * 1e-3) * 12 * n / 6537.3e9:.3f}  {p.describe()}")
     p.close()
