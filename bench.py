@@ -54,10 +54,10 @@ WORKLOADS = {
 }
 # DRAM bytes (read + write) per launch of the dominant kernel, from `ncu --set full` captures
 # committed under profiles/ (a profiler run is never a bench value; this is the traffic only)
-TRAFFIC_NCU = {"c2": 134259456 + 37774592, "c4": 2147519000 + 1041052000}
+TRAFFIC_NCU = {"c2": 134259456 + 37774592, "c4": 2147520000 + 1040470000}
 TRAFFIC_SRC = {"c2": "profiles/r2_c2_splant_inc_ncu_full.txt: dram__bytes_read.sum 134.26 MB + "
                      "dram__bytes_write.sum 37.77 MB per launch (algorithmic 201.3 MB; part of c stays dirty in L2)",
-               "c4": "profiles/r2_c4_splant_n1024_ncu_full.txt: 2.148 GB read + 1.041 GB written per launch (algorithmic 3.221 GB)"}
+               "c4": "profiles/r2_c4_splant_wide_v2_ncu_full.txt: 2.148 GB read + 1.040 GB written per launch (algorithmic 3.221 GB)"}
 SEED = 0x4E545442323030
 L2_BYTES = 126 * 1000 * 1000
 
@@ -759,9 +759,11 @@ def main() -> int:
                                "large-n product pipeline (whole step)",
                      "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": roof_ms,
                      "traffic_source": TRAFFIC_SRC.get(args.workload)},
-        "int_roofline": {"bound": "multiplier (fmaheavy) pipe; the n<=256 Plantard kernel trades multiplier slots for "
-                                  "ALU instructions, so issue slots and the two integer pipes are near level "
-                                  "(ncu, profiles/): read this fraction next to roofline.frac, not as the binding one",
+        "int_roofline": {"bound": "integer pipes / issue slots: the signed Plantard kernels level their instructions over "
+                                  "the multiplier (fmaheavy) and ALU pipes and run at 82 - 83 % of the issue slots "
+                                  "(ncu, profiles/); `frac` counts the multiplier slots the kernel spends, "
+                                  "survey_3_per_modmul the 3 IMAD per modular multiplication of SURVEY 8d: read both "
+                                  "next to roofline.frac, neither is the binding one",
                          "achieved": slot_achieved, "peak": imad_peak, "unit": "IMAD-slot lane-ops/s",
                          "frac": slot_achieved / imad_peak if imad_peak else None,
                          "slots_per_polymul": slots,
