@@ -321,7 +321,7 @@ def slots_per_polymul(n: int, plantard: bool, signed: bool = False) -> int:
     measured half rate) + 2 IMAD; pointwise Montgomery = 2 IMAD.HI + 2 IMAD; the n^-1 scaling costs one
     extra multiplication on the sum branch of the last stage.  Plantard (q <= 12385): butterfly 3,
     pointwise 4, scale 3; at n <= 256 butterfly and scale 2 (IMAD, SHF, IMAD, SHF).  Signed Plantard
-    kernels (ntt_small_splant.cuh, ntt_splant_n1024.cuh: the default): L - 2 stages per transform with 2
+    kernels (ntt_small_splant.cuh, ntt_splant_wide.cuh: the default): L - 2 stages per transform with 2
     multiplications per butterfly, 4 in the butterflies of the last inverse stage, and per group of four
     coefficients 4 Barrett steps (2 each), 16 + 3 raw products and 7 reductions (2 each): n (3 L + 5.25)."""
     bflies = 3 * (n // 2) * (n.bit_length() - 1)

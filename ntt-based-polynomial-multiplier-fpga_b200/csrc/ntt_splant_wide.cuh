@@ -1,5 +1,5 @@
 /*
- * ntt_splant_n1024.cuh -- fused product kernel for n = 1024 (and n = 512), half-word moduli: the arithmetic of
+ * ntt_splant_wide.cuh -- fused product kernel for n = 1024 (and n = 512), half-word moduli: the arithmetic of
  * ntt_small_splant.cuh (signed Plantard, five-instruction butterflies, two stages left to a group
  * multiplication) in a geometry whose code FITS THE INSTRUCTION CACHE.
  *

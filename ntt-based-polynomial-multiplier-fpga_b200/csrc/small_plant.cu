@@ -6,7 +6,7 @@
 
 #include "ntt_small_plant.cuh"
 #include "ntt_small_splant.cuh"
-#include "ntt_splant_n1024.cuh"
+#include "ntt_splant_wide.cuh"
 #include "plan.h"
 
 namespace {
@@ -231,7 +231,7 @@ int run_splant(const nttb200_plan *P, void *c, const void *a, const void *b, siz
   return 0;
 }
 
-/* n = 1024: the three-layout kernel of ntt_splant_n1024.cuh (NTTB200_PLANT_N1024=0 keeps the one-layout-
+/* n = 1024: the three-layout kernel of ntt_splant_wide.cuh (NTTB200_PLANT_N1024=0 keeps the one-layout-
  * per-phase kernel polymul_splant_kernel<10>).  The same kernel is instantiated for n = 512 and measured
  * there 1.5 % SLOWER than polymul_splant_kernel<9> (654 against 665 M polymul/s; two polynomials per warp
  * keep that loop's stalls lower, and layout C of the 9 index bits has two-way bank conflicts), so n = 512

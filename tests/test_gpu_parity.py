@@ -122,7 +122,7 @@ def test_config2_batch_2e16_vs_all_four_reference_variants(plan256, oracle, load
 @pytest.mark.parametrize("signed", [0, 1, 2])
 def test_half_word_moduli_plantard_vs_shoup_kernels(gpu, oracle, monkeypatch, n, q, signed):
     """q <= 12385: the product runs a Plantard kernel -- signed = 1: the default signed kernels
-    (ntt_small_splant.cuh, ntt_splant_n1024.cuh at n = 1024); 0: the unsigned kernel of
+    (ntt_small_splant.cuh, ntt_splant_wide.cuh at n = 1024); 0: the unsigned kernel of
     ntt_small_plant.cuh (NTTB200_PLANT_SIGNED=0); 2: at n >= 512 the OTHER signed kernel of the size --
     the same plan with NTTB200_PLAN_NO_PLANTARD runs the Shoup/Montgomery kernel.  All against the oracle, with worst-case rows (all q-1 and alternating 0 / q-1: every
     lazy bound is attained) and ragged batch sizes."""
