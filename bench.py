@@ -566,6 +566,7 @@ def main() -> int:
     plan, bufs, sets, stream = W.plan, W.bufs, W.sets, W.stream
     row_bytes = n * 4
     ms, ms_local, clocks = W.timed(args.steps, warmup, local)
+    rank_ms = sh.gather_over_ranks(ms_local, dev) if world > 1 else [ms_local]
     launches_per_step = W.launches_per_step
     value = world * batch * args.steps / (ms * 1e-3)
     parity_ok, parity_checker, parity_rows = W.parity(args.steps - 1, 4096 if n <= 1024 else 24)
@@ -749,6 +750,7 @@ def main() -> int:
                          "mode": os.environ.get("NTTB200_WIRE", "auto")},
                 "host_bytes_per_step": 3 * batch * row_bytes, "parity_ok": e2e_ok},
         "gpu_launches": launches_per_step * args.steps,
+        "rank_ms": rank_ms,       # device time of the K steps on every rank; `value` uses their maximum
         "clocks": clocks,
         "sustained": sustained,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",

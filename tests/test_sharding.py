@@ -40,7 +40,8 @@ def _worker(rank, world, port, q):
     c = O.product(n, qq, a[lo:hi], b[lo:hi], 10)                       # stand-in for the GPU call
     t = sh.max_over_ranks(float(rank + 1))
     done = sh.sum_over_ranks(float(hi - lo))
-    q.put((rank, lo, hi, c.tolist(), t, done))
+    every = sh.gather_over_ranks(float(10 * rank + 1))
+    q.put((rank, lo, hi, c.tolist(), t, done, every))
     dist.destroy_process_group()
 
 
@@ -67,6 +68,7 @@ def test_two_ranks_gloo():
     assert [r[1:3] for r in res] == [(0, 5), (5, 10)]
     assert all(r[4] == 2.0 for r in res)             # max over ranks
     assert all(r[5] == 10.0 for r in res)            # units processed by all ranks
+    assert all(r[6] == [1.0, 11.0] for r in res)     # every rank's value, in rank order
 
 
 def test_c_shard_bounds_match_the_python_partition(nttb200):
