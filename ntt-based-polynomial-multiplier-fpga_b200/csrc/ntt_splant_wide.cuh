@@ -10,8 +10,9 @@
  * profiles/r2_c4_splant_ncu_full.txt).
  *
  * Geometry: still one warp per polynomial, but 16 registers per "virtual lane" and 64 virtual lanes: the
- * warp runs every phase twice (a rolled loop over the two halves of the virtual lanes, same code) and the
- * two operands of the forward transform through ONE copy of the code (a rolled loop over a, b).  With 4
+ * warp runs every phase for both halves of the virtual lanes (layouts A and C: a rolled loop, same code;
+ * layout B: both halves at once, their elements arrive paired in 64-bit words) and the two operands of the
+ * forward transform through ONE copy of the code (a rolled loop over a, b).  With 4
  * index bits in registers per layout it takes three layouts of the 10 index bits i9 .. i0:
  *
  *      layout A   registers i9 i8 i7 i6   half i5          lane i4 .. i0        stages on bits 9 .. 6
@@ -38,8 +39,8 @@
  * to 0.10 warps per issue cycle, issue slots 69.5 % -> 83.1 % busy (3.32 instructions per clock and SM, what
  * the n = 256 kernel reaches), c4 279.5 -> 302 M polymul/s.
  *
- * n = 512 can run the same kernel (NTTB200_PLANT_N1024=2; measured 1.5 % slower than the one-layout-per-phase
- * kernel there, so it is not the default) with 32 virtual lanes (no halves) and three stages in layout B:
+ * n = 512 can run the same kernel (NTTB200_PLANT_N1024=2; measured level with the one-layout-per-phase
+ * kernel there, 655 against 659 M polymul/s, so that one stays the default) with 32 virtual lanes (no halves) and three stages in layout B:
  *      layout A   registers i8 i7 i6 i5   lane i4 .. i0          stages on bits 8 .. 5
  *      layout B   registers i4 i3 i2 i1   lane i8 .. i5, i0      stages on bits 4 .. 2 (i1 rides along)
  *      layout C   registers i3 i2 i1 i0   lane i8 .. i4          group multiplication

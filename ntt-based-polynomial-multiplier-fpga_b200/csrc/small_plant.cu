@@ -233,9 +233,8 @@ int run_splant(const nttb200_plan *P, void *c, const void *a, const void *b, siz
 
 /* n = 1024: the three-layout kernel of ntt_splant_wide.cuh (NTTB200_PLANT_N1024=0 keeps the one-layout-
  * per-phase kernel polymul_splant_kernel<10>).  The same kernel is instantiated for n = 512 and measured
- * there 1.5 % SLOWER than polymul_splant_kernel<9> (654 against 665 M polymul/s; two polynomials per warp
- * keep that loop's stalls lower, and layout C of the 9 index bits has two-way bank conflicts), so n = 512
- * takes it only with NTTB200_PLANT_N1024=2 (the tests do). */
+ * there level with polymul_splant_kernel<9> (655 against 659 M polymul/s), so n = 512 takes it only with
+ * NTTB200_PLANT_N1024=2 (the tests do). */
 #ifndef SPLANT_N1024_WARPS
 #define SPLANT_N1024_WARPS 4
 #endif
