@@ -1160,3 +1160,40 @@ def test_asynchronous_host_buffer_products_equal_the_synchronous_call(gpu, oracl
             for h in keep:
                 h.free()
     p.close()
+
+
+def test_asynchronous_products_from_several_threads(gpu, oracle):
+    """Four threads queue and wait for host-buffer products on ONE plan at the same time (submission is
+    serialised inside the library, the worker runs one stream of jobs), with synchronous calls thrown in:
+    every thread gets its own results back."""
+    import threading
+    n, q = 256, 12289
+    p = gpu.Plan(n, q)
+    errors = []
+
+    def work(tid):
+        try:
+            rng = np.random.default_rng(1000 + tid)
+            for it in range(6):
+                rows = int(rng.choice([5, 300, 2048, 4096, 9000]))
+                a, b = oracle.random((rows, n), q, 7 * tid + it), oracle.random((rows, n), q, 900 + 7 * tid + it)
+                c = np.full((rows, n), -1, np.int32)
+                if it % 3 == 2:
+                    c = p.polymul(a, b)
+                else:
+                    t = p.polymul_async_ptr(c.ctypes.data, a.ctypes.data, b.ctypes.data, rows)
+                    p.wait(t)
+                pick = np.unique(np.r_[0, rows - 1, rng.integers(0, rows, 12)])
+                if not (c[pick] == oracle.product(n, q, a[pick], b[pick], 10)).all():
+                    errors.append((tid, it, rows))
+        except Exception as ex:                     # noqa: BLE001 -- reported by the main thread
+            errors.append((tid, repr(ex)))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    p.wait(0)
+    p.close()
