@@ -321,13 +321,13 @@ def slots_per_polymul(n: int, plantard: bool, signed: bool = False) -> int:
     measured half rate) + 2 IMAD; pointwise Montgomery = 2 IMAD.HI + 2 IMAD; the n^-1 scaling costs one
     extra multiplication on the sum branch of the last stage.  Plantard (q <= 12385): butterfly 3,
     pointwise 4, scale 3; at n <= 256 butterfly and scale 2 (IMAD, SHF, IMAD, SHF).  Signed Plantard
-    kernels (ntt_small_splant.cuh, ntt_splant_wide.cuh: the default): L - 2 stages per transform with 2
-    multiplications per butterfly, 4 in the butterflies of the last inverse stage, and per group of four
-    coefficients 4 Barrett steps (2 each), 16 + 3 raw products and 7 reductions (2 each): n (3 L + 5.25)."""
+    kernels (ntt_small_splant.cuh, ntt_splant_wide.cuh: the default): L - 3 stages per transform with 2
+    multiplications per butterfly, 4 in the butterflies of the last inverse stage, and per group of eight
+    coefficients 8 Barrett steps (2 each), 64 + 7 raw products and 15 reductions (2 each): n (3 L + 7.125)."""
     bflies = 3 * (n // 2) * (n.bit_length() - 1)
     L = n.bit_length() - 1
     if plantard and signed:
-        return 2 * n * (L - 2) + (n // 4) * 41 + n * (L - 3) + 2 * n
+        return 2 * n * (L - 3) + (n // 8) * 117 + n * (L - 4) + 2 * n
     if plantard and n <= 256:
         return 2 * bflies + 4 * n + 2 * (n // 2)
     if plantard:

@@ -97,8 +97,11 @@ __device__ __forceinline__ int sp_red(int x, const SpRegs &G) {
 __host__ __device__ constexpr bool sp_use_mad(int i) {
   return SPLANT_MAD_NUM > 0 && (i % SPLANT_MAD_DEN) < SPLANT_MAD_NUM;
 }
-/* CT: X' = X + T, Y' = X - T = 2X - X' */
-__device__ __forceinline__ void sp_ct(uint32_t &X, uint32_t &Y, uint32_t wt, const SpRegs &G, bool mad = false) {
+/* CT: X' = X + T, Y' = X - T = 2X - X'.  redx: X takes a Barrett step first, so that both results are within
+ * q + 20 of zero (the last forward stage ahead of a group multiplication of eight, see SpDrop) */
+__device__ __forceinline__ void sp_ct(uint32_t &X, uint32_t &Y, uint32_t wt, const SpRegs &G, bool mad = false,
+                                      bool redx = false) {
+  if (redx) X = (uint32_t)sp_red((int)X, G);
   const int u = sp_mul_u((int)Y, wt, G);
   const int xn = (int)X + (u >> 16);
   if (mad) {
@@ -180,7 +183,7 @@ __host__ __device__ constexpr int sp_phase_out_mixed(int bits, int b_in, int fir
   return worst;
 }
 
-/* ---- incomplete transform (SPLANT_INCOMPLETE = number of stages left out, default 2) -------------
+/* ---- incomplete transform (SPLANT_INCOMPLETE = number of stages left out, default 3) -------------
  * The last D forward stages, the pointwise product and the first D inverse stages are replaced by one
  * multiplication of polynomials of degree 2^D - 1 per group of 2^D registers: before its last D stages
  * the Cooley-Tukey network holds a_0 + a_1 x + ... in Z_q[x]/(x^(2^D) - w^2) in the group at positions
@@ -196,17 +199,27 @@ __host__ __device__ constexpr int sp_phase_out_mixed(int bits, int b_in, int fir
  * D = 1: 23 instructions per pair against 2 x 5 (butterflies of a and b) + 2 x 8 (pointwise) + 6
  * (inverse butterfly) = 32; D = 2: 59 per group of four against 2 x 23 + 20 + 12 = 78 (measured: c2
  * 1 371 -> 1 473 M polymul/s with D = 1); and the lane phase keeps a half / a quarter of the twiddles.
- * D = 3 does not fit: redc(x) = ((x q^-1 >> 16) q + D) >> 16 needs |x| <= M = 11.5 q^2 (header), and
+ * D = 3 does not fit THIS WAY: redc(x) = ((x q^-1 >> 16) q + D) >> 16 needs |x| <= M = 11.5 q^2 (header), and
  * with |b| <= (L + 2 - D) q / 2 a sum of 2^D products reaches 2^D (q/2 + 20)(L + 2 - D) q / 2 + q^2 / 4
- * = 10.3 q^2 at n = 1024, D = 2 (run_splant checks it), 14 q^2 at D = 3. */
+ * = 10.3 q^2 at n = 1024, D = 2 (run_splant checks it), 14 q^2 at D = 3 -- see XR below for how it does. */
 #ifndef SPLANT_INCOMPLETE
-#define SPLANT_INCOMPLETE 2
+#define SPLANT_INCOMPLETE 3
 #endif
+/* THREE stages (groups of eight, degree-7 polynomials mod x^8 - w^2) fit after all if BOTH operands come
+ * out of the forward transform small: the X leg of every butterfly of the last forward stage takes the
+ * Barrett step (as many Barrett steps as reducing all of a: n per product), so both results of that stage
+ * are within q + 20 of zero, a sum of eight products stays below 8.03 q^2 + q^2/4 < M = 11.5 q^2, and the
+ * group multiplication needs no Barrett step of its own.  64 + 7 products, 15 reductions and the 8 Barrett
+ * steps: 155 instructions per eight coefficients against 182 for two groups of four and the stage between
+ * them (XR below; run_splant checks the bound for the plan's q). */
 template <int L>
 struct SpDrop {
   static constexpr int H = SmallGeom<L>::H;
   static constexpr int V = SPLANT_INCOMPLETE < H ? SPLANT_INCOMPLETE : H;    /* stages left out */
   static constexpr int D = 1 << V;                                           /* registers per group */
+  static constexpr bool XR = (V >= 3);           /* operands reduced by the last forward stage, not by the group */
+  static constexpr bool XR_ROWS = XR && (H - V > 0);   /* that stage is the last one of the lane phase ...     */
+  static constexpr bool XR_COLS = XR && (H - V == 0);  /* ... or of the register phase on the high index bits  */
 };
 
 /* per-lane twiddles of the lane phase, levels 0 .. H-1-V (LaneTw1 holds all H levels) */
@@ -297,7 +310,7 @@ __device__ __forceinline__ void sp_groupmul(uint32_t (&xa)[SmallGeom<L>::NV], co
   for (int r = 0; r < Gm::NV; r += D) {
     uint32_t a[D], lo[D], hi[D];
 #pragma unroll
-    for (int i = 0; i < D; i++) a[i] = (uint32_t)sp_red((int)xa[r + i], G);
+    for (int i = 0; i < D; i++) a[i] = SpDrop<L>::XR ? xa[r + i] : (uint32_t)sp_red((int)xa[r + i], G);
     const uint32_t zeta = (uint32_t)zt.get(r >> Gm::H, (r & (Gm::T - 1)) >> V);
 #pragma unroll
     for (int k = 0; k < D; k++) { lo[k] = 0; hi[k] = 0; }
@@ -316,7 +329,7 @@ __device__ __forceinline__ void sp_groupmul(uint32_t (&xa)[SmallGeom<L>::NV], co
     }
   }
 }
-template <int L>
+template <int L, bool XLAST = false>
 __device__ __forceinline__ void sp_fwd_cols(uint32_t (&x)[SmallGeom<L>::NV], const SPlantParams<SmallGeom<L>::R> &P,
                                             const SpRegs &G) {
   using Gm = SmallGeom<L>;
@@ -326,7 +339,8 @@ __device__ __forceinline__ void sp_fwd_cols(uint32_t (&x)[SmallGeom<L>::NV], con
 #pragma unroll
     for (int k = 0; k < Gm::NV; k++) {
       if (k & (1 << kb)) continue;
-      sp_ct(x[k], x[k | (1 << kb)], P.ufwd[(1 << s) + (k >> (kb + 1))], G, sp_use_mad(pl_ord(k, kb) + s));
+      sp_ct(x[k], x[k | (1 << kb)], P.ufwd[(1 << s) + (k >> (kb + 1))], G, sp_use_mad(pl_ord(k, kb) + s),
+            XLAST && s == Gm::R - 1);
     }
   }
 }
@@ -340,7 +354,7 @@ __device__ __forceinline__ void sp_fwd_rows(uint32_t (&x)[SmallGeom<L>::NV], con
     for (int r = 0; r < Gm::NV; r++) {
       if (r & (1 << bit)) continue;
       sp_ct(x[r], x[r | (1 << bit)], tw.get(r >> Gm::H, lv, (r & (Gm::T - 1)) >> (bit + 1)), G,
-            sp_use_mad(pl_ord(r, bit) + lv + 1));
+            sp_use_mad(pl_ord(r, bit) + lv + 1), SpDrop<L>::XR_ROWS && lv == Gm::H - SpDrop<L>::V - 1);
     }
   }
 }
@@ -515,8 +529,8 @@ polymul_splant_kernel(const __grid_constant__ SPlantParams<SmallGeom<L>::R> P) {
       if (dyn) rounds_left--;
     }
 
-    sp_fwd_cols<L>(xa, P, G);
-    sp_fwd_cols<L>(xb, P, G);
+    sp_fwd_cols<L, SpDrop<L>::XR_COLS>(xa, P, G);
+    sp_fwd_cols<L, SpDrop<L>::XR_COLS>(xb, P, G);
     if (Gm::H > 0) {
       store_cols<L>(xa, sm_a, l);
       if (Pg::SHARE_XCHG) {                           /* one buffer: a goes through, then b */
@@ -556,7 +570,7 @@ polymul_splant_kernel(const __grid_constant__ SPlantParams<SmallGeom<L>::R> P) {
       /* the registers that only ever took sums (index bits SP_DROP .. H-1 all zero) go back to the
        * centre, so that the second phase starts from the bound of the others */
       constexpr int worst = sp_phase_out(Gm::H, 1, SP_DROP);
-      constexpr int second = sp_phase_out_mixed(Gm::H, 1, SP_DROP);
+      constexpr int second = sp_phase_out_mixed(Gm::H, 1, SP_DROP) > 2 ? sp_phase_out_mixed(Gm::H, 1, SP_DROP) : 2;
       if (worst > second) {
 #pragma unroll
         for (int g = 0; g < (1 << Gm::G); g++)
@@ -568,7 +582,7 @@ polymul_splant_kernel(const __grid_constant__ SPlantParams<SmallGeom<L>::R> P) {
       store_rows<L>(xa, sm_a, l);
       __syncwarp();
       load_cols<L>(xa, sm_a, l);
-      constexpr int b_in = (worst > second) ? (second > 2 ? second : 2) : worst;
+      constexpr int b_in = (worst > second) ? second : worst;
       sp_inv_cols<L, b_in>(xa, P, G);
     } else {
       sp_inv_cols<L, 1>(xa, P, G);

@@ -58,7 +58,10 @@ struct WideGeom {
   static_assert(L == 9 || L == 10, "n = 512 or 1024");
   static constexpr int N = 1 << L;
   static constexpr int HALVES = 1 << (L - 9);
-  static constexpr int NB = L - 6;                  /* stages of layout B (on its upper register bits) */
+  static constexpr int V = SPLANT_INCOMPLETE >= 3 ? 3 : 2;   /* stages left to the group multiplication */
+  static constexpr int D = 1 << V;                  /* registers per group in layout C                  */
+  static constexpr bool XR = (V >= 3);              /* the last stage of layout B reduces its X legs (SpDrop) */
+  static constexpr int NB = L - 4 - V;              /* stages of layout B (on its upper register bits) */
   static constexpr int FIRST = 4 - NB;              /* lowest register bit of layout B that is a stage */
   static constexpr int PADMUL = 2;                  /* word i sits at i + 2 (i >> 5): even words stay even  */
   static constexpr int WK = N + PADMUL * (N >> 5);  /* words per padded polynomial                          */
@@ -77,7 +80,7 @@ struct WideGeom {
 
 /* NB Cooley-Tukey stages on register bits 3 .. 4-NB with the lane's twiddles (levels 0 .. NB-1 of
  * LaneTw1<8>: level m holds table entries (16 << m) + (row << m) + u, u < 2^m) */
-template <int NB>
+template <int NB, bool XLAST>
 __device__ __forceinline__ void wide_fwd_lane(uint32_t (&x)[16], const LaneTw1<8> &tw, const SpRegs &G) {
 #pragma unroll
   for (int lv = 0; lv < NB; lv++) {
@@ -85,7 +88,8 @@ __device__ __forceinline__ void wide_fwd_lane(uint32_t (&x)[16], const LaneTw1<8
 #pragma unroll
     for (int r = 0; r < 16; r++) {
       if (r & (1 << bit)) continue;
-      sp_ct(x[r], x[r | (1 << bit)], tw.get(0, lv, r >> (bit + 1)), G, sp_use_mad(pl_ord(r, bit) + lv + 1));
+      sp_ct(x[r], x[r | (1 << bit)], tw.get(0, lv, r >> (bit + 1)), G, sp_use_mad(pl_ord(r, bit) + lv + 1),
+            XLAST && lv == NB - 1);
     }
   }
 }
@@ -103,27 +107,29 @@ __device__ __forceinline__ void wide_inv_lane(uint32_t (&x)[16], const LaneTw1<8
     }
   }
 }
-/* group multiplication of layout C: four groups of four registers, Z of group g in z[g] */
-__device__ __forceinline__ void wide_groupmul(uint32_t (&xa)[16], const uint32_t (&xb)[16], const int (&z)[4],
+/* group multiplication of layout C: 16 / D groups of D registers, Z of group g in z[g]; XR: the operands
+ * arrive reduced (SpDrop), else a takes its Barrett step here */
+template <int D, bool XR>
+__device__ __forceinline__ void wide_groupmul(uint32_t (&xa)[16], const uint32_t (&xb)[16], const int (&z)[16 / D],
                                               const SpRegs &G) {
 #pragma unroll
-  for (int r = 0; r < 16; r += 4) {
-    uint32_t a[4], lo[4], hi[4];
+  for (int r = 0; r < 16; r += D) {
+    uint32_t a[D], lo[D], hi[D];
 #pragma unroll
-    for (int i = 0; i < 4; i++) a[i] = (uint32_t)sp_red((int)xa[r + i], G);
+    for (int i = 0; i < D; i++) a[i] = XR ? xa[r + i] : (uint32_t)sp_red((int)xa[r + i], G);
 #pragma unroll
-    for (int k = 0; k < 4; k++) { lo[k] = 0; hi[k] = 0; }
+    for (int k = 0; k < D; k++) { lo[k] = 0; hi[k] = 0; }
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < D; i++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        if (i + j < 4) lo[i + j] += a[i] * xb[r + j];
-        else hi[i + j - 4] += a[i] * xb[r + j];
+      for (int j = 0; j < D; j++) {
+        if (i + j < D) lo[i + j] += a[i] * xb[r + j];
+        else hi[i + j - D] += a[i] * xb[r + j];
       }
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < D; k++) {
       uint32_t c = lo[k];
-      if (k < 3) c += (uint32_t)sp_redc((int)hi[k], G) * (uint32_t)z[r >> 2];
+      if (k < D - 1) c += (uint32_t)sp_redc((int)hi[k], G) * (uint32_t)z[r / D];
       xa[r + k] = (uint32_t)sp_redc((int)c, G);
     }
   }
@@ -220,8 +226,8 @@ polymul_splant_wide_kernel(const __grid_constant__ SPlantParams<4> P) {
           x0[k] = v.x;
           x1[k] = v.y;
         }
-        wide_fwd_lane<W::NB>(x0, twf, G);
-        wide_fwd_lane<W::NB>(x1, twf, G);
+        wide_fwd_lane<W::NB, W::XR>(x0, twf, G);
+        wide_fwd_lane<W::NB, W::XR>(x1, twf, G);
 #pragma unroll
         for (int k = 0; k < 16; k++) *reinterpret_cast<uint2 *>(wk + base + W::b_off(k)) = make_uint2(x0[k], x1[k]);
       } else {                                             /* layout B: the next NB stages */
@@ -229,7 +235,7 @@ polymul_splant_wide_kernel(const __grid_constant__ SPlantParams<4> P) {
         const int base = W::b_base(hi4, b0);
 #pragma unroll
         for (int k = 0; k < 16; k++) x[k] = wk[base + W::b_off(k)];
-        wide_fwd_lane<W::NB>(x, twf, G);
+        wide_fwd_lane<W::NB, W::XR>(x, twf, G);
 #pragma unroll
         for (int k = 0; k < 16; k++) wk[base + W::b_off(k)] = x[k];
       }
@@ -256,9 +262,15 @@ polymul_splant_wide_kernel(const __grid_constant__ SPlantParams<4> P) {
         xa[k] = va.x; xa[k + 1] = va.y;
         xb[k] = vb.x; xb[k + 1] = vb.y;
       }
-      const uint4 zv = __ldg(reinterpret_cast<const uint4 *>(P.zeta) + v);
-      const int z[4] = {(int)zv.x, (int)zv.y, (int)zv.z, (int)zv.w};
-      wide_groupmul(xa, xb, z, G);
+      int z[16 / W::D];
+      if (W::D == 4) {
+        const uint4 zv = __ldg(reinterpret_cast<const uint4 *>(P.zeta) + v);
+        z[0] = (int)zv.x; z[1] = (int)zv.y; z[16 / W::D - 2] = (int)zv.z; z[16 / W::D - 1] = (int)zv.w;
+      } else {
+        const uint2 zv = __ldg(reinterpret_cast<const uint2 *>(P.zeta) + v);
+        z[0] = (int)zv.x; z[16 / W::D - 1] = (int)zv.y;
+      }
+      wide_groupmul<W::D, W::XR>(xa, xb, z, G);
 #pragma unroll
       for (int k = 0; k < 16; k += 2) *reinterpret_cast<uint2 *>(wk_a + base + k) = make_uint2(xa[k], xa[k + 1]);
     }

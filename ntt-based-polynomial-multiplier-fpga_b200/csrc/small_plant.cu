@@ -171,7 +171,10 @@ int run_splant(const nttb200_plan *P, void *c, const void *a, const void *b, siz
   if (8ull * q * q > mmax) return nttb200_fail(NTTB200_EPARAM, "q=%u is too large for the signed Plantard kernel", q);
   /* the group multiplication reduces sums of 2^V raw products a b with |a| <= q/2 + 20 (Barrett step),
    * |b| <= (L + 2 - V) q / 2 (forward values after L - V stages), plus one product of two centred values */
-  if (V > 0 && (uint64_t)(1 << V) * (q / 2 + 21) * ((uint64_t)(L + 2 - V) * q / 2 + 1) + (uint64_t)q * q / 4 > mmax)
+  /* (three stages left out: both operands come out of the last forward stage within q + 20 of zero) */
+  const uint64_t gsum = SpDrop<L>::XR ? (uint64_t)(1 << V) * (q + 21) * (q + 21)
+                                      : (uint64_t)(1 << V) * (q / 2 + 21) * ((uint64_t)(L + 2 - V) * q / 2 + 1);
+  if (V > 0 && gsum + (uint64_t)q * q / 4 > mmax)
     return nttb200_fail(NTTB200_EPARAM, "q=%u is too large for the signed Plantard kernel at n=%u", q, Gm::N);
   p.dd = (uint32_t)((mmax + 65535ull * q + 65535ull) / 65536ull);
   p.cbar = (uint32_t)(((1ull << SP_RED_SHIFT) + q / 2) / q);
@@ -250,8 +253,8 @@ int plant_n1024() {
 }
 template <int L, typename IO = uint32_t, typename OIO = IO>
 int run_splant_wide(const nttb200_plan *P, void *c, const void *a, const void *b, size_t batch, cudaStream_t st) {
-  constexpr int N = 1 << L, V = 2;
   using W = WideGeom<L>;
+  constexpr int N = 1 << L, V = W::V;
   constexpr int WARPS = SPLANT_N1024_WARPS;
   const bool cyclic = (P->flags & NTTB200_PLAN_CYCLIC) != 0;
   const DevTable &fwd = cyclic ? P->fwd_plain : P->fwd_mixed;
@@ -263,7 +266,8 @@ int run_splant_wide(const nttb200_plan *P, void *c, const void *a, const void *b
   p.q = q; p.qinv = P->m.qinv;
   const uint64_t mmax = ((1ull << 32) - 65536ull * (q + 4)) / 2;       /* as run_splant */
   if (8ull * q * q > mmax ||
-      (uint64_t)(1 << V) * (q / 2 + 21) * ((uint64_t)(L + 2 - V) * q / 2 + 1) + (uint64_t)q * q / 4 > mmax)
+      (V >= 3 ? (uint64_t)(1 << V) * (q + 21) * (q + 21)
+              : (uint64_t)(1 << V) * (q / 2 + 21) * ((uint64_t)(L + 2 - V) * q / 2 + 1)) + (uint64_t)q * q / 4 > mmax)
     return nttb200_fail(NTTB200_EPARAM, "q=%u is too large for the signed Plantard kernel at n=%d", q, N);
   p.dd = (uint32_t)((mmax + 65535ull * q + 65535ull) / 65536ull);
   p.cbar = (uint32_t)(((1ull << SP_RED_SHIFT) + q / 2) / q);
