@@ -323,7 +323,7 @@ def slots_per_polymul(n: int, plantard: bool, signed: bool = False) -> int:
     pointwise 4, scale 3; at n <= 256 butterfly and scale 2 (IMAD, SHF, IMAD, SHF).  Signed Plantard
     kernels (ntt_small_splant.cuh, ntt_splant_wide.cuh: the default): L - 3 stages per transform with 2
     multiplications per butterfly, 4 in the butterflies of the last inverse stage, and per group of eight
-    coefficients 8 Barrett steps (2 each), 64 + 7 raw products and 15 reductions (2 each): n (3 L + 7.125)."""
+    coefficients 8 Barrett steps (2 each), 64 + 7 raw products and 15 reductions (2 each): n (3 L + 6.625)."""
     bflies = 3 * (n // 2) * (n.bit_length() - 1)
     L = n.bit_length() - 1
     if plantard and signed:
