@@ -1,6 +1,6 @@
 /*
  * ntt_splant_wide.cuh -- fused product kernel for n = 1024 (and n = 512), half-word moduli: the arithmetic of
- * ntt_small_splant.cuh (signed Plantard, five-instruction butterflies, two stages left to a group
+ * ntt_small_splant.cuh (signed Plantard, five-instruction butterflies, three stages left to a group
  * multiplication) in a geometry whose code FITS THE INSTRUCTION CACHE.
  *
  * Why: one warp per polynomial with 32 coefficients per lane (polymul_splant_kernel<10>) unrolls to
@@ -16,8 +16,8 @@
  * index bits in registers per layout it takes three layouts of the 10 index bits i9 .. i0:
  *
  *      layout A   registers i9 i8 i7 i6   half i5          lane i4 .. i0        stages on bits 9 .. 6
- *      layout B   registers i5 i4 i3 i2   half i0          lane i9 .. i6, i1    stages on bits 5 .. 2
- *      layout C   registers i3 i2 i1 i0   half i9          lane i8 .. i4        group multiplication
+ *      layout B   registers i5 i4 i3 i2   half i0          lane i9 .. i6, i1    stages on bits 5 .. 3 (i2 rides along)
+ *      layout C   registers i3 i2 i1 i0   half i9          lane i8 .. i4        two groups of eight: multiplication
  *
  * (forward A -> B -> C, inverse C -> B -> A; dataflow of R/NTT/ntt.C:342-371 and 428-451 as in
  * ntt_small_splant.cuh).  The polynomial lives in the warp's shared memory between the phases, every
@@ -33,17 +33,18 @@
  * 15), those of layout B depend on i9 .. i6 only, i.e. on the lane and not on the half: 15 + 15 words per
  * lane held in registers for the whole kernel; the four Z of layout C are one 16-byte load per half.
  *
- * Price: three more trips through shared memory per coefficient: 3 194 instead of 3 087 warp instructions
- * per polynomial (3 382 with 32-bit accesses everywhere).  The loop is 1 727 instructions = 28 KB, 95
- * registers.  Measured on B200 (profiles/r2_c4_splant_wide_v2_ncu_full.txt): `no_instruction` drops from 1.45
- * to 0.10 warps per issue cycle, issue slots 69.5 % -> 83.1 % busy (3.32 instructions per clock and SM, what
- * the n = 256 kernel reaches), c4 279.5 -> 302 M polymul/s.
+ * Price: three more trips through shared memory per coefficient.  With two stages left out (the form the
+ * captures were taken with): 3 194 instead of 3 087 warp instructions per polynomial (3 382 with 32-bit
+ * accesses everywhere), loop 1 727 instructions = 28 KB, 95 registers; measured on B200
+ * (profiles/r2_c4_splant_wide_v2_ncu_full.txt): `no_instruction` drops from 1.45 to 0.10 warps per issue cycle,
+ * issue slots 69.5 % -> 83.1 % busy (3.32 instructions per clock and SM, what the n = 256 kernel reaches), c4
+ * 279.5 -> 302 M polymul/s.  With three stages left out: loop 1 632 instructions, c4 305 - 307 M.
  *
  * n = 512 can run the same kernel (NTTB200_PLANT_N1024=2; measured level with the one-layout-per-phase
  * kernel there, 655 against 659 M polymul/s, so that one stays the default) with 32 virtual lanes (no halves) and three stages in layout B:
  *      layout A   registers i8 i7 i6 i5   lane i4 .. i0          stages on bits 8 .. 5
- *      layout B   registers i4 i3 i2 i1   lane i8 .. i5, i0      stages on bits 4 .. 2 (i1 rides along)
- *      layout C   registers i3 i2 i1 i0   lane i8 .. i4          group multiplication
+ *      layout B   registers i4 i3 i2 i1   lane i8 .. i5, i0      stages on bits 4, 3 (i2, i1 ride along)
+ *      layout C   registers i3 i2 i1 i0   lane i8 .. i4          two groups of eight: multiplication
  * (32-bit accesses in B: its register pairs are not adjacent words).
  */
 #pragma once
