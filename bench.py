@@ -54,10 +54,10 @@ WORKLOADS = {
 }
 # DRAM bytes (read + write) per launch of the dominant kernel, from `ncu --set full` captures
 # committed under profiles/ (a profiler run is never a bench value; this is the traffic only)
-TRAFFIC_NCU = {"c2": 134262784 + 38077184, "c4": 2147558000 + 1041997000}
+TRAFFIC_NCU = {"c2": 134266624 + 37117952, "c4": 2147526000 + 1041490000}
 TRAFFIC_SRC = {"c2": "profiles/r2_c2_splant_final_ncu_full.txt: dram__bytes_read.sum 134.26 MB + "
-                     "dram__bytes_write.sum 38.08 MB per launch (algorithmic 201.3 MB; part of c stays dirty in L2)",
-               "c4": "profiles/r2_c4_splant_wide_v2_ncu_full.txt: 2.148 GB read + 1.042 GB written per launch (algorithmic 3.221 GB)"}
+                     "dram__bytes_write.sum 37.12 MB per launch (algorithmic 201.3 MB; part of c stays dirty in L2)",
+               "c4": "profiles/r2_c4_splant_wide_final_ncu_full.txt: 2.148 GB read + 1.041 GB written per launch (algorithmic 3.221 GB)"}
 SEED = 0x4E545442323030
 L2_BYTES = 126 * 1000 * 1000
 
