@@ -87,12 +87,14 @@ __device__ __forceinline__ int sp_red(int x, const SpRegs &G) {
  * two cycles, so the ALU pipe then binds at 6 cycles per warp butterfly.  Written as mad.lo (X, 2, -X')
  * ptxas picks IMAD or LEA per instance and levels the two pipes (SASS of microbench 18: 1 287 IMAD
  * against 1 274 ALU instructions): 5 cycles.  SPLANT_MAD_NUM of every SPLANT_MAD_DEN butterflies use
- * the mad form. */
+ * the mad form.  In the kernel the group multiplication is three quarters IMAD, so the butterflies give the
+ * multiplier pipe some room: every other butterfly in the mad form measured best (c2: all 1 540, one in two
+ * 1 556, one in four 1 548 M polymul/s; c3 1 546 / 1 560 / 1 540; c4 level). */
 #ifndef SPLANT_MAD_NUM
 #define SPLANT_MAD_NUM 1
 #endif
 #ifndef SPLANT_MAD_DEN
-#define SPLANT_MAD_DEN 1
+#define SPLANT_MAD_DEN 2
 #endif
 __host__ __device__ constexpr bool sp_use_mad(int i) {
   return SPLANT_MAD_NUM > 0 && (i % SPLANT_MAD_DEN) < SPLANT_MAD_NUM;
