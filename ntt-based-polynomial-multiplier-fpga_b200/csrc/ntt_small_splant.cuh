@@ -307,7 +307,7 @@ __device__ __forceinline__ void sp_groupmul(uint32_t (&xa)[SmallGeom<L>::NV], co
                                             const LaneZeta<L> &zt, const SpRegs &G) {
   using Gm = SmallGeom<L>;
   constexpr int V = SpDrop<L>::V, D = SpDrop<L>::D;
-  static_assert(Gm::H >= 1 && V >= 1, "groups live in the lane-phase layout");
+  static_assert(Gm::H >= 1, "groups live in the lane-phase layout");
 #pragma unroll
   for (int r = 0; r < Gm::NV; r += D) {
     uint32_t a[D], lo[D], hi[D];
